@@ -1,0 +1,62 @@
+"""ctypes binding of libmelogan_b200.so (the C ABI declared in include/melogan_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+caller gets an exception -- nothing on the product path is computed on the CPU.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmelogan_b200.so")
+
+MG_OK, MG_ERR_INVALID, MG_ERR_CUDA, MG_ERR_NONFINITE, MG_ERR_STATE = 0, -1, -2, -3, -4
+
+
+class MeloGanNativeError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"melogan_b200 native call failed (status {status}): {text}")
+        self.status = status
+
+
+_lib = None
+_vp, _ll, _i, _d, _f, _u32 = (ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_double, ctypes.c_float,
+                              ctypes.c_uint32)
+
+_SIGNATURES = {
+    "mg_last_error": ([], ctypes.c_char_p),
+    "mg_abi_version": ([], _i),
+    "mg_build_info": ([], ctypes.c_char_p),
+    "mg_scale_mask": ([ctypes.c_char_p, _i], _u32),
+    "mg_extract_notes_gan": ([_vp, _ll, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_extract_notes_gan_host": ([_vp, _ll, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_extract_notes_abs": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_extract_notes_abs_host": ([_vp, _ll, _i, _vp, _vp, _vp, _vp], _i),
+    "mg_adam_step": ([_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _i, _f, _ll, _vp, _vp, _vp], _i),
+}
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MeloGanNativeError(MG_ERR_STATE, f"{LIB_PATH} not built; run `make -C melo-gan_b200/csrc`")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = argtypes, restype
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(status):
+    if status != MG_OK:
+        raise MeloGanNativeError(status, lib().mg_last_error().decode())
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))
