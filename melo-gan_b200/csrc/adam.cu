@@ -33,9 +33,10 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
                                          float beta2, float one_minus_b2, float eps, float decay_mul,
                                          const AdamScalars s) {
     p = p * decay_mul;  // AdamW: p.mul_(1 - lr*wd); multiplies by exactly 1.0f otherwise
-    // torch lerp: weight < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
-    const float diff = g - m;
-    m = (w_lerp < 0.5f) ? __fadd_rn(m, __fmul_rn(w_lerp, diff)) : __fsub_rn(g, __fmul_rn(diff, one_minus_w));
+    // torch lerp (ATen Lerp.h, vectorised form): fma(coeff, end - start, base) with
+    // (coeff, base) = weight < 0.5 ? (w, start) : (w - 1, end)
+    const float diff = __fsub_rn(g, m);
+    m = (w_lerp < 0.5f) ? __fmaf_rn(w_lerp, diff, m) : __fmaf_rn(-one_minus_w, diff, g);
     v = __fadd_rn(__fmul_rn(v, beta2), __fmul_rn(__fmul_rn(one_minus_b2, g), g));
     const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), eps);
     p = __fadd_rn(p, __fdiv_rn(__fmul_rn(s.neg_step_size, m), denom));

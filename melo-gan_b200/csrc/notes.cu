@@ -223,6 +223,11 @@ extern "C" int mg_extract_notes_gan(const float* rolls, long long nrolls, int nr
     MG_REQUIRE(nrolls >= 0 && nrows >= 0 && nrows <= kMaxRows, "extract_notes_gan: nrows must be in [0,%d]", kMaxRows);
     MG_REQUIRE((allowed_mask & 0xFFFu) != 0, "extract_notes_gan: empty scale mask");
     if (nrolls == 0) return MG_OK;
+    if (nrows == 0) {  // empty rolls: zero notes each
+        MG_REQUIRE(counts, "extract_notes_gan: null pointer");
+        MG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * nrolls, mg::as_stream(stream)));
+        return MG_OK;
+    }
     MG_REQUIRE(rolls && counts && pitch && velocity && start && end, "extract_notes_gan: null pointer");
     int rc = init_once();
     if (rc != MG_OK) return rc;

@@ -33,9 +33,11 @@ def _run(n, steps, kind, lr, betas, wd):
         upd_ref = (ref_p.data - before).double()
         upd = (ours_p.data.cpu() - before).double()
         scale = upd_ref.abs().max().item()
-        assert (upd - upd_ref).abs().max().item() <= 2e-6 * scale + 1e-12, (t, kind)
+        # p itself is rounded to float32 after the update: allow one ulp of |p| on top of the update error
+        tol = 2e-6 * scale + 1.2e-7 * before.abs().double() + 1e-12
+        assert bool(((upd - upd_ref).abs() <= tol).all()), (t, kind)
         st = ref.state[ref_p]
-        assert torch.allclose(ours.exp_avg[:n].cpu(), st["exp_avg"], rtol=1e-6, atol=1e-12)
+        assert torch.allclose(ours.exp_avg[:n].cpu(), st["exp_avg"], rtol=1e-6, atol=1e-10)
         assert torch.allclose(ours.exp_avg_sq[:n].cpu(), st["exp_avg_sq"], rtol=1e-6, atol=1e-16)
         assert int(ours.step_dev.item()) == t + 1
 
