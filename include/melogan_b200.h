@@ -92,6 +92,124 @@ int mg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  double lr, double beta1, double beta2, double eps, double weight_decay, int decoupled,
                  float grad_scale, long long step, long long* step_dev, uint16_t* bf16_copy, void* stream);
 
+
+/* ==========================================================================================
+ * GAN training hot path (SURVEY.md 8a rows A-1 .. A-9).
+ *
+ * One opaque context owns every workspace (activations saved for backward, scratch) for a fixed
+ * per-rank batch size; parameters, gradients and optimizer state stay in caller-owned device
+ * memory (the host side keeps them as views of flat torch buffers) and are bound by pointer.
+ * All tensors at this boundary are float32, contiguous, channels-last exactly as the reference
+ * modules exchange them: notes (B, max_notes, note_dim), embeddings (B, embed_dim), ...
+ * `precision` selects the arithmetic of the big contractions: 0 = fp32 on CUDA cores (parity
+ * mode, 1e-5), 1 = bf16 operands on tcgen05 tensor cores with fp32 TMEM accumulation (1e-2).
+ * ========================================================================================== */
+typedef struct mg_gan mg_gan;
+
+typedef struct mg_gan_config {
+    int batch;          /* B: samples per step on this rank                                  */
+    int precision;      /* 0 = fp32, 1 = bf16 tensor cores                                   */
+    int max_notes;      /* gan_config.yaml MAX_NOTES (multiple of 8)                         */
+    int note_dim;       /* NOTE_DIM (must be 4)                                              */
+    int noise_dim;      /* NOISE_DIM                                                         */
+    int latent_dim;     /* LATENT_DIM                                                        */
+    int gen_hidden;     /* NoiseToLatent hidden width (512: train_gan.py:95-102 default)     */
+    int numeric_dim;    /* NUMERIC_INPUT_DIM                                                 */
+    int enc_hidden1;    /* ENCODER_HIDDEN[0]                                                 */
+    int enc_hidden2;    /* ENCODER_HIDDEN[1]                                                 */
+    int embed_dim;      /* ENCODER_OUT_DIM                                                   */
+    int n_classes;      /* emotion classes (4)                                               */
+    double enc_dropout; /* FeatureEncoder dropout p (0.2: constructor default)               */
+    double lambda_gp;   /* LAMBDA_GP                                                         */
+    double lambda_emotion; /* LAMBDA_EMOTION                                                 */
+    double bn_momentum; /* 0.1                                                               */
+    double bn_eps;      /* 1e-5                                                              */
+} mg_gan_config;
+
+enum { MG_MOD_ENCODER = 0, MG_MOD_GENERATOR = 1, MG_MOD_CRITIC = 2, MG_MOD_EMOTION = 3 };
+
+int mg_gan_create(const mg_gan_config* cfg, mg_gan** out);
+void mg_gan_destroy(mg_gan* ctx);
+long long mg_gan_workspace_bytes(const mg_gan* ctx);
+
+/* Bind parameter (and optionally gradient) pointers of one module, in the reference's
+ * state_dict order (buffers last):
+ *   ENCODER   (8):  net.0.{weight,bias} net.1.{w,b} net.4.{w,b} net.7.{w,b}       feature_encoder.py:17-41
+ *   GENERATOR (22): noise_to_latent.net.{0,2}.{w,b} decoder.pre.{0,2}.{w,b} decoder.deconv.0.{w,b}
+ *                   deconv.1.{w,b} deconv.3.{w,b} deconv.4.{w,b} deconv.6.{w,b}   then the buffers
+ *                   deconv.1.running_{mean,var} deconv.4.running_{mean,var}       models.py:20-64
+ *   CRITIC    (10): conv.{0,2,4}.{w,b} fc.1.{w,b} real_fake.{w,b}                 models.py:140-156
+ *   EMOTION   (32): for i in 0..3: encoder.conv.i.net.0.{w,b} net.1.{w,b,running_mean,running_var};
+ *                   encoder.project.{w,b} classifier.net.{0,3}.{w,b} classifier.head.{w,b}
+ * grads has the same order and length as the trainable prefix (8 / 18 / 10); NULL = no gradients. */
+int mg_gan_bind(mg_gan* ctx, int module, void* const* params, int nparams, void* const* grads, int ngrads);
+/* The frozen emotion discriminator's BatchNorm is folded once per bind; call again after loading new weights. */
+
+/* A-1  FeatureEncoder.forward / backward          src/gan/feature_encoder.py:43-45
+ * mask1 (B, enc_hidden1), mask2 (B, enc_hidden2): dropout keep-masks (1/0) when train != 0 (NULL with
+ * train == 0 = eval).  backward adds the parameter gradients of d(emb) into the bound grad buffers. */
+int mg_feature_encoder_forward(mg_gan* ctx, const float* numeric, const float* mask1, const float* mask2,
+                               int train, float* emb_out, void* stream);
+int mg_feature_encoder_backward(mg_gan* ctx, const float* demb, void* stream);
+
+/* A-2..A-4  Generator.forward (warm_start: cat[noise, emb])   src/gan/models.py:108-130
+ * train != 0: BatchNorm uses batch statistics and updates the bound running stats (momentum);
+ * train == 0: running statistics.  notes_out (B, max_notes, 4), latent_out (B, latent_dim) may be NULL.
+ * backward: dnotes (B, max_notes, 4) [+ dlatent] -> G parameter gradients (added) and demb_out (B, embed_dim). */
+int mg_generator_forward(mg_gan* ctx, const float* noise, const float* emb, int train, float* notes_out,
+                         float* latent_out, void* stream);
+int mg_generator_backward(mg_gan* ctx, const float* dnotes, const float* dlatent, float* demb_out, void* stream);
+
+/* A-5  Discriminator.forward (WGAN critic)         src/gan/models.py:158-169
+ * nsamples <= 3*batch; emb row of sample r is emb[r % batch] (NULL: no conditioning term).
+ * backward: dscore (nsamples) -> optional parameter gradients (added), dnotes_out, demb_out (may be NULL). */
+int mg_discriminator_forward(mg_gan* ctx, const float* notes, const float* emb, int nsamples, float* score_out,
+                             void* stream);
+int mg_discriminator_backward(mg_gan* ctx, const float* dscore, int param_grads, float* dnotes_out,
+                              float* demb_out, void* stream);
+/* Same plus the critic's parameter gradients (added into the bound grads); `notes` is the tensor the
+ * preceding mg_discriminator_forward read (conv.0's weight gradient needs it). */
+int mg_discriminator_backward_ex(mg_gan* ctx, const float* notes, const float* dscore, float* dnotes_out,
+                                 float* demb_out, void* stream);
+
+/* A-6 + A-7  critic loss, forward and backward in one call:
+ *   loss_d = mean(D(fake)) - mean(D(real)) + lambda_gp * GP(real, fake, alpha)
+ * (src/gan/train_gan.py:191-203 and compute_gradient_penalty src/gan/utils.py:75-90, including the
+ * double backward through the critic).  alpha (B) is the per-sample interpolation weight.
+ * Adds d(loss_d)/d(theta_D) into the bound critic grads; metrics_out (4 floats, device):
+ * [loss_d, gp, mean D(real), mean D(fake)]. */
+int mg_critic_loss_backward(mg_gan* ctx, const float* real, const float* fake, const float* emb,
+                            const float* alpha, float* metrics_out, void* stream);
+
+/* A-8  EmotionDiscriminator.forward in eval mode + input gradient (frozen weights)
+ *      src/emotion_discriminator/ed_model.py:147-165 */
+int mg_emotion_forward(mg_gan* ctx, const float* notes, float* logits_out, void* stream);
+int mg_emotion_backward_input(mg_gan* ctx, const float* dlogits, float* dnotes_out, int accumulate, void* stream);
+
+/* A-7 composite: the whole critic step body up to (not including) opt_D.step()
+ *      src/gan/train_gan.py:185-203: E_num and G forward without grad (dropout on, BN batch stats,
+ *      running stats updated), then mg_critic_loss_backward.  Caller zeroes the critic grads first. */
+int mg_critic_step(mg_gan* ctx, const float* real, const float* numeric, const float* noise, const float* alpha,
+                   const float* mask1, const float* mask2, float* metrics_out, void* stream);
+
+/* A-9 composite: generator step body up to opt_G.step()   src/gan/train_gan.py:215-247
+ *      loss_g = -mean(D(G(z))) + lambda_emotion * CE(ED(G(z)), labels); adds gradients of G and E_num.
+ *      The critic's own (discarded) weight gradients of this backward are not computed.
+ *      labels (B) int64; metrics_out (2 floats): [loss_g_adv, loss_g_emo]. */
+int mg_generator_step(mg_gan* ctx, const float* numeric, const float* noise, const long long* labels,
+                      const float* mask1, const float* mask2, float* metrics_out, void* stream);
+
+/* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
+int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
+
+/* Test/diagnostic access to a named internal workspace buffer (see DESIGN.md for the names). */
+int mg_gan_buffer(mg_gan* ctx, const char* name, void** ptr, long long* nbytes);
+
+/* Counter-based RNG fill used by the throughput path (noise ~ N(0,1), alpha ~ U[0,1), keep-masks):
+ * kind 0 = normal, 1 = uniform [0,1), 2 = Bernoulli(p) as 0/1 floats. */
+int mg_rng_fill(float* out, long long n, int kind, float p, unsigned long long seed, unsigned long long offset,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,439 @@
+// elem.cuh -- HBM-bound elementwise / reduction kernels of the GAN step (sm_100a).
+// Activation tensors are channels-last [rows, C] with C contiguous; T is float (fp32 parity mode) or
+// __nv_bfloat16 (bf16 mode).  Reductions over rows write per-CTA partials and a second tiny kernel
+// finishes them in a fixed order (deterministic, no float atomics) unless noted.
+#pragma once
+#include "gemm_simt.cuh"
+
+namespace mg {
+
+// ---------------------------------------------------------------------------------------------
+// column reductions over rows:  out[k][c] = sum_{r in [r0,r1)} f_k(row r, col c)
+// one CTA = 32 (cols) x 8 (row lanes) threads striding over a row chunk; partials [nchunk][K][C]
+// ---------------------------------------------------------------------------------------------
+enum ColOp {
+    COL_SUM = 0,        // f0 = x
+    COL_SUM_SQ = 1,     // f0 = x, f1 = x*x                      (BatchNorm batch statistics)
+    COL_BN_BWD = 2,     // f0 = dy, f1 = dy * xhat                (xhat from x, mean, invstd)
+    COL_WSUM = 3        // f0 = w[r] * x                          (row-weighted sum)
+};
+
+struct ColReduceArgs {
+    const void* x; int ldx;            // x[r*ldx + c]
+    const void* y; int ldy;            // second operand (COL_BN_BWD: dy; x is the pre-BN activation)
+    const float* mean; const float* invstd;
+    const float* roww;                 // COL_WSUM: weight of row r is roww[r / roww_div]
+    int roww_div;
+    long long r0, r1; int C;
+    float* partial;                    // [nchunk][nout][C]
+    int rows_per_chunk;
+};
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
+    constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
+    __shared__ float red[NOUT][8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    const long long rb = P.r0 + (long long)blockIdx.y * P.rows_per_chunk;
+    long long re = rb + P.rows_per_chunk;
+    if (re > P.r1) re = P.r1;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < P.C) {
+        const T* x = static_cast<const T*>(P.x);
+        const T* y = static_cast<const T*>(P.y);
+        float mu = 0.f, is = 0.f;
+        if (OP == COL_BN_BWD) { mu = P.mean[c]; is = P.invstd[c]; }
+        for (long long r = rb + ry; r < re; r += 8) {
+            const float xv = ld_as_float(x + r * P.ldx + c);
+            if (OP == COL_SUM) a0 += xv;
+            else if (OP == COL_SUM_SQ) { a0 += xv; a1 = fmaf(xv, xv, a1); }
+            else if (OP == COL_BN_BWD) {
+                const float dy = ld_as_float(y + r * P.ldy + c);
+                a0 += dy; a1 = fmaf(dy, (xv - mu) * is, a1);
+            } else a0 = fmaf(P.roww[r / P.roww_div], xv, a0);
+        }
+    }
+    red[0][ry][cx] = a0;
+    if (NOUT == 2) red[1][ry][cx] = a1;
+    __syncthreads();
+    if (ry == 0 && c < P.C) {
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += red[k][j][cx];
+            P.partial[((long long)blockIdx.y * NOUT + k) * P.C + c] = s;
+        }
+    }
+}
+
+// out[k*out_kstride + perm(c)] (+)= alpha * sum_chunks partial[chunk][k][c]   (float64 accumulation)
+__global__ void colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout, int C, float* out,
+                                        int out_kstride, int perm_q, int perm_p, float alpha, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nout * C) return;
+    const int k = i / C, c = i - k * C;
+    double s = 0.0;
+    for (int j = 0; j < nchunk; ++j) s += (double)partial[((long long)j * nout + k) * C + c];
+    float* o = out + (long long)k * out_kstride + perm_index(c, perm_q, perm_p);
+    const float v = (float)(s * (double)alpha);
+    *o = accumulate ? *o + v : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm1d (training) helpers for G's two BN layers        reference models.py:57,60
+// ---------------------------------------------------------------------------------------------
+// stats[0][c] = sum x, stats[1][c] = sum x^2 over R rows -> mean, invstd (biased var), running update
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, long long R, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
+                                   float* running_var, int update_running) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double n = (double)R;
+    const double mu = (double)stats[c] / n;
+    double var = (double)stats[C + c] / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (update_running) {
+        const double unbiased = R > 1 ? var * n / (n - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
+}
+
+// y = relu((x - mean) * invstd * gamma + beta)      (eval mode: mean/invstd come from running stats)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4,
+                                                            int C, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = (int)((i * 4) % C);
+        float v[4];
+        ld4(x + i * 4, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float sc = invstd[c + e] * gamma[c + e];
+            v[e] = fmaxf(fmaf(v[e] - mean[c + e], sc, beta[c + e]), 0.0f);
+        }
+        st4(y + i * 4, v);
+    }
+}
+
+// dx = gamma*invstd*(dy - s1/R - xhat*s2/R), sums = [s1 | s2] (dy already carries the ReLU mask)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                           T* __restrict__ dx, long long n4, int C, float invR,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ sums) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = (int)((i * 4) % C);
+        float xv[4], dv[4], o[4];
+        ld4(x + i * 4, xv);
+        ld4(dy + i * 4, dv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float xh = (xv[e] - mean[c + e]) * invstd[c + e];
+            o[e] = gamma[c + e] * invstd[c + e] * (dv[e] - sums[c + e] * invR - xh * sums[C + c + e] * invR);
+        }
+        st4(dx + i * 4, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling and broadcast
+// ---------------------------------------------------------------------------------------------
+// out[s, c] = scale * sum_l x[s, l, c]        (AdaptiveAvgPool1d(1): scale = 1/L)
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) pool_rows_kernel(const T* __restrict__ x, TO* __restrict__ out, int S, int L,
+                                                        int C, float scale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (c >= C || s >= S) return;
+    const T* p = x + ((long long)s * L) * C + c;
+    float a = 0.f;
+    for (int l = 0; l < L; ++l) a += ld_as_float(p + (long long)l * C);
+    st_from_float(out + (long long)s * C + c, a * scale);
+}
+
+// out[s, l, c] = src[s, c] * scale * colscale[c] * f'(ref[s, l, c])
+//   mode MUL_LRELU_SIGN / MUL_RELU_SIGN: derivative from the sign of the saved activation; MUL_VALUE: ref holds f'
+template <typename TS, typename T>
+__global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __restrict__ src, const T* __restrict__ ref,
+                                                             T* __restrict__ out, long long n4, int L, int C,
+                                                             float scale, const float* __restrict__ colscale,
+                                                             int mode) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long LC = (long long)L * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const long long e0 = i * 4;
+        const long long s = e0 / LC;
+        const int c = (int)(e0 % C);
+        float r[4], o[4];
+        ld4(ref + e0, r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float d = (mode == MUL_LRELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.2f)
+                      : (mode == MUL_RELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.f) : r[e];
+            const float cs = colscale ? colscale[c + e] : 1.0f;
+            o[e] = ld_as_float(src + s * C + c + e) * scale * cs * d;
+        }
+        st4(out + e0, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FeatureEncoder pieces (tiny tensors, float only)          reference feature_encoder.py:17-41
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over D (<= 32) features per row; writes y and xhat
+__global__ void layernorm_small_kernel(const float* __restrict__ x, int B, int D, const float* __restrict__ w,
+                                       const float* __restrict__ b, float eps, float* __restrict__ y,
+                                       float* __restrict__ xhat) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    float mu = 0.f;
+    for (int j = 0; j < D; ++j) mu += x[r * D + j];
+    mu /= (float)D;
+    float var = 0.f;
+    for (int j = 0; j < D; ++j) { const float d = x[r * D + j] - mu; var = fmaf(d, d, var); }
+    var /= (float)D;
+    const float is = rsqrtf(var + eps);
+    for (int j = 0; j < D; ++j) {
+        const float xh = (x[r * D + j] - mu) * is;
+        if (xhat) xhat[r * D + j] = xh;
+        y[r * D + j] = fmaf(xh, w[j], b[j]);
+    }
+}
+
+// h = gelu(z) * mask * scale   (mask == nullptr: eval mode, no dropout)
+__global__ void gelu_dropout_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mask, float scale,
+                                        float* __restrict__ h, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = gelu_f(z[i]);
+    h[i] = mask ? g * (mask[i] * scale) : g;
+}
+// dz = dh * mask * scale * gelu'(z)
+__global__ void gelu_dropout_bwd_kernel(const float* dh, const float* __restrict__ z,
+                                        const float* __restrict__ mask, float scale, float* dz, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float m = mask ? mask[i] * scale : 1.0f;
+    dz[i] = dh[i] * m * gelu_grad_f(z[i]);
+}
+
+// xcat[b] = [a[b, 0:Da] | c[b, 0:Dc]]
+__global__ void concat2_kernel(const float* __restrict__ a, int Da, const float* __restrict__ c, int Dc,
+                               float* __restrict__ out, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = Da + Dc;
+    if (i >= B * D) return;
+    const int b = i / D, j = i - b * D;
+    out[i] = j < Da ? a[b * Da + j] : c[b * Dc + (j - Da)];
+}
+
+// out[b, j] (+)= src[b, off + j]  for j < D   (slice of a wider row)
+__global__ void slice_add_kernel(const float* __restrict__ src, int lds, int off, float* __restrict__ out, int D,
+                                 int B, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int b = i / D, j = i - b * D;
+    const float v = src[(long long)b * lds + off + j];
+    out[i] = accumulate ? out[i] + v : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// critic head, gradient penalty, losses
+// ---------------------------------------------------------------------------------------------
+// score[r] = hf[r,:] . w[0:F] + emb[r % B,:] . w[F:F+E] + bias           reference models.py:164-169
+__global__ void critic_score_kernel(const float* __restrict__ hf, const float* __restrict__ emb,
+                                    const float* __restrict__ w, const float* __restrict__ bias, int R, int B, int F,
+                                    int E, float* __restrict__ score) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    float a = 0.f;
+    for (int j = lane; j < F; j += 32) a = fmaf(hf[(long long)r * F + j], w[j], a);
+    if (emb)
+        for (int j = lane; j < E; j += 32) a = fmaf(emb[(long long)(r % B) * E + j], w[F + j], a);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) score[r] = a + bias[0];
+}
+
+// dzf[r, j] = seed[r] * w[j] * lrelu'(hf[r, j])
+__global__ void critic_head_bwd_kernel(const float* __restrict__ hf, const float* __restrict__ w,
+                                       const float* __restrict__ seed, int R, int F, float* __restrict__ dzf) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * F) return;
+    const int r = (int)(i / F), j = (int)(i - (long long)r * F);
+    dzf[i] = seed[r] * w[j] * (hf[i] > 0.f ? 1.f : 0.2f);
+}
+
+// X3 = [real | fake | alpha*real + (1-alpha)*fake]  (each segment B*per floats)   utils.py:76-78
+__global__ void __launch_bounds__(256) assemble_critic_input_kernel(const float4* __restrict__ real,
+                                                                    const float4* __restrict__ fake,
+                                                                    const float* __restrict__ alpha,
+                                                                    float4* __restrict__ x3, int B, int per4) {
+    const long long n = (long long)B * per4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 r = __ldg(real + i), f = __ldg(fake + i);
+        const float a = alpha[i / per4];
+        const float na = 1.0f - a;
+        float4 m;
+        m.x = __fadd_rn(__fmul_rn(a, r.x), __fmul_rn(na, f.x));
+        m.y = __fadd_rn(__fmul_rn(a, r.y), __fmul_rn(na, f.y));
+        m.z = __fadd_rn(__fmul_rn(a, r.z), __fmul_rn(na, f.z));
+        m.w = __fadd_rn(__fmul_rn(a, r.w), __fmul_rn(na, f.w));
+        x3[i] = r; x3[n + i] = f; x3[2 * n + i] = m;
+    }
+}
+
+// per sample: n = ||g||_2 over `per` floats; gp_b = (n-1)^2; u = lambda * 2(n-1)/(B n) * g written to `u`
+__global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ g, float* __restrict__ u, int per,
+                                                      float lambda_over_B, float* __restrict__ gp_per_sample,
+                                                      float* __restrict__ norm_per_sample) {
+    __shared__ float red[8];
+    __shared__ float s_coef;
+    const int b = blockIdx.x;
+    const float* gb = g + (long long)b * per;
+    float a = 0.f;
+    for (int i = threadIdx.x; i < per; i += blockDim.x) a = fmaf(gb[i], gb[i], a);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        const float nrm = sqrtf(s);
+        gp_per_sample[b] = (nrm - 1.0f) * (nrm - 1.0f);
+        if (norm_per_sample) norm_per_sample[b] = nrm;
+        s_coef = nrm > 0.f ? lambda_over_B * 2.0f * (nrm - 1.0f) / nrm : 0.f;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    float* ub = u + (long long)b * per;
+    for (int i = threadIdx.x; i < per; i += blockDim.x) ub[i] = coef * gb[i];
+}
+
+// metrics of the critic step, one thread block: means over B of score segments and gp
+// out: [0]=loss_d [1]=gp [2]=mean d_real [3]=mean d_fake
+__global__ void critic_loss_kernel(const float* __restrict__ score, const float* __restrict__ gp_ps, int B,
+                                   float lambda_gp, float* __restrict__ out) {
+    __shared__ double red[3][32];
+    double a = 0, f = 0, g = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) { a += score[i]; f += score[B + i]; g += gp_ps[i]; }
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); f += __shfl_xor_sync(0xffffffffu, f, o);
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = f; red[2][threadIdx.x >> 5] = g; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = f = g = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; f += red[1][i]; g += red[2][i]; }
+        const float dr = (float)(a / B), df = (float)(f / B), gp = (float)(g / B);
+        out[0] = df - dr + lambda_gp * gp; out[1] = gp; out[2] = dr; out[3] = df;
+    }
+}
+
+// generator losses: adv = -mean(score); CE over 4-way logits; dlogits = weight * (softmax - onehot)/B
+// out: [0]=loss_g_adv [1]=loss_g_emo
+__global__ void generator_loss_kernel(const float* __restrict__ score, const float* __restrict__ logits,
+                                      const long long* __restrict__ labels, int B, int NC, float emo_weight,
+                                      float* __restrict__ dlogits, float* __restrict__ out) {
+    __shared__ double red[2][32];
+    double a = 0, ce = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        a += score[i];
+        const float* l = logits + (long long)i * NC;
+        float mx = l[0];
+        for (int k = 1; k < NC; ++k) mx = fmaxf(mx, l[k]);
+        float se = 0.f;
+        for (int k = 0; k < NC; ++k) se += expf(l[k] - mx);
+        const float lse = mx + logf(se);
+        const int y = (int)labels[i];
+        ce += (double)(lse - l[y]);
+        for (int k = 0; k < NC; ++k)
+            dlogits[(long long)i * NC + k] = emo_weight * (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) / (float)B;
+    }
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); ce += __shfl_xor_sync(0xffffffffu, ce, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = ce; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = ce = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; ce += red[1][i]; }
+        out[0] = (float)(-a / B); out[1] = (float)(ce / B);
+    }
+}
+
+// a[i] *= b[i]
+__global__ void mul_inplace_kernel(float* a, const float* b, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] *= b[i];
+}
+// a[i] += b[i]
+__global__ void axpy_kernel(float* a, const float* b, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+// a[i] += x[i]; b[i] += y[i]   (accumulate the two BatchNorm affine gradients)
+__global__ void add2_kernel(float* a, const float* x, float* b, const float* y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] += x[i]; b[i] += y[i]; }
+}
+// hf[i] = lrelu'(hf[i]) * q[i]
+__global__ void lrelu_mask_mul_inplace_kernel(float* hf, const float* q, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hf[i] = (hf[i] > 0.f ? 1.f : 0.2f) * q[i];
+}
+// eval-mode BatchNorm: mean/invstd from the running statistics
+__global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, int C, float* mean, float* invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) { mean[c] = rm[c]; invstd[c] = 1.0f / sqrtf(rv[c] + eps); }
+}
+__global__ void const_fill_kernel(float* p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// demb[b, j] (+)= seed[b] * w[F + j]     (critic conditioning term, models.py:165-168)
+__global__ void critic_demb_kernel(const float* seed, const float* w, int B, int F, int E, float* demb, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * E) return;
+    const float v = seed[i / E] * w[F + i % E];
+    demb[i] = accumulate ? demb[i] + v : v;
+}
+__global__ void critic_seed_kernel(float* seed, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * B) return;
+    seed[i] = i < B ? -1.0f / (float)B : (i < 2 * B ? 1.0f / (float)B : 1.0f);
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// eval-mode BatchNorm folded into a per-channel scale/shift around a conv bias:
+//   y = (conv + bias - rm) * g/sqrt(rv+eps) + b  =  conv*scale + shift
+__global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ rm,
+                               const float* __restrict__ rv, float eps, int C, float* __restrict__ scale,
+                               float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float s = gamma[c] / sqrtf(rv[c] + eps);
+    scale[c] = s;
+    shift[c] = fmaf((conv_bias ? conv_bias[c] : 0.f) - rm[c], s, beta[c]);
+}
+
+}  // namespace mg

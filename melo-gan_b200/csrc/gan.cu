@@ -1,0 +1,865 @@
+// gan.cu -- the GAN training hot path of Melo-GAN on B200: module forwards/backwards and the two
+// step bodies of reference src/gan/train_gan.py:183-251, as sequences of sm_100a kernels.
+//
+// Data layout: every activation is channels-last [sample, position, channel] in HBM, so a conv is an
+// implicit GEMM whose A rows are contiguous channel vectors and whose taps are row shifts; the
+// reference's permute(0,2,1) at models.py:73,159 and ed_model.py:65 disappear.  G.decoder.pre.2's
+// output is produced directly in that layout by permuting the weight-row index (n_perm), so the
+// view(b,256,L0) at models.py:70 costs nothing.
+//
+// Critic step: D has no BatchNorm, so real, fake and the interpolate x_hat run as ONE
+// 3B-row batch through one forward chain and one dgrad chain with per-row seeds (-1/B, +1/B, 1).
+// LeakyReLU is piecewise linear, so the double backward of the gradient penalty reduces to a
+// forward-like "adjoint" chain on u = dL/d(grad_x) with the saved sign masks plus wgrad-shaped
+// contractions; the adjoint activations overwrite the x_hat rows of the saved activations, which
+// lets a single wgrad per layer cover all 3B rows (first-order + penalty terms at once).
+#include <math.h>
+#include <string.h>
+
+#include "gan_ctx.cuh"
+
+using namespace mg;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+struct Bump {
+    char* base; size_t off = 0;
+    std::vector<mg_gan::Named>* named;
+    template <typename T>
+    T* get(const char* name, size_t count) {
+        const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        if (base && named) named->push_back({name, p, count * sizeof(T)});
+        off += bytes;
+        return p;
+    }
+};
+
+void layout(mg_gan* c, char* base) {
+    Bump b{base, 0, base ? &c->named : nullptr};
+    const size_t B = c->B, T = c->T, L0 = c->L0;
+    const size_t es = c->bf16 ? 2 : 4;                       // activation element size
+    auto act = [&](const char* name, size_t count) { return (void*)b.get<char>(name, count * es); };
+    const mg_gan_config& f = c->cfg;
+    // FeatureEncoder
+    c->e_xhat = b.get<float>("e.xhat", B * f.numeric_dim);
+    c->e_ln = b.get<float>("e.ln", B * f.numeric_dim);
+    c->e_z1 = b.get<float>("e.z1", B * f.enc_hidden1);
+    c->e_h1 = b.get<float>("e.h1", B * f.enc_hidden1);
+    c->e_z2 = b.get<float>("e.z2", B * f.enc_hidden2);
+    c->e_h2 = b.get<float>("e.h2", B * f.enc_hidden2);
+    c->e_emb = b.get<float>("e.emb", B * f.embed_dim);
+    c->e_d1 = b.get<float>("e.d1", B * f.enc_hidden1);
+    c->e_d2 = b.get<float>("e.d2", B * f.enc_hidden2);
+    c->e_dln = b.get<float>("e.dln", B * f.numeric_dim);
+    // Generator
+    c->g_xcat = b.get<float>("g.xcat", B * c->zin);
+    c->g_ha = b.get<float>("g.ha", B * f.gen_hidden);
+    c->g_lat = b.get<float>("g.latent", B * f.latent_dim);
+    c->g_hb = b.get<float>("g.hb", B * 512);
+    c->g_notes = b.get<float>("g.notes", B * T * 4);
+    c->g_y0 = act("g.y0", B * L0 * 256);
+    c->g_x1 = act("g.x1", B * 2 * L0 * 128);
+    c->g_y1 = act("g.y1", B * 2 * L0 * 128);
+    c->g_x2 = act("g.x2", B * 4 * L0 * 64);
+    c->g_y2 = act("g.y2", B * 4 * L0 * 64);
+    c->g_bn1_stats = b.get<float>("g.bn1.stats", 256);
+    c->g_bn1_mean = b.get<float>("g.bn1.mean", 128);
+    c->g_bn1_is = b.get<float>("g.bn1.invstd", 128);
+    c->g_bn2_stats = b.get<float>("g.bn2.stats", 128);
+    c->g_bn2_mean = b.get<float>("g.bn2.mean", 64);
+    c->g_bn2_is = b.get<float>("g.bn2.invstd", 64);
+    c->g_bn_sums = b.get<float>("g.bn.sums", 256);
+    c->g_dy2 = act("g.dy2", B * 4 * L0 * 64);
+    c->g_dx2 = act("g.dx2", B * 4 * L0 * 64);
+    c->g_dy1 = act("g.dy1", B * 2 * L0 * 128);
+    c->g_dx1 = act("g.dx1", B * 2 * L0 * 128);
+    c->g_dy0 = act("g.dy0", B * L0 * 256);
+    c->g_dhb = b.get<float>("g.dhb", B * 512);
+    c->g_dlat = b.get<float>("g.dlat", B * f.latent_dim);
+    c->g_dha = b.get<float>("g.dha", B * f.gen_hidden);
+    c->g_dxcat = b.get<float>("g.dxcat", B * c->zin);
+    c->g_demb = b.get<float>("g.demb", B * f.embed_dim);
+    // Critic: up to 3B rows
+    const size_t R = 3 * B, per = L0 * 256;                  // every critic activation has L0*256 elements
+    c->d_x3 = b.get<float>("d.x3", R * T * 4);
+    c->d_h1 = act("d.h1", R * per);
+    c->d_h2 = act("d.h2", R * per);
+    c->d_h3 = act("d.h3", R * per);
+    c->d_pool = b.get<float>("d.pool", R * 256);
+    c->d_hf = b.get<float>("d.hf", R * 256);
+    c->d_score = b.get<float>("d.score", R);
+    c->d_seed = b.get<float>("d.seed", R);
+    c->d_dzf = b.get<float>("d.dzf", R * 256);
+    c->d_dp = b.get<float>("d.dp", R * 256);
+    c->d_dz3 = act("d.dz3", R * per);
+    c->d_dz2 = act("d.dz2", R * per);
+    c->d_dz1 = act("d.dz1", R * per);
+    c->d_gx = b.get<float>("d.gx", B * T * 4);
+    c->d_gp_ps = b.get<float>("d.gp_ps", B);
+    c->d_q = b.get<float>("d.q", B * 256);
+    c->d_dnotes = b.get<float>("d.dnotes", B * T * 4);
+    // Emotion discriminator
+    const int ech[4] = {64, 128, 256, 256};
+    static const char* hn[4] = {"ed.h0", "ed.h1", "ed.h2", "ed.h3"};
+    static const char* gn[4] = {"ed.g0", "ed.g1", "ed.g2", "ed.g3"};
+    static const char* sn[4] = {"ed.scale0", "ed.scale1", "ed.scale2", "ed.scale3"};
+    static const char* tn[4] = {"ed.shift0", "ed.shift1", "ed.shift2", "ed.shift3"};
+    for (int i = 0; i < 4; ++i) {
+        c->ed_h[i] = act(hn[i], B * T * ech[i]);
+        c->ed_g[i] = act(gn[i], B * T * ech[i]);
+        c->ed_scale[i] = b.get<float>(sn[i], 256);
+        c->ed_shift[i] = b.get<float>(tn[i], 256);
+    }
+    c->ed_dzA = act("ed.dzA", B * T * 256);
+    c->ed_dzB = act("ed.dzB", B * T * 256);
+    c->ed_pool = b.get<float>("ed.pool", B * 256);
+    c->ed_pj = b.get<float>("ed.pj", B * 256);
+    c->ed_c1 = b.get<float>("ed.c1", B * 256);
+    c->ed_c1g = b.get<float>("ed.c1g", B * 256);
+    c->ed_c2 = b.get<float>("ed.c2", B * 128);
+    c->ed_c2g = b.get<float>("ed.c2g", B * 128);
+    c->ed_logits = b.get<float>("ed.logits", B * 8);
+    c->ed_dlogits = b.get<float>("ed.dlogits", B * 8);
+    c->ed_d128 = b.get<float>("ed.d128", B * 128);
+    c->ed_d256a = b.get<float>("ed.d256a", B * 256);
+    c->ed_d256b = b.get<float>("ed.d256b", B * 256);
+    // misc
+    c->partial_floats = (size_t)128 * 2 * 256 * L0 > (size_t)1 << 20 ? (size_t)128 * 2 * 256 * L0 : (size_t)1 << 20;
+    c->partial = b.get<float>("partial", c->partial_floats);
+    c->metrics = b.get<float>("metrics", 16);
+    c->seed_g = b.get<float>("seed_g", B);
+    c->arena_bytes = b.off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A-1 FeatureEncoder
+// ------------------------------------------------------------------------------------------------
+int fe_forward(mg_gan* c, const float* numeric, const float* mask1, const float* mask2, int train, float* emb_out,
+               cudaStream_t st) {
+    const mg_gan_config& f = c->cfg;
+    const int B = c->B;
+    const float scale = (float)(1.0 / (1.0 - f.enc_dropout));
+    layernorm_small_kernel<<<(B + 127) / 128, 128, 0, st>>>(numeric, B, f.numeric_dim, c->E.ln_w, c->E.ln_b, 1e-5f,
+                                                            c->e_ln, c->e_xhat);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->e_ln, c->e_z1, c->E.w1, c->E.b1, B, f.numeric_dim, f.enc_hidden1, ACT_NONE,
+                                     nullptr, st)));
+    long long n = (long long)B * f.enc_hidden1;
+    gelu_dropout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->e_z1, train ? mask1 : nullptr, scale,
+                                                                          c->e_h1, n);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->e_h1, c->e_z2, c->E.w2, c->E.b2, B, f.enc_hidden1, f.enc_hidden2, ACT_NONE,
+                                     nullptr, st)));
+    n = (long long)B * f.enc_hidden2;
+    gelu_dropout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->e_z2, train ? mask2 : nullptr, scale,
+                                                                          c->e_h2, n);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->e_h2, emb_out, c->E.w3, c->E.b3, B, f.enc_hidden2, f.embed_dim, ACT_NONE,
+                                     nullptr, st)));
+    c->e_mask1 = train ? mask1 : nullptr;
+    c->e_mask2 = train ? mask2 : nullptr;
+    c->fwd_state |= FWD_E;
+    return MG_OK;
+}
+
+int fe_backward(mg_gan* c, const float* demb, cudaStream_t st) {
+    const mg_gan_config& f = c->cfg;
+    const int B = c->B;
+    const float scale = (float)(1.0 / (1.0 - f.enc_dropout));
+    // net.7
+    MG_TRY((linear_wgrad<float, float>(demb, c->e_h2, c->gE.w3, 0, B, f.enc_hidden2, f.embed_dim, st)));
+    MG_TRY((colreduce<float, COL_SUM>(c, demb, f.embed_dim, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                      f.embed_dim, c->gE.b3, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((linear_dgrad<float, float>(demb, c->e_d2, c->E.w3, B, f.enc_hidden2, f.embed_dim, nullptr, MUL_NONE, st)));
+    long long n = (long long)B * f.enc_hidden2;
+    gelu_dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->e_d2, c->e_z2, c->e_mask2, scale, c->e_d2, n);
+    MG_LAUNCH_OK();
+    // net.4
+    MG_TRY((linear_wgrad<float, float>(c->e_d2, c->e_h1, c->gE.w2, 0, B, f.enc_hidden1, f.enc_hidden2, st)));
+    MG_TRY((colreduce<float, COL_SUM>(c, c->e_d2, f.enc_hidden2, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                      f.enc_hidden2, c->gE.b2, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((linear_dgrad<float, float>(c->e_d2, c->e_d1, c->E.w2, B, f.enc_hidden1, f.enc_hidden2, nullptr, MUL_NONE, st)));
+    n = (long long)B * f.enc_hidden1;
+    gelu_dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->e_d1, c->e_z1, c->e_mask1, scale, c->e_d1, n);
+    MG_LAUNCH_OK();
+    // net.1
+    MG_TRY((linear_wgrad<float, float>(c->e_d1, c->e_ln, c->gE.w1, 0, B, f.numeric_dim, f.enc_hidden1, st)));
+    MG_TRY((colreduce<float, COL_SUM>(c, c->e_d1, f.enc_hidden1, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                      f.enc_hidden1, c->gE.b1, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((linear_dgrad<float, float>(c->e_d1, c->e_dln, c->E.w1, B, f.numeric_dim, f.enc_hidden1, nullptr, MUL_NONE, st)));
+    // net.0 LayerNorm affine: d(bias) = sum dln, d(weight) = sum dln * xhat  (no input gradient needed)
+    MG_TRY((colreduce<float, COL_SUM>(c, c->e_dln, f.numeric_dim, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                      f.numeric_dim, c->gE.ln_b, 0, 0, 0, 1.0f, 1, st)));
+    // d(weight) = sum dln * xhat: product into e_xhat (no longer needed), then a column sum
+    {
+        const long long m = (long long)B * f.numeric_dim;
+        mul_inplace_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->e_xhat, c->e_dln, m);
+        MG_LAUNCH_OK();
+        MG_TRY((colreduce<float, COL_SUM>(c, c->e_xhat, f.numeric_dim, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                          f.numeric_dim, c->gE.ln_w, 0, 0, 0, 1.0f, 1, st)));
+    }
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A-2..A-4 Generator
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int bn_train_or_eval(mg_gan* c, const T* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
+                     const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st) {
+    if (train) {
+        MG_TRY((colreduce<T, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
+                                         1.0f, 0, st)));
+        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows, (float)c->cfg.bn_eps,
+                                                            (float)c->cfg.bn_momentum, mean, invstd, rm, rv, 1);
+    } else {
+        bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rm, rv, (float)c->cfg.bn_eps, C, mean, invstd);
+    }
+    MG_LAUNCH_OK();
+    const long long n4 = rows * C / 4;
+    bn_relu_apply_kernel<T><<<grid_for(n4), 256, 0, st>>>(x, y, n4, C, mean, invstd, gamma, beta);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+template <typename T>
+int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, float* notes_out, float* latent_out,
+                cudaStream_t st) {
+    const mg_gan_config& f = c->cfg;
+    const int B = c->B, L0 = c->L0;
+    {
+        const int n = B * c->zin;
+        concat2_kernel<<<(n + 255) / 256, 256, 0, st>>>(noise, f.noise_dim, emb, f.embed_dim, c->g_xcat, B);
+        MG_LAUNCH_OK();
+    }
+    MG_TRY((linear_fwd<float, float>(c->g_xcat, c->g_ha, c->G.a_w, c->G.a_b, B, c->zin, f.gen_hidden, ACT_RELU, nullptr, st)));
+    MG_TRY((linear_fwd<float, float>(c->g_ha, c->g_lat, c->G.l_w, c->G.l_b, B, f.gen_hidden, f.latent_dim, ACT_NONE, nullptr, st)));
+    MG_TRY((linear_fwd<float, float>(c->g_lat, c->g_hb, c->G.p0_w, c->G.p0_b, B, f.latent_dim, 512, ACT_RELU, nullptr, st)));
+    // pre.2 (+ReLU) written channels-last: logical column n = l*256 + c  <->  weight row c*L0 + l
+    MG_TRY((linear_fwd<float, T>(c->g_hb, (T*)c->g_y0, c->G.p2_w, c->G.p2_b, B, 512, 256 * L0, ACT_RELU, nullptr, st,
+                                 256, L0)));
+    // deconv.0 -> BN -> ReLU
+    MG_TRY((upsample2_fwd<T, T>((const T*)c->g_y0, (T*)c->g_x1, c->G.d0_w, c->G.d0_b, B, L0, 256, 128, 5, 128 * 5,
+                                ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    MG_TRY((bn_train_or_eval<T>(c, (const T*)c->g_x1, (T*)c->g_y1, (long long)B * 2 * L0, 128, c->g_bn1_stats,
+                                c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->G.bn1_b, c->G.bn1_rm, c->G.bn1_rv, train, st)));
+    // deconv.3 -> BN -> ReLU
+    MG_TRY((upsample2_fwd<T, T>((const T*)c->g_y1, (T*)c->g_x2, c->G.d3_w, c->G.d3_b, B, 2 * L0, 128, 64, 5, 64 * 5,
+                                ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    MG_TRY((bn_train_or_eval<T>(c, (const T*)c->g_x2, (T*)c->g_y2, (long long)B * 4 * L0, 64, c->g_bn2_stats,
+                                c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st)));
+    // deconv.6 -> notes (B, T, 4) float32, already in the reference's permuted (B, notes, 4) order
+    float* notes = notes_out ? notes_out : c->g_notes;
+    MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y2, notes, c->G.d6_w, c->G.d6_b, B, 4 * L0, 64, 4, 5, 4 * 5,
+                                    ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    if (latent_out)
+        MG_CUDA_OK(cudaMemcpyAsync(latent_out, c->g_lat, sizeof(float) * B * f.latent_dim, cudaMemcpyDeviceToDevice, st));
+    c->fwd_state |= FWD_G;
+    return MG_OK;
+}
+
+template <typename T>
+int bn_backward(mg_gan* c, const T* x, const T* dy, T* dx, long long rows, int C, const float* mean,
+                const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st) {
+    // sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat
+    MG_TRY((colreduce<T, COL_BN_BWD>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
+                                     0, st)));
+    add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
+    MG_LAUNCH_OK();
+    const long long n4 = rows * C / 4;
+    bn_bwd_apply_kernel<T><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
+                                                         c->g_bn_sums);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+template <typename T>
+int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* demb_out, cudaStream_t st) {
+    const mg_gan_config& f = c->cfg;
+    const int B = c->B, L0 = c->L0, T4 = c->T;
+    // ---- deconv.6: bias, wgrad, dgrad (strided conv of dnotes with W[ci][co][t]) masked by ReLU(y2) ----
+    MG_TRY((colreduce<float, COL_SUM>(c, dnotes, 4, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, (long long)B * T4, 4,
+                                      c->gG.d6_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((convT_wgrad<T, float>((const T*)c->g_y2, dnotes, c->gG.d6_w, B, 4 * L0, 64, 4, st)));
+    MG_TRY((conv_fwd<float, T>(dnotes, (T*)c->g_dy2, c->G.d6_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr,
+                               nullptr, c->g_y2, MUL_RELU_SIGN, st, /*w_nstride (n=ci)*/ 4 * 5, /*w_kstride (k=co)*/ 5)));
+    // ---- BN2 backward ----
+    MG_TRY((bn_backward<T>(c, (const T*)c->g_x2, (const T*)c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
+                           c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->gG.bn2_w, c->gG.bn2_b, st)));
+    // ---- deconv.3 ----
+    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx2, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                  (long long)B * 4 * L0, 64, c->gG.d3_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((convT_wgrad<T, T>((const T*)c->g_y1, (const T*)c->g_dx2, c->gG.d3_w, B, 2 * L0, 128, 64, st)));
+    MG_TRY((conv_fwd<T, T>((const T*)c->g_dx2, (T*)c->g_dy1, c->G.d3_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE,
+                           nullptr, nullptr, c->g_y1, MUL_RELU_SIGN, st, 64 * 5, 5)));
+    MG_TRY((bn_backward<T>(c, (const T*)c->g_x1, (const T*)c->g_dy1, (T*)c->g_dx1, (long long)B * 2 * L0, 128,
+                           c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->gG.bn1_w, c->gG.bn1_b, st)));
+    // ---- deconv.0 ----
+    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx1, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                  (long long)B * 2 * L0, 128, c->gG.d0_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((convT_wgrad<T, T>((const T*)c->g_y0, (const T*)c->g_dx1, c->gG.d0_w, B, L0, 256, 128, st)));
+    MG_TRY((conv_fwd<T, T>((const T*)c->g_dx1, (T*)c->g_dy0, c->G.d0_w, nullptr, B, 2 * L0, 128, 256, 5, 2, 2, ACT_NONE,
+                           nullptr, nullptr, c->g_y0, MUL_RELU_SIGN, st, 128 * 5, 5)));
+    // ---- pre.2 (weight rows permuted: logical n = l*256 + c <-> physical c*L0 + l) ----
+    const int N2 = 256 * L0;
+    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dy0, N2, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B, N2,
+                                  c->gG.p2_b, 0, 256, L0, 1.0f, 1, st)));
+    MG_TRY((linear_wgrad<T, float>((const T*)c->g_dy0, c->g_hb, c->gG.p2_w, 0, B, 512, N2, st, 256, L0)));
+    MG_TRY((linear_dgrad<T, float>((const T*)c->g_dy0, c->g_dhb, c->G.p2_w, B, 512, N2, c->g_hb, MUL_RELU_SIGN, st, 256, L0)));
+    // ---- pre.0 ----
+    MG_TRY((colreduce<float, COL_SUM>(c, c->g_dhb, 512, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B, 512, c->gG.p0_b,
+                                      0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((linear_wgrad<float, float>(c->g_dhb, c->g_lat, c->gG.p0_w, 0, B, f.latent_dim, 512, st)));
+    MG_TRY((linear_dgrad<float, float>(c->g_dhb, c->g_dlat, c->G.p0_w, B, f.latent_dim, 512, nullptr, MUL_NONE, st)));
+    if (dlatent) {
+        const long long n = (long long)B * f.latent_dim;
+        axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->g_dlat, dlatent, n);
+        MG_LAUNCH_OK();
+    }
+    // ---- noise_to_latent.net.2 ----
+    MG_TRY((colreduce<float, COL_SUM>(c, c->g_dlat, f.latent_dim, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                      f.latent_dim, c->gG.l_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((linear_wgrad<float, float>(c->g_dlat, c->g_ha, c->gG.l_w, 0, B, f.gen_hidden, f.latent_dim, st)));
+    MG_TRY((linear_dgrad<float, float>(c->g_dlat, c->g_dha, c->G.l_w, B, f.gen_hidden, f.latent_dim, c->g_ha,
+                                       MUL_RELU_SIGN, st)));
+    // ---- noise_to_latent.net.0 ----
+    MG_TRY((colreduce<float, COL_SUM>(c, c->g_dha, f.gen_hidden, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B,
+                                      f.gen_hidden, c->gG.a_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((linear_wgrad<float, float>(c->g_dha, c->g_xcat, c->gG.a_w, 0, B, c->zin, f.gen_hidden, st)));
+    if (demb_out) {
+        MG_TRY((linear_dgrad<float, float>(c->g_dha, c->g_dxcat, c->G.a_w, B, c->zin, f.gen_hidden, nullptr, MUL_NONE, st)));
+        const int n = B * f.embed_dim;
+        slice_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->g_dxcat, c->zin, f.noise_dim, demb_out, f.embed_dim, B, 0);
+        MG_LAUNCH_OK();
+    }
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A-5 Discriminator (critic)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int disc_forward(mg_gan* c, const float* notes, const float* emb, int R, float* score_out, cudaStream_t st) {
+    const int L0 = c->L0, T4 = c->T;
+    MG_TRY((conv_fwd<float, T>(notes, (T*)c->d_h1, c->D.c0_w, c->D.c0_b, R, T4, 4, 64, 5, 2, 2, ACT_LRELU, nullptr,
+                               nullptr, nullptr, MUL_NONE, st)));
+    MG_TRY((conv_fwd<T, T>((const T*)c->d_h1, (T*)c->d_h2, c->D.c2_w, c->D.c2_b, R, 4 * L0, 64, 128, 5, 2, 2, ACT_LRELU,
+                           nullptr, nullptr, nullptr, MUL_NONE, st)));
+    MG_TRY((conv_fwd<T, T>((const T*)c->d_h2, (T*)c->d_h3, c->D.c4_w, c->D.c4_b, R, 2 * L0, 128, 256, 5, 2, 2, ACT_LRELU,
+                           nullptr, nullptr, nullptr, MUL_NONE, st)));
+    pool_rows_kernel<T, float><<<dim3(1, R), 256, 0, st>>>((const T*)c->d_h3, c->d_pool, R, L0, 256, 1.0f / (float)L0);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->d_pool, c->d_hf, c->D.fc_w, c->D.fc_b, R, 256, 256, ACT_LRELU, nullptr, st)));
+    float* score = score_out ? score_out : c->d_score;
+    critic_score_kernel<<<(R + 7) / 8, 256, 0, st>>>(c->d_hf, emb, c->D.rf_w, c->D.rf_b, R, c->B, 256,
+                                                     emb ? c->cfg.embed_dim : 0, score);
+    MG_LAUNCH_OK();
+    c->d_rows = R;
+    c->d_emb = emb;
+    c->fwd_state |= FWD_D;
+    return MG_OK;
+}
+
+// dgrad chain for all R rows from per-row seeds; optionally continues to d(notes) for rows [x0, x0+xn)
+template <typename T>
+int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int xn, int accumulate, cudaStream_t st) {
+    const int L0 = c->L0;
+    const size_t per = (size_t)L0 * 256;
+    {
+        const long long n = (long long)R * 256;
+        critic_head_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_hf, c->D.rf_w, seed, R, 256, c->d_dzf);
+        MG_LAUNCH_OK();
+    }
+    MG_TRY((linear_dgrad<float, float>(c->d_dzf, c->d_dp, c->D.fc_w, R, 256, 256, nullptr, MUL_NONE, st)));
+    {
+        const long long n4 = (long long)R * per / 4;
+        bcast_rows_mul_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(c->d_dp, (const T*)c->d_h3, (T*)c->d_dz3, n4, L0, 256,
+                                                                     1.0f / (float)L0, nullptr, MUL_LRELU_SIGN);
+        MG_LAUNCH_OK();
+    }
+    // conv.4 dgrad: k = conv_out 256, n = conv_in 128;  W [256][128][5]
+    MG_TRY((upsample2_fwd<T, T>((const T*)c->d_dz3, (T*)c->d_dz2, c->D.c4_w, nullptr, R, L0, 256, 128, 5, 128 * 5,
+                                ACT_NONE, c->d_h2, MUL_LRELU_SIGN, 0, st)));
+    MG_TRY((upsample2_fwd<T, T>((const T*)c->d_dz2, (T*)c->d_dz1, c->D.c2_w, nullptr, R, 2 * L0, 128, 64, 5, 64 * 5,
+                                ACT_NONE, c->d_h1, MUL_LRELU_SIGN, 0, st)));
+    if (dnotes && xn > 0) {
+        const T* dz1 = (const T*)c->d_dz1 + (size_t)x0 * per;
+        MG_TRY((upsample2_fwd<T, float>(dz1, dnotes, c->D.c0_w, nullptr, xn, 4 * L0, 64, 4, 5, 4 * 5, ACT_NONE, nullptr,
+                                        MUL_NONE, accumulate, st)));
+    }
+    return MG_OK;
+}
+
+// parameter gradients from the saved (possibly adjoint-overwritten) activations, rows [0, R);
+// bias terms and the embedding part of real_fake only see rows [0, Rb)
+template <typename T>
+int disc_wgrad(mg_gan* c, const float* x_in, const float* seed, int R, int Rb, cudaStream_t st) {
+    const int L0 = c->L0, T4 = c->T, E = c->cfg.embed_dim;
+    // real_fake: d w[0:256] = sum_r seed_r * hf[r]; d w[256:] = sum_{r<Rb} seed_r emb[r % B]; d b = sum_{r<Rb} seed_r
+    MG_TRY((colreduce<float, COL_WSUM>(c, c->d_hf, 256, nullptr, 0, nullptr, nullptr, seed, 1, 0, R, 256, c->gD.rf_w, 0,
+                                       0, 0, 1.0f, 1, st)));
+    if (c->d_emb) {
+        for (int s0 = 0; s0 < Rb; s0 += c->B)   // segment by segment: emb rows repeat every B
+            MG_TRY((colreduce<float, COL_WSUM>(c, c->d_emb - (size_t)s0 * E, E, nullptr, 0, nullptr, nullptr, seed, 1, s0,
+                                               s0 + c->B, E, c->gD.rf_w + 256, 0, 0, 0, 1.0f, 1, st)));
+    }
+    MG_TRY((colreduce<float, COL_SUM>(c, seed, 1, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, Rb, 1, c->gD.rf_b, 0, 0, 0,
+                                      1.0f, 1, st)));
+    // fc.1
+    MG_TRY((linear_wgrad<float, float>(c->d_dzf, c->d_pool, c->gD.fc_w, 0, R, 256, 256, st)));
+    MG_TRY((colreduce<float, COL_SUM>(c, c->d_dzf, 256, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, Rb, 256, c->gD.fc_b,
+                                      0, 0, 0, 1.0f, 1, st)));
+    // conv.4 / conv.2 / conv.0
+    MG_TRY((conv_wgrad<T, T>((const T*)c->d_dz3, (const T*)c->d_h2, c->gD.c4_w, 0, (long long)R * L0, 2 * L0, 128, 256, 5,
+                             2, 2, st)));
+    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz3, 256, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                  (long long)Rb * L0, 256, c->gD.c4_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((conv_wgrad<T, T>((const T*)c->d_dz2, (const T*)c->d_h1, c->gD.c2_w, 0, (long long)R * 2 * L0, 4 * L0, 64, 128,
+                             5, 2, 2, st)));
+    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz2, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                  (long long)Rb * 2 * L0, 128, c->gD.c2_b, 0, 0, 0, 1.0f, 1, st)));
+    MG_TRY((conv_wgrad<T, float>((const T*)c->d_dz1, x_in, c->gD.c0_w, 0, (long long)R * 4 * L0, T4, 4, 64, 5, 2, 2, st)));
+    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz1, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                  (long long)Rb * 4 * L0, 64, c->gD.c0_b, 0, 0, 0, 1.0f, 1, st)));
+    return MG_OK;
+}
+
+// A-6 + A-7 loss part
+template <typename T>
+int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const float* emb, const float* alpha,
+                         float* metrics_out, cudaStream_t st) {
+    const int B = c->B, L0 = c->L0, T4 = c->T;
+    const size_t per = (size_t)L0 * 256, pern = (size_t)T4 * 4;
+    assemble_critic_input_kernel<<<grid_for((long long)B * pern / 4), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(real), reinterpret_cast<const float4*>(fake), alpha,
+        reinterpret_cast<float4*>(c->d_x3), B, (int)(pern / 4));
+    MG_LAUNCH_OK();
+    MG_TRY((disc_forward<T>(c, c->d_x3, emb, 3 * B, nullptr, st)));
+    critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->d_seed, B);
+    MG_LAUNCH_OK();
+    // one dgrad chain for all 3B rows; the x_hat rows continue to grad_x
+    MG_TRY((disc_dgrad<T>(c, c->d_seed, 3 * B, c->d_gx, 2 * B, B, 0, st)));
+    // penalty and u = dL/d(grad_x), written over the x_hat rows of X3
+    float* u = c->d_x3 + (size_t)2 * B * pern;
+    gp_norm_kernel<<<B, 256, 0, st>>>(c->d_gx, u, (int)pern, (float)(c->cfg.lambda_gp / (double)B), c->d_gp_ps, nullptr);
+    MG_LAUNCH_OK();
+    critic_loss_kernel<<<1, 256, 0, st>>>(c->d_score, c->d_gp_ps, B, (float)c->cfg.lambda_gp, metrics_out ? metrics_out : c->metrics);
+    MG_LAUNCH_OK();
+    // adjoint forward chain on the x_hat rows, overwriting their saved activations in place
+    T* h1x = (T*)c->d_h1 + (size_t)2 * B * per;
+    T* h2x = (T*)c->d_h2 + (size_t)2 * B * per;
+    T* h3x = (T*)c->d_h3 + (size_t)2 * B * per;
+    MG_TRY((conv_fwd<float, T>(u, h1x, c->D.c0_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr, nullptr, h1x,
+                               MUL_LRELU_SIGN, st)));
+    MG_TRY((conv_fwd<T, T>(h1x, h2x, c->D.c2_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE, nullptr, nullptr, h2x,
+                           MUL_LRELU_SIGN, st)));
+    MG_TRY((conv_fwd<T, T>(h2x, h3x, c->D.c4_w, nullptr, B, 2 * L0, 128, 256, 5, 2, 2, ACT_NONE, nullptr, nullptr, h3x,
+                           MUL_LRELU_SIGN, st)));
+    float* poolx = c->d_pool + (size_t)2 * B * 256;
+    float* hfx = c->d_hf + (size_t)2 * B * 256;
+    pool_rows_kernel<T, float><<<dim3(1, B), 256, 0, st>>>(h3x, poolx, B, L0, 256, 1.0f / (float)L0);
+    MG_LAUNCH_OK();
+    // q = Wfc dgp, then hf' = lrelu'(hf) * q in place (so that d w_rf[0:256] picks up sum mf*q with seed 1)
+    MG_TRY((linear_fwd<float, float>(poolx, c->d_q, c->D.fc_w, nullptr, B, 256, 256, ACT_NONE, nullptr, st)));
+    {
+        const long long n = (long long)B * 256;
+        lrelu_mask_mul_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hfx, c->d_q, n);
+        MG_LAUNCH_OK();
+    }
+    MG_TRY((disc_wgrad<T>(c, c->d_x3, c->d_seed, 3 * B, 2 * B, st)));
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A-8 EmotionDiscriminator (eval, frozen)
+// ------------------------------------------------------------------------------------------------
+int ed_fold(mg_gan* c, cudaStream_t st) {
+    const int ch[4] = {64, 128, 256, 256};
+    for (int i = 0; i < 4; ++i) {
+        bn_fold_kernel<<<(ch[i] + 127) / 128, 128, 0, st>>>(c->ED.conv[i].b, c->ED.conv[i].g, c->ED.conv[i].be,
+                                                            c->ED.conv[i].rm, c->ED.conv[i].rv, 1e-5f, ch[i],
+                                                            c->ed_scale[i], c->ed_shift[i]);
+        MG_LAUNCH_OK();
+    }
+    c->ed_folded = true;
+    return MG_OK;
+}
+
+template <typename T>
+int ed_forward(mg_gan* c, const float* notes, float* logits_out, cudaStream_t st) {
+    const int B = c->B, T4 = c->T, NC = c->cfg.n_classes;
+    if (!c->ed_folded) MG_TRY(ed_fold(c, st));
+    MG_TRY((conv_fwd<float, T>(notes, (T*)c->ed_h[0], c->ED.conv[0].w, c->ed_shift[0], B, T4, 4, 64, 5, 1, 2, ACT_GELU,
+                               c->ed_scale[0], c->ed_g[0], nullptr, MUL_NONE, st)));
+    const int ci[4] = {4, 64, 128, 256}, co[4] = {64, 128, 256, 256};
+    for (int i = 1; i < 4; ++i)
+        MG_TRY((conv_fwd<T, T>((const T*)c->ed_h[i - 1], (T*)c->ed_h[i], c->ED.conv[i].w, c->ed_shift[i], B, T4, ci[i],
+                               co[i], 3, 1, 1, ACT_GELU, c->ed_scale[i], c->ed_g[i], nullptr, MUL_NONE, st)));
+    pool_rows_kernel<T, float><<<dim3(1, B), 256, 0, st>>>((const T*)c->ed_h[3], c->ed_pool, B, T4, 256, 1.0f / (float)T4);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->ed_pool, c->ed_pj, c->ED.pj_w, c->ED.pj_b, B, 256, 256, ACT_NONE, nullptr, st)));
+    MG_TRY((linear_fwd<float, float>(c->ed_pj, c->ed_c1, c->ED.c0_w, c->ED.c0_b, B, 256, 256, ACT_GELU, c->ed_c1g, st)));
+    MG_TRY((linear_fwd<float, float>(c->ed_c1, c->ed_c2, c->ED.c3_w, c->ED.c3_b, B, 256, 128, ACT_GELU, c->ed_c2g, st)));
+    MG_TRY((linear_fwd<float, float>(c->ed_c2, logits_out ? logits_out : c->ed_logits, c->ED.hd_w, c->ED.hd_b, B, 128, NC,
+                                     ACT_NONE, nullptr, st)));
+    c->fwd_state |= FWD_ED;
+    return MG_OK;
+}
+
+template <typename T>
+int ed_backward_input(mg_gan* c, const float* dlogits, float* dnotes, int accumulate, cudaStream_t st) {
+    const int B = c->B, T4 = c->T, NC = c->cfg.n_classes;
+    MG_TRY((linear_dgrad<float, float>(dlogits, c->ed_d128, c->ED.hd_w, B, 128, NC, c->ed_c2g, MUL_VALUE, st)));
+    MG_TRY((linear_dgrad<float, float>(c->ed_d128, c->ed_d256a, c->ED.c3_w, B, 256, 128, c->ed_c1g, MUL_VALUE, st)));
+    MG_TRY((linear_dgrad<float, float>(c->ed_d256a, c->ed_d256b, c->ED.c0_w, B, 256, 256, nullptr, MUL_NONE, st)));
+    MG_TRY((linear_dgrad<float, float>(c->ed_d256b, c->ed_d256a, c->ED.pj_w, B, 256, 256, nullptr, MUL_NONE, st)));
+    // d(conv3 pre-BN output) = dpool/T * gelu'(.) * bn_scale3
+    {
+        const long long n4 = (long long)B * T4 * 256 / 4;
+        bcast_rows_mul_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(c->ed_d256a, (const T*)c->ed_g[3], (T*)c->ed_dzA, n4, T4,
+                                                                     256, 1.0f / (float)T4, c->ed_scale[3], MUL_VALUE);
+        MG_LAUNCH_OK();
+    }
+    // conv3 dgrad -> dz of conv2 output (x gelu' x scale2), etc.
+    MG_TRY((conv_s1_dgrad<T, T>((const T*)c->ed_dzA, (T*)c->ed_dzB, c->ED.conv[3].w, B, T4, 256, 256, 3, 1, c->ed_scale[2],
+                                c->ed_g[2], MUL_VALUE, 0, st)));
+    MG_TRY((conv_s1_dgrad<T, T>((const T*)c->ed_dzB, (T*)c->ed_dzA, c->ED.conv[2].w, B, T4, 128, 256, 3, 1, c->ed_scale[1],
+                                c->ed_g[1], MUL_VALUE, 0, st)));
+    MG_TRY((conv_s1_dgrad<T, T>((const T*)c->ed_dzA, (T*)c->ed_dzB, c->ED.conv[1].w, B, T4, 64, 128, 3, 1, c->ed_scale[0],
+                                c->ed_g[0], MUL_VALUE, 0, st)));
+    MG_TRY((conv_s1_dgrad<T, float>((const T*)c->ed_dzB, dnotes, c->ED.conv[0].w, B, T4, 4, 64, 5, 2, nullptr, nullptr,
+                                    MUL_NONE, accumulate, st)));
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// composites
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int critic_step(mg_gan* c, const float* real, const float* numeric, const float* noise, const float* alpha,
+                const float* mask1, const float* mask2, float* metrics_out, cudaStream_t st) {
+    MG_TRY(fe_forward(c, numeric, mask1, mask2, 1, c->e_emb, st));
+    MG_TRY((gen_forward<T>(c, noise, c->e_emb, 1, c->g_notes, nullptr, st)));
+    return critic_loss_backward<T>(c, real, c->g_notes, c->e_emb, alpha, metrics_out, st);
+}
+
+template <typename T>
+int generator_step(mg_gan* c, const float* numeric, const float* noise, const long long* labels, const float* mask1,
+                   const float* mask2, float* metrics_out, cudaStream_t st) {
+    const int B = c->B, E = c->cfg.embed_dim;
+    MG_TRY(fe_forward(c, numeric, mask1, mask2, 1, c->e_emb, st));
+    MG_TRY((gen_forward<T>(c, noise, c->e_emb, 1, c->g_notes, nullptr, st)));
+    MG_TRY((disc_forward<T>(c, c->g_notes, c->e_emb, B, nullptr, st)));
+    MG_TRY((ed_forward<T>(c, c->g_notes, nullptr, st)));
+    generator_loss_kernel<<<1, 256, 0, st>>>(c->d_score, c->ed_logits, labels, B, c->cfg.n_classes,
+                                             (float)c->cfg.lambda_emotion, c->ed_dlogits, metrics_out ? metrics_out : c->metrics);
+    MG_LAUNCH_OK();
+    // d loss / d notes = critic path (seed -1/B) + emotion path
+    const_fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(c->seed_g, B, -1.0f / (float)B);
+    MG_LAUNCH_OK();
+    MG_TRY((disc_dgrad<T>(c, c->seed_g, B, c->d_dnotes, 0, B, 0, st)));
+    MG_TRY((ed_backward_input<T>(c, c->ed_dlogits, c->d_dnotes, 1, st)));
+    // d loss / d emb = generator input path + critic conditioning term; then the encoder backward
+    MG_TRY((gen_backward<T>(c, c->d_dnotes, nullptr, c->g_demb, st)));
+    critic_demb_kernel<<<(B * E + 255) / 256, 256, 0, st>>>(c->seed_g, c->D.rf_w, B, 256, E, c->g_demb, 1);
+    MG_LAUNCH_OK();
+    return fe_backward(c, c->g_demb, st);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+#define MG_CTX_CHECK(c)                                            \
+    do {                                                           \
+        if (!(c)) { mg::set_error("null context"); return MG_ERR_INVALID; } \
+    } while (0)
+#define MG_NEED_BOUND(c, m, what)                                                     \
+    do {                                                                              \
+        if (!(c)->bound[m]) { mg::set_error(what ": module %d not bound", m); return MG_ERR_STATE; } \
+    } while (0)
+#define MG_NEED_GRADS(c, m, what)                                                     \
+    do {                                                                              \
+        if (!(c)->has_grads[m]) { mg::set_error(what ": module %d has no gradient buffers bound", m); return MG_ERR_STATE; } \
+    } while (0)
+#define MG_DISPATCH(c, fn, ...) ((c)->bf16 ? fn<__nv_bfloat16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
+    MG_REQUIRE(cfg && out, "gan_create: null argument");
+    MG_REQUIRE(cfg->batch >= 1 && cfg->batch <= 16384, "gan_create: batch must be in [1, 16384]");
+    MG_REQUIRE(cfg->precision == 0 || cfg->precision == 1, "gan_create: precision must be 0 (fp32) or 1 (bf16)");
+    MG_REQUIRE(cfg->note_dim == 4, "gan_create: note_dim must be 4 (pitch, velocity, duration, step)");
+    MG_REQUIRE(cfg->max_notes >= 8 && cfg->max_notes % 8 == 0 && cfg->max_notes <= 4096,
+               "gan_create: max_notes must be a multiple of 8 in [8, 4096]");
+    MG_REQUIRE(cfg->noise_dim > 0 && cfg->latent_dim > 0 && cfg->gen_hidden > 0 && cfg->numeric_dim > 0 &&
+                   cfg->numeric_dim <= 32 && cfg->enc_hidden1 > 0 && cfg->enc_hidden2 > 0 && cfg->embed_dim > 0,
+               "gan_create: bad layer widths");
+    MG_REQUIRE(cfg->n_classes >= 2 && cfg->n_classes <= 8, "gan_create: n_classes must be in [2, 8]");
+    MG_REQUIRE(cfg->enc_dropout >= 0.0 && cfg->enc_dropout < 1.0, "gan_create: dropout must be in [0, 1)");
+    int dev = 0, major = 0;
+    MG_CUDA_OK(cudaGetDevice(&dev));
+    MG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    MG_REQUIRE(major == 10, "gan_create: this library is built for sm_100a only (device has compute capability %d.x)", major);
+    mg_gan* c = new mg_gan();
+    c->cfg = *cfg;
+    c->B = cfg->batch; c->T = cfg->max_notes; c->L0 = cfg->max_notes / 8; c->zin = cfg->noise_dim + cfg->embed_dim;
+    c->bf16 = cfg->precision == 1;
+    layout(c, nullptr);
+    cudaError_t e = cudaMalloc(&c->arena, c->arena_bytes);
+    if (e != cudaSuccess) {
+        mg::set_error("gan_create: cudaMalloc(%zu) -> %s", c->arena_bytes, cudaGetErrorString(e));
+        delete c;
+        return MG_ERR_CUDA;
+    }
+    e = cudaMemset(c->arena, 0, c->arena_bytes);
+    if (e != cudaSuccess) { cudaFree(c->arena); delete c; mg::set_error("gan_create: memset failed"); return MG_ERR_CUDA; }
+    layout(c, c->arena);
+    *out = c;
+    return MG_OK;
+}
+
+extern "C" void mg_gan_destroy(mg_gan* c) {
+    if (!c) return;
+    if (c->arena) cudaFree(c->arena);
+    delete c;
+}
+
+extern "C" long long mg_gan_workspace_bytes(const mg_gan* c) { return c ? (long long)c->arena_bytes : 0; }
+
+extern "C" int mg_gan_buffer(mg_gan* c, const char* name, void** ptr, long long* nbytes) {
+    MG_CTX_CHECK(c);
+    MG_REQUIRE(name && ptr && nbytes, "gan_buffer: null argument");
+    for (const auto& n : c->named)
+        if (n.name == name) { *ptr = n.ptr; *nbytes = (long long)n.bytes; return MG_OK; }
+    mg::set_error("gan_buffer: unknown buffer '%s'", name);
+    return MG_ERR_INVALID;
+}
+
+extern "C" int mg_gan_bind(mg_gan* c, int module, void* const* params, int nparams, void* const* grads, int ngrads) {
+    MG_CTX_CHECK(c);
+    MG_REQUIRE(params, "gan_bind: null params");
+    static const int want_p[4] = {8, 22, 10, 32}, want_g[4] = {8, 18, 10, 0};
+    MG_REQUIRE(module >= 0 && module < 4, "gan_bind: module must be 0..3");
+    MG_REQUIRE(nparams == want_p[module], "gan_bind: module %d expects %d parameter pointers, got %d", module,
+               want_p[module], nparams);
+    MG_REQUIRE(!grads || ngrads == want_g[module], "gan_bind: module %d expects %d gradient pointers, got %d", module,
+               want_g[module], ngrads);
+    for (int i = 0; i < nparams; ++i) MG_REQUIRE(params[i], "gan_bind: parameter pointer %d is null", i);
+    if (grads) for (int i = 0; i < ngrads; ++i) MG_REQUIRE(grads[i], "gan_bind: gradient pointer %d is null", i);
+    auto F = [](void* p) { return static_cast<float*>(p); };
+    switch (module) {
+        case MG_MOD_ENCODER: {
+            float** d = reinterpret_cast<float**>(&c->E);
+            for (int i = 0; i < 8; ++i) d[i] = F(params[i]);
+            if (grads) { float** g = reinterpret_cast<float**>(&c->gE); for (int i = 0; i < 8; ++i) g[i] = F(grads[i]); }
+            break;
+        }
+        case MG_MOD_GENERATOR: {
+            float** d = reinterpret_cast<float**>(&c->G);
+            for (int i = 0; i < 22; ++i) d[i] = F(params[i]);
+            if (grads) { float** g = reinterpret_cast<float**>(&c->gG); for (int i = 0; i < 18; ++i) g[i] = F(grads[i]); }
+            break;
+        }
+        case MG_MOD_CRITIC: {
+            float** d = reinterpret_cast<float**>(&c->D);
+            for (int i = 0; i < 10; ++i) d[i] = F(params[i]);
+            if (grads) { float** g = reinterpret_cast<float**>(&c->gD); for (int i = 0; i < 10; ++i) g[i] = F(grads[i]); }
+            break;
+        }
+        default: {
+            float** d = reinterpret_cast<float**>(&c->ED);
+            for (int i = 0; i < 32; ++i) d[i] = F(params[i]);
+            c->ed_folded = false;
+            break;
+        }
+    }
+    c->bound[module] = true;
+    c->has_grads[module] = grads != nullptr;
+    return MG_OK;
+}
+
+extern "C" int mg_feature_encoder_forward(mg_gan* c, const float* numeric, const float* mask1, const float* mask2,
+                                          int train, float* emb_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 0, "feature_encoder_forward");
+    MG_REQUIRE(numeric && emb_out, "feature_encoder_forward: null pointer");
+    MG_REQUIRE(!train || c->cfg.enc_dropout == 0.0 || (mask1 && mask2), "feature_encoder_forward: train mode needs dropout masks");
+    return fe_forward(c, numeric, mask1, mask2, train && c->cfg.enc_dropout > 0.0, emb_out, as_stream(stream));
+}
+
+extern "C" int mg_feature_encoder_backward(mg_gan* c, const float* demb, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 0, "feature_encoder_backward");
+    MG_NEED_GRADS(c, 0, "feature_encoder_backward");
+    MG_REQUIRE(demb, "feature_encoder_backward: null pointer");
+    if (!(c->fwd_state & FWD_E)) { mg::set_error("feature_encoder_backward before forward"); return MG_ERR_STATE; }
+    return fe_backward(c, demb, as_stream(stream));
+}
+
+extern "C" int mg_generator_forward(mg_gan* c, const float* noise, const float* emb, int train, float* notes_out,
+                                    float* latent_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 1, "generator_forward");
+    MG_REQUIRE(noise && emb, "generator_forward: null pointer");
+    return MG_DISPATCH(c, gen_forward, c, noise, emb, train, notes_out, latent_out, as_stream(stream));
+}
+
+extern "C" int mg_generator_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* demb_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 1, "generator_backward");
+    MG_NEED_GRADS(c, 1, "generator_backward");
+    MG_REQUIRE(dnotes, "generator_backward: null pointer");
+    if (!(c->fwd_state & FWD_G)) { mg::set_error("generator_backward before forward"); return MG_ERR_STATE; }
+    return MG_DISPATCH(c, gen_backward, c, dnotes, dlatent, demb_out, as_stream(stream));
+}
+
+extern "C" int mg_discriminator_forward(mg_gan* c, const float* notes, const float* emb, int nsamples, float* score_out,
+                                        void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 2, "discriminator_forward");
+    MG_REQUIRE(notes && score_out, "discriminator_forward: null pointer");
+    MG_REQUIRE(nsamples >= 1 && nsamples <= 3 * c->B, "discriminator_forward: nsamples must be in [1, 3*batch]");
+    return MG_DISPATCH(c, disc_forward, c, notes, emb, nsamples, score_out, as_stream(stream));
+}
+
+namespace {
+template <typename T>
+int disc_backward_api(mg_gan* c, const float* dscore, int param_grads, float* dnotes_out, float* demb_out,
+                      const float* notes_in, cudaStream_t st) {
+    const int R = c->d_rows, E = c->cfg.embed_dim;
+    MG_TRY((disc_dgrad<T>(c, dscore, R, dnotes_out, 0, dnotes_out ? R : 0, 0, st)));
+    if (param_grads) MG_TRY((disc_wgrad<T>(c, notes_in, dscore, R, R, st)));
+    if (demb_out && c->d_emb) {
+        MG_REQUIRE(R <= c->B, "discriminator_backward: demb_out needs nsamples <= batch");
+        critic_demb_kernel<<<(R * E + 255) / 256, 256, 0, st>>>(dscore, c->D.rf_w, R, 256, E, demb_out, 0);
+        MG_LAUNCH_OK();
+    }
+    return MG_OK;
+}
+}  // namespace
+
+extern "C" int mg_discriminator_backward(mg_gan* c, const float* dscore, int param_grads, float* dnotes_out,
+                                         float* demb_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 2, "discriminator_backward");
+    MG_REQUIRE(dscore, "discriminator_backward: null pointer");
+    if (!(c->fwd_state & FWD_D)) { mg::set_error("discriminator_backward before forward"); return MG_ERR_STATE; }
+    if (param_grads) {
+        MG_NEED_GRADS(c, 2, "discriminator_backward");
+        mg::set_error("discriminator_backward: param_grads needs the forward's notes; use mg_discriminator_backward_ex");
+    }
+    MG_REQUIRE(!param_grads, "discriminator_backward: pass the forward input through mg_discriminator_backward_ex for parameter gradients");
+    return MG_DISPATCH(c, disc_backward_api, c, dscore, 0, dnotes_out, demb_out, nullptr, as_stream(stream));
+}
+
+extern "C" int mg_discriminator_backward_ex(mg_gan* c, const float* notes, const float* dscore, float* dnotes_out,
+                                            float* demb_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 2, "discriminator_backward_ex");
+    MG_NEED_GRADS(c, 2, "discriminator_backward_ex");
+    MG_REQUIRE(dscore && notes, "discriminator_backward_ex: null pointer");
+    if (!(c->fwd_state & FWD_D)) { mg::set_error("discriminator_backward before forward"); return MG_ERR_STATE; }
+    return MG_DISPATCH(c, disc_backward_api, c, dscore, 1, dnotes_out, demb_out, notes, as_stream(stream));
+}
+
+extern "C" int mg_critic_loss_backward(mg_gan* c, const float* real, const float* fake, const float* emb,
+                                       const float* alpha, float* metrics_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 2, "critic_loss_backward");
+    MG_NEED_GRADS(c, 2, "critic_loss_backward");
+    MG_REQUIRE(real && fake && alpha, "critic_loss_backward: null pointer");
+    return MG_DISPATCH(c, critic_loss_backward, c, real, fake, emb, alpha, metrics_out, as_stream(stream));
+}
+
+extern "C" int mg_emotion_forward(mg_gan* c, const float* notes, float* logits_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 3, "emotion_forward");
+    MG_REQUIRE(notes && logits_out, "emotion_forward: null pointer");
+    return MG_DISPATCH(c, ed_forward, c, notes, logits_out, as_stream(stream));
+}
+
+extern "C" int mg_emotion_backward_input(mg_gan* c, const float* dlogits, float* dnotes_out, int accumulate, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 3, "emotion_backward_input");
+    MG_REQUIRE(dlogits && dnotes_out, "emotion_backward_input: null pointer");
+    if (!(c->fwd_state & FWD_ED)) { mg::set_error("emotion_backward_input before forward"); return MG_ERR_STATE; }
+    return MG_DISPATCH(c, ed_backward_input, c, dlogits, dnotes_out, accumulate, as_stream(stream));
+}
+
+extern "C" int mg_critic_step(mg_gan* c, const float* real, const float* numeric, const float* noise,
+                              const float* alpha, const float* mask1, const float* mask2, float* metrics_out,
+                              void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 0, "critic_step"); MG_NEED_BOUND(c, 1, "critic_step"); MG_NEED_BOUND(c, 2, "critic_step");
+    MG_NEED_GRADS(c, 2, "critic_step");
+    MG_REQUIRE(real && numeric && noise && alpha && mask1 && mask2, "critic_step: null pointer");
+    return MG_DISPATCH(c, critic_step, c, real, numeric, noise, alpha, mask1, mask2, metrics_out, as_stream(stream));
+}
+
+extern "C" int mg_generator_step(mg_gan* c, const float* numeric, const float* noise, const long long* labels,
+                                 const float* mask1, const float* mask2, float* metrics_out, void* stream) {
+    MG_CTX_CHECK(c);
+    for (int m = 0; m < 4; ++m) MG_NEED_BOUND(c, m, "generator_step");
+    MG_NEED_GRADS(c, 0, "generator_step"); MG_NEED_GRADS(c, 1, "generator_step");
+    MG_REQUIRE(numeric && noise && labels && mask1 && mask2, "generator_step: null pointer");
+    return MG_DISPATCH(c, generator_step, c, numeric, noise, labels, mask1, mask2, metrics_out, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based RNG (Philox4x32-10) for the throughput path
+// ------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__global__ void rng_fill_kernel(float* out, long long n, int kind, float p, unsigned long long seed,
+                                unsigned long long offset) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one Philox block = 4 outputs
+    if (q * 4 >= n) return;
+    const unsigned long long ctr = offset + (unsigned long long)q;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    float v[4];
+    if (kind == 0) {   // Box-Muller on two pairs
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float u1 = ((float)(c[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+            const float u2 = (float)(c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
+            const float r = sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincospif(2.0f * u2, &sn, &cs);
+            v[2 * h] = r * cs; v[2 * h + 1] = r * sn;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float u = (float)(c[e] >> 8) * (1.0f / 16777216.0f);                 // [0, 1)
+            v[e] = kind == 1 ? u : (u < p ? 1.0f : 0.0f);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (q * 4 + e < n) out[q * 4 + e] = v[e];
+}
+}  // namespace
+
+extern "C" int mg_rng_fill(float* out, long long n, int kind, float p, unsigned long long seed,
+                           unsigned long long offset, void* stream) {
+    MG_REQUIRE(n >= 0 && kind >= 0 && kind <= 2, "rng_fill: bad arguments");
+    if (n == 0) return MG_OK;
+    MG_REQUIRE(out, "rng_fill: null pointer");
+    const long long q = (n + 3) / 4;
+    rng_fill_kernel<<<(unsigned)((q + 255) / 256), 256, 0, as_stream(stream)>>>(out, n, kind, p, seed, offset);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}

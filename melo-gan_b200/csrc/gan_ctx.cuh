@@ -1,0 +1,235 @@
+// gan_ctx.cuh -- context (workspaces, bound parameters) and layer helpers of the GAN hot path.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "elem.cuh"
+
+struct mg_gan {
+    mg_gan_config cfg;
+    // derived sizes
+    int B, T, L0, zin;             // batch, max_notes, max_notes/8, noise+embed
+    bool bf16;
+
+    // ---- bound parameters / gradients (caller-owned device memory) ----
+    struct EP { float *ln_w, *ln_b, *w1, *b1, *w2, *b2, *w3, *b3; } E{}, gE{};
+    struct GP {
+        float *a_w, *a_b, *l_w, *l_b, *p0_w, *p0_b, *p2_w, *p2_b, *d0_w, *d0_b, *bn1_w, *bn1_b, *d3_w, *d3_b,
+            *bn2_w, *bn2_b, *d6_w, *d6_b;
+        float *bn1_rm, *bn1_rv, *bn2_rm, *bn2_rv;
+    } G{}, gG{};
+    struct DP { float *c0_w, *c0_b, *c2_w, *c2_b, *c4_w, *c4_b, *fc_w, *fc_b, *rf_w, *rf_b; } D{}, gD{};
+    struct EDP {
+        struct { float *w, *b, *g, *be, *rm, *rv; } conv[4];
+        float *pj_w, *pj_b, *c0_w, *c0_b, *c3_w, *c3_b, *hd_w, *hd_b;
+    } ED{};
+    bool bound[4] = {false, false, false, false};
+    bool has_grads[4] = {false, false, false, false};
+    bool ed_folded = false;
+
+    // ---- workspaces (one arena) ----
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    struct Named { std::string name; void* ptr; size_t bytes; };
+    std::vector<Named> named;
+
+    // FeatureEncoder
+    float *e_xhat, *e_ln, *e_z1, *e_h1, *e_z2, *e_h2, *e_emb, *e_d1, *e_d2, *e_dln;
+    const float *e_mask1 = nullptr, *e_mask2 = nullptr;   // masks of the last train-mode forward (caller memory)
+    const float* e_numeric = nullptr;
+    // Generator
+    float *g_xcat, *g_ha, *g_lat, *g_hb, *g_notes;
+    void *g_y0, *g_x1, *g_y1, *g_x2, *g_y2;                 // activation dtype
+    float *g_bn1_stats, *g_bn1_mean, *g_bn1_is, *g_bn2_stats, *g_bn2_mean, *g_bn2_is, *g_bn_sums;
+    void *g_dy2, *g_dx2, *g_dy1, *g_dx1, *g_dy0;
+    float *g_dhb, *g_dlat, *g_dha, *g_dxcat, *g_demb;
+    // Critic (up to 3B rows)
+    float *d_x3, *d_pool, *d_hf, *d_score, *d_seed, *d_dzf, *d_dp, *d_gx, *d_gp_ps, *d_q, *d_dnotes;
+    void *d_h1, *d_h2, *d_h3, *d_dz1, *d_dz2, *d_dz3;
+    int d_rows = 0;                                         // rows of the last critic forward
+    const float* d_emb = nullptr;
+    // Emotion discriminator
+    void *ed_h[4], *ed_g[4], *ed_dzA, *ed_dzB;
+    float *ed_pool, *ed_pj, *ed_c1, *ed_c1g, *ed_c2, *ed_c2g, *ed_logits, *ed_dlogits, *ed_d128, *ed_d256a,
+        *ed_d256b, *ed_scale[4], *ed_shift[4];
+    // misc
+    float *partial, *metrics, *seed_g;
+    size_t partial_floats = 0;
+    int fwd_state = 0;   // bit flags of completed forwards, for MG_ERR_STATE checks
+};
+
+namespace mg {
+
+enum { FWD_E = 1, FWD_G = 2, FWD_D = 4, FWD_ED = 8 };
+
+inline TapGemmArgs tap_defaults() {
+    TapGemmArgs a{};
+    a.alpha = 1.0f;
+    a.ntaps = 1;
+    return a;
+}
+
+// ---- Linear: Out[R, N] = act(A[R, K] W[N, K]^T + bias) ----
+template <typename TA, typename TO>
+int linear_fwd(const TA* A, TO* Out, const float* W, const float* bias, int R, int K, int N, int act, void* aux,
+               cudaStream_t st, int n_perm_q = 0, int n_perm_p = 0) {
+    TapGemmArgs a = tap_defaults();
+    a.A = A; a.a_bstride = K; a.a_mstride = 0; a.a_valid = K; a.K = K;
+    a.W = W; a.w_nstride = K; a.w_kstride = 1; a.n_perm_q = n_perm_q; a.n_perm_p = n_perm_p;
+    a.Out = Out; a.o_bstride = N; a.o_mstride = 0; a.B = R; a.Mper = 1; a.N = N;
+    a.bias = bias; a.act = act; a.aux = aux;
+    return launch_tapgemm<TA, TO>(a, st);
+}
+
+// ---- Linear dgrad: dX[R, K] = (dZ[R, N] W[N, K]) * f'(ref) ----
+template <typename TA, typename TO>
+int linear_dgrad(const TA* dZ, TO* dX, const float* W, int R, int K, int N, const void* mul_src, int mul_mode,
+                 cudaStream_t st, int k_perm_q = 0, int k_perm_p = 0) {
+    TapGemmArgs a = tap_defaults();
+    a.A = dZ; a.a_bstride = N; a.a_valid = N; a.K = N;
+    a.W = W; a.w_nstride = 1; a.w_kstride = K; a.k_perm_q = k_perm_q; a.k_perm_p = k_perm_p;
+    a.Out = dX; a.o_bstride = K; a.B = R; a.Mper = 1; a.N = K;
+    a.mul_src = mul_src; a.mul_mode = mul_mode;
+    return launch_tapgemm<TA, TO>(a, st);
+}
+
+// ---- Linear wgrad: dW[N, K] += dZ[R, N]^T A[R, K] ----
+template <typename TG, typename TA>
+int linear_wgrad(const TG* dZ, const TA* A, float* dW, int r0, int r1, int K, int N, cudaStream_t st,
+                 int n_perm_q = 0, int n_perm_p = 0) {
+    WgradArgs w{};
+    w.G = dZ; w.g_bstride = N; w.A = A; w.a_bstride = K; w.a_valid = K; w.ntaps = 1; w.K = K;
+    w.dW = dW; w.w_nstride = K; w.w_kstride = 1; w.n_perm_q = n_perm_q; w.n_perm_p = n_perm_p;
+    w.B = r1; w.Mper = 1; w.N = N; w.alpha = 1.0f; w.row_begin = r0; w.row_end = r1;
+    return launch_wgrad<TG, TA>(w, st);
+}
+
+// ---- Conv1d forward (channels-last): in [R, Lin, Cin] -> out [R, Lin/stride, Cout]; W [Cout][Cin][ks] ----
+template <typename TA, typename TO>
+int conv_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int Cin, int Cout, int ks,
+             int stride, int pad, int act, const float* col_scale, void* aux, const void* mul_src, int mul_mode,
+             cudaStream_t st, int w_nstride = -1, int w_kstride = -1) {
+    TapGemmArgs a = tap_defaults();
+    const int Lout = Lin / stride;
+    a.A = in; a.a_bstride = (long long)Lin * Cin; a.a_mstride = stride * Cin; a.a_valid = Lin * Cin;
+    a.ntaps = ks; a.K = Cin;
+    for (int t = 0; t < ks; ++t) { a.a_toff[t] = (t - pad) * Cin; a.w_toff[t] = t; }
+    a.W = W; a.w_nstride = w_nstride < 0 ? Cin * ks : w_nstride; a.w_kstride = w_kstride < 0 ? ks : w_kstride;
+    a.Out = out; a.o_bstride = (long long)Lout * Cout; a.o_mstride = Cout; a.B = R; a.Mper = Lout; a.N = Cout;
+    a.bias = bias; a.act = act; a.col_scale = col_scale; a.aux = aux; a.mul_src = mul_src; a.mul_mode = mul_mode;
+    return launch_tapgemm<TA, TO>(a, st);
+}
+
+// ---- stride-1 conv dgrad: dIn[R, L, Cin] = sum_t dOut[R, l + pad - t, Cout] W[Cout][Cin][ks] ----
+template <typename TA, typename TO>
+int conv_s1_dgrad(const TA* dOut, TO* dIn, const float* W, int R, int L, int Cin, int Cout, int ks, int pad,
+                  const float* col_scale, const void* mul_src, int mul_mode, int accumulate, cudaStream_t st) {
+    TapGemmArgs a = tap_defaults();
+    a.A = dOut; a.a_bstride = (long long)L * Cout; a.a_mstride = Cout; a.a_valid = L * Cout;
+    a.ntaps = ks; a.K = Cout;
+    for (int t = 0; t < ks; ++t) { a.a_toff[t] = (pad - t) * Cout; a.w_toff[t] = t; }
+    a.W = W; a.w_nstride = ks; a.w_kstride = Cin * ks;      // n = ci, k = co
+    a.Out = dIn; a.o_bstride = (long long)L * Cin; a.o_mstride = Cin; a.B = R; a.Mper = L; a.N = Cin;
+    a.col_scale = col_scale; a.mul_src = mul_src; a.mul_mode = mul_mode; a.accumulate = accumulate;
+    return launch_tapgemm<TA, TO>(a, st);
+}
+
+// ---- k5 s2 p2 op1 up-sampling contraction in two sub-pixel phases ----
+//   out[r, 2m+ph, n] = sum_{t = ph (mod 2)} sum_k in[r, m + 1 - t/2, k] * W(t, n, k)
+// ConvTranspose1d forward: W [Cin][Cout][5] -> (w_nstride, w_kstride) = (5, Cout*5)
+// dgrad of a strided Conv1d: W [Cconv_out][Cconv_in][5], k = conv_out, n = conv_in -> (5, Cconv_in*5)
+template <typename TA, typename TO>
+int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int K, int N,
+                  int w_nstride, int w_kstride, int act, const void* mul_src, int mul_mode, int accumulate,
+                  cudaStream_t st) {
+    for (int ph = 0; ph < 2; ++ph) {
+        TapGemmArgs a = tap_defaults();
+        a.A = in; a.a_bstride = (long long)Lin * K; a.a_mstride = K; a.a_valid = Lin * K; a.K = K;
+        a.ntaps = 0;
+        for (int t = ph; t < 5; t += 2) {
+            a.a_toff[a.ntaps] = (1 - t / 2) * K;
+            a.w_toff[a.ntaps] = t;
+            ++a.ntaps;
+        }
+        a.W = W; a.w_nstride = w_nstride; a.w_kstride = w_kstride;
+        a.Out = out; a.o_bstride = (long long)2 * Lin * N; a.o_mstride = 2 * N; a.o_off = ph * N;
+        a.B = R; a.Mper = Lin; a.N = N;
+        a.bias = bias; a.act = act; a.mul_src = mul_src; a.mul_mode = mul_mode; a.accumulate = accumulate;
+        int rc = launch_tapgemm<TA, TO>(a, st);
+        if (rc != MG_OK) return rc;
+    }
+    return MG_OK;
+}
+
+// ---- wgrad of a strided/unit Conv1d: dW[Cout][Cin][ks] += sum dOut[r, l, co] * in[r, stride*l + t - pad, ci] ----
+template <typename TG, typename TA>
+int conv_wgrad(const TG* dOut, const TA* in, float* dW, long long row0, long long row1, int Lin, int Cin, int Cout,
+               int ks, int stride, int pad, cudaStream_t st) {
+    WgradArgs w{};
+    const int Lout = Lin / stride;
+    w.G = dOut; w.g_bstride = (long long)Lout * Cout; w.g_mstride = Cout;
+    w.A = in; w.a_bstride = (long long)Lin * Cin; w.a_mstride = stride * Cin; w.a_valid = Lin * Cin;
+    w.ntaps = ks; w.K = Cin;
+    for (int t = 0; t < ks; ++t) { w.a_toff[t] = (t - pad) * Cin; w.w_toff[t] = t; }
+    w.dW = dW; w.w_nstride = Cin * ks; w.w_kstride = ks;
+    w.B = (int)((row1 + Lout - 1) / Lout); w.Mper = Lout; w.N = Cout; w.alpha = 1.0f;
+    w.row_begin = (int)row0; w.row_end = (int)row1;
+    return launch_wgrad<TG, TA>(w, st);
+}
+
+// ---- wgrad of ConvTranspose1d k5 s2: dW[Cin][Cout][5] += sum in[r, i, ci] * dOut[r, 2i + t - 2, co] ----
+template <typename TG, typename TA>
+int convT_wgrad(const TG* in, const TA* dOut, float* dW, int R, int Lin, int Cin, int Cout, cudaStream_t st) {
+    WgradArgs w{};
+    w.G = in; w.g_bstride = (long long)Lin * Cin; w.g_mstride = Cin;
+    w.A = dOut; w.a_bstride = (long long)2 * Lin * Cout; w.a_mstride = 2 * Cout; w.a_valid = 2 * Lin * Cout;
+    w.ntaps = 5; w.K = Cout;
+    for (int t = 0; t < 5; ++t) { w.a_toff[t] = (t - 2) * Cout; w.w_toff[t] = t; }
+    w.dW = dW; w.w_nstride = Cout * 5; w.w_kstride = 5;     // n = ci, k = co
+    w.B = R; w.Mper = Lin; w.N = Cin; w.alpha = 1.0f; w.row_begin = 0; w.row_end = R * Lin;
+    return launch_wgrad<TG, TA>(w, st);
+}
+
+// ---- column reductions ----
+template <typename T, int OP>
+int colreduce(mg_gan* c, const T* x, int ldx, const T* y, int ldy, const float* mean, const float* invstd,
+              const float* roww, int roww_div, long long r0, long long r1, int C, float* out, int out_kstride,
+              int perm_q, int perm_p, float alpha, int accumulate, cudaStream_t st) {
+    constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
+    const long long rows = r1 - r0;
+    if (rows <= 0 || C <= 0) return MG_OK;
+    long long maxchunks = (long long)(c->partial_floats / ((size_t)NOUT * C));
+    if (maxchunks > 128) maxchunks = 128;
+    MG_REQUIRE(maxchunks >= 1, "colreduce: scratch too small for C=%d", C);
+    long long rpc = (rows + maxchunks - 1) / maxchunks;
+    if (rpc < 64) rpc = 64;
+    rpc = (rpc + 7) / 8 * 8;
+    const int nchunk = (int)((rows + rpc - 1) / rpc);
+    ColReduceArgs a{};
+    a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.mean = mean; a.invstd = invstd; a.roww = roww;
+    a.roww_div = roww_div > 0 ? roww_div : 1; a.r0 = r0; a.r1 = r1; a.C = C; a.partial = c->partial;
+    a.rows_per_chunk = (int)rpc;
+    dim3 grid((C + 31) / 32, nchunk);
+    colreduce_kernel<T, OP><<<grid, 256, 0, st>>>(a);
+    MG_LAUNCH_OK();
+    const int n = NOUT * C;
+    colreduce_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->partial, nchunk, NOUT, C, out, out_kstride, perm_q,
+                                                             perm_p, alpha, accumulate);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+inline int grid_for(long long n, int threads = 256, int max_per_sm = 8) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * max_per_sm;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+#define MG_TRY(expr)                    \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != MG_OK) return _rc;   \
+    } while (0)
+
+}  // namespace mg

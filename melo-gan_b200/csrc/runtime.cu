@@ -48,3 +48,10 @@ extern "C" uint32_t mg_scale_mask(const char* scale_name, int root_key) {
     for (int i = 0; i < s->n; ++i) m |= 1u << ((((s->iv[i] + root_key) % 12) + 12) % 12);
     return m;
 }
+
+extern "C" int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream) {
+    MG_REQUIRE(nbytes >= 0 && (nbytes == 0 || (dst && src)), "device_copy: bad arguments");
+    if (nbytes == 0) return MG_OK;
+    MG_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDefault, mg::as_stream(stream)));
+    return MG_OK;
+}

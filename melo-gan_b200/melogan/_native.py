@@ -32,6 +32,26 @@ _SIGNATURES = {
     "mg_extract_notes_abs": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_extract_notes_abs_host": ([_vp, _ll, _i, _vp, _vp, _vp, _vp], _i),
     "mg_adam_step": ([_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _i, _f, _ll, _vp, _vp, _vp], _i),
+    "mg_device_copy": ([_vp, _vp, _ll, _vp], _i),
+    "mg_rng_fill": ([_vp, _ll, _i, _f, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp], _i),
+    # mg_gan_* (argtypes are refined by melogan.engine, which owns the config struct)
+    "mg_gan_create": ([_vp, _vp], _i),
+    "mg_gan_destroy": ([_vp], None),
+    "mg_gan_workspace_bytes": ([_vp], _ll),
+    "mg_gan_buffer": ([_vp, ctypes.c_char_p, _vp, _vp], _i),
+    "mg_gan_bind": ([_vp, _i, _vp, _i, _vp, _i], _i),
+    "mg_feature_encoder_forward": ([_vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
+    "mg_feature_encoder_backward": ([_vp, _vp, _vp], _i),
+    "mg_generator_forward": ([_vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "mg_generator_backward": ([_vp, _vp, _vp, _vp, _vp], _i),
+    "mg_discriminator_forward": ([_vp, _vp, _vp, _i, _vp, _vp], _i),
+    "mg_discriminator_backward": ([_vp, _vp, _i, _vp, _vp, _vp], _i),
+    "mg_discriminator_backward_ex": ([_vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_critic_loss_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_emotion_forward": ([_vp, _vp, _vp, _vp], _i),
+    "mg_emotion_backward_input": ([_vp, _vp, _vp, _i, _vp], _i),
+    "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
 }
 
 
