@@ -199,6 +199,14 @@ int mg_critic_step(mg_gan* ctx, const float* real, const float* numeric, const f
 int mg_generator_step(mg_gan* ctx, const float* numeric, const float* noise, const long long* labels,
                       const float* mask1, const float* mask2, float* metrics_out, void* stream);
 
+/* Instrumentation used by bench.py: number of kernels this library has launched so far, and a probe that
+ * brackets every launch of one kernel family (1 = SIMT tap-GEMM, 2 = SIMT wgrad, 3 = tcgen05 GEMM,
+ * 4 = tcgen05 wgrad, 5 = note extraction, 6 = Adam) with CUDA events on the launching stream.
+ * mg_probe_end: out[0] launches, out[1] total ms, out[2] algorithmic FLOPs, out[3] algorithmic bytes. */
+long long mg_launch_count(void);
+int mg_probe_begin(int family);
+int mg_probe_end(double* out);
+
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
 
@@ -209,6 +217,11 @@ int mg_gan_buffer(mg_gan* ctx, const char* name, void** ptr, long long* nbytes);
  * kind 0 = normal, 1 = uniform [0,1), 2 = Bernoulli(p) as 0/1 floats. */
 int mg_rng_fill(float* out, long long n, int kind, float p, unsigned long long seed, unsigned long long offset,
                 void* stream);
+/* CUDA-graph-safe form: the Philox offset is (*counter_dev) * counter_mul, read on the device at run
+ * time; mg_counter_add advances the counter inside the same stream/graph. */
+int mg_rng_fill_counter(float* out, long long n, int kind, float p, unsigned long long seed,
+                        const unsigned long long* counter_dev, unsigned long long counter_mul, void* stream);
+int mg_counter_add(unsigned long long* counter_dev, unsigned long long inc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,7 @@ extern "C" int mg_adam_step(float* param, const float* grad, float* exp_avg, flo
     const long long cap = (long long)mg::num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    mg::ProbeScope probe(mg::PROBE_ADAM, 0.0, 28.0 * (double)n + (bf16_copy ? 2.0 * (double)n : 0.0), st);
     adam_kernel<<<(int)blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
                                              (float)(1.0 - beta2), (float)eps, decay_mul,
                                              grad_scale, sc, reinterpret_cast<__nv_bfloat16*>(bf16_copy));

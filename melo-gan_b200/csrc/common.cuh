@@ -11,6 +11,17 @@ namespace mg {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+void count_launch();   // every kernel launch of this library goes through MG_LAUNCH_OK()
+
+// Optional per-kernel-family probe (bench.py roofline): CUDA events around each launch of one family.
+enum ProbeFamily { PROBE_NONE = 0, PROBE_TAPGEMM = 1, PROBE_WGRAD = 2, PROBE_TC_GEMM = 3, PROBE_TC_WGRAD = 4,
+                   PROBE_NOTES = 5, PROBE_ADAM = 6 };
+struct ProbeScope {
+    bool on = false;
+    cudaStream_t st;
+    ProbeScope(int family, double flops, double bytes, cudaStream_t stream);
+    ~ProbeScope();
+};
 
 #define MG_CUDA_OK(expr)                                                                    \
     do {                                                                                    \
@@ -29,7 +40,11 @@ int num_sms();
         }                                     \
     } while (0)
 
-#define MG_LAUNCH_OK()  MG_CUDA_OK(cudaGetLastError())
+#define MG_LAUNCH_OK()                      \
+    do {                                    \
+        MG_CUDA_OK(cudaGetLastError());     \
+        mg::count_launch();                 \
+    } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -821,9 +821,11 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
 }
 __global__ void rng_fill_kernel(float* out, long long n, int kind, float p, unsigned long long seed,
-                                unsigned long long offset) {
+                                unsigned long long offset, const unsigned long long* counter_dev,
+                                unsigned long long counter_mul) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one Philox block = 4 outputs
     if (q * 4 >= n) return;
+    if (counter_dev) offset += *counter_dev * counter_mul;
     const unsigned long long ctr = offset + (unsigned long long)q;
     uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -859,7 +861,31 @@ extern "C" int mg_rng_fill(float* out, long long n, int kind, float p, unsigned 
     if (n == 0) return MG_OK;
     MG_REQUIRE(out, "rng_fill: null pointer");
     const long long q = (n + 3) / 4;
-    rng_fill_kernel<<<(unsigned)((q + 255) / 256), 256, 0, as_stream(stream)>>>(out, n, kind, p, seed, offset);
+    rng_fill_kernel<<<(unsigned)((q + 255) / 256), 256, 0, as_stream(stream)>>>(out, n, kind, p, seed, offset, nullptr, 0);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+namespace {
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+}  // namespace
+
+extern "C" int mg_rng_fill_counter(float* out, long long n, int kind, float p, unsigned long long seed,
+                                   const unsigned long long* counter_dev, unsigned long long counter_mul,
+                                   void* stream) {
+    MG_REQUIRE(n >= 0 && kind >= 0 && kind <= 2 && counter_dev, "rng_fill_counter: bad arguments");
+    if (n == 0) return MG_OK;
+    MG_REQUIRE(out, "rng_fill_counter: null pointer");
+    const long long q = (n + 3) / 4;
+    rng_fill_kernel<<<(unsigned)((q + 255) / 256), 256, 0, as_stream(stream)>>>(out, n, kind, p, seed, 0, counter_dev,
+                                                                                counter_mul);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+extern "C" int mg_counter_add(unsigned long long* counter_dev, unsigned long long inc, void* stream) {
+    MG_REQUIRE(counter_dev, "counter_add: null pointer");
+    counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter_dev, inc);
     MG_LAUNCH_OK();
     return MG_OK;
 }

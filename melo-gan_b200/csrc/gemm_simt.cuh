@@ -305,6 +305,8 @@ int launch_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     for (int t = 0; t < P.ntaps; ++t) vec = vec && (P.a_toff[t] % 4 == 0);
     if (P.mul_src) vec = vec && (((uintptr_t)P.mul_src) % (4 * eo) == 0);
     if (P.aux) vec = vec && (((uintptr_t)P.aux) % (4 * eo) == 0);
+    ProbeScope probe(PROBE_TAPGEMM, 2.0 * (double)rows * P.N * P.ntaps * P.K,
+                     (double)rows * (P.K * ea + P.N * eo), st);
     if (P.N <= 8) {
         dim3 grid((unsigned)((rows + 511) / 512), (unsigned)((P.N + 7) / 8));
         if (vec) tapgemm_kernel<TA, TO, 512, 8, 4, 4, 1, true><<<grid, 256, 0, st>>>(P);
@@ -437,6 +439,7 @@ int launch_wgrad(const WgradArgs& P, cudaStream_t st) {
                (P.a_valid % 4 == 0) && (P.g_mstride % 4 == 0) && (P.g_bstride % 4 == 0) && (P.g_off % 4 == 0) &&
                (((uintptr_t)P.A) % (4 * sizeof(TA)) == 0) && (((uintptr_t)P.G) % (4 * sizeof(TG)) == 0);
     for (int t = 0; t < P.ntaps; ++t) vec = vec && (P.a_toff[t] % 4 == 0);
+    ProbeScope probe(PROBE_WGRAD, 2.0 * (double)nrows * P.N * Ktot, (double)nrows * (P.N * sizeof(TG) + P.K * sizeof(TA)), st);
     dim3 grid(tn, tk, (unsigned)splits);
     if (vec) wgrad_kernel<TG, TA, true><<<grid, 256, 0, st>>>(P, rps);
     else wgrad_kernel<TG, TA, false><<<grid, 256, 0, st>>>(P, rps);

@@ -243,6 +243,7 @@ extern "C" int mg_extract_notes_gan(const float* rolls, long long nrolls, int nr
     P.counts = counts; P.pitch = pitch; P.velocity = velocity; P.start = start; P.end = end;
     const long long ntiles = (nrolls + kRollsPerCta - 1) / kRollsPerCta;
     const int grid = (int)((ntiles < (long long)mg::num_sms() * 2) ? ntiles : (long long)mg::num_sms() * 2);
+    mg::ProbeScope probe(mg::PROBE_NOTES, 0.0, (double)nrolls * (nrows * 16.0 + 4.0), mg::as_stream(stream));
     extract_notes_gan_kernel<<<grid, kThreads, kGanSmem, mg::as_stream(stream)>>>(P);
     MG_LAUNCH_OK();
     return MG_OK;

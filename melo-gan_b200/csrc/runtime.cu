@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mg {
@@ -23,7 +26,59 @@ int num_sms() {
     }
     return n;
 }
+
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---- probe ----
+static int g_probe_family = PROBE_NONE;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_probe_events;
+static double g_probe_flops = 0.0, g_probe_bytes = 0.0;
+static size_t g_probe_used = 0;
+
+ProbeScope::ProbeScope(int family, double flops, double bytes, cudaStream_t stream) : st(stream) {
+    if (family != g_probe_family || g_probe_family == PROBE_NONE) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    if (g_probe_used == g_probe_events.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        g_probe_events.push_back({a, b});
+    }
+    cudaEventRecord(g_probe_events[g_probe_used].first, stream);
+    g_probe_flops += flops; g_probe_bytes += bytes;
+    on = true;
+}
+ProbeScope::~ProbeScope() {
+    if (!on) return;
+    cudaEventRecord(g_probe_events[g_probe_used].second, st);
+    ++g_probe_used;
+}
 }  // namespace mg
+
+extern "C" long long mg_launch_count(void) { return mg::g_launches; }
+
+extern "C" int mg_probe_begin(int family) {
+    mg::g_probe_family = family;
+    mg::g_probe_used = 0;
+    mg::g_probe_flops = mg::g_probe_bytes = 0.0;
+    return MG_OK;
+}
+
+// out[0] = launches, out[1] = total ms, out[2] = total algorithmic flops, out[3] = total algorithmic bytes
+extern "C" int mg_probe_end(double* out) {
+    MG_REQUIRE(out, "probe_end: null pointer");
+    double ms = 0.0;
+    for (size_t i = 0; i < mg::g_probe_used; ++i) {
+        MG_CUDA_OK(cudaEventSynchronize(mg::g_probe_events[i].second));
+        float t = 0.f;
+        MG_CUDA_OK(cudaEventElapsedTime(&t, mg::g_probe_events[i].first, mg::g_probe_events[i].second));
+        ms += t;
+    }
+    out[0] = (double)mg::g_probe_used; out[1] = ms; out[2] = mg::g_probe_flops; out[3] = mg::g_probe_bytes;
+    mg::g_probe_family = mg::PROBE_NONE;
+    return MG_OK;
+}
 
 extern "C" const char* mg_last_error(void) { return mg::g_err; }
 extern "C" int mg_abi_version(void) { return 1; }
