@@ -207,6 +207,11 @@ long long mg_launch_count(void);
 int mg_probe_begin(int family);
 int mg_probe_end(double* out);
 
+/* bf16 mode only: 1 (default) routes tensor-core-shaped contractions to the tcgen05 kernels, 0 keeps them on
+ * the CUDA-core kernels (same bf16 operands; used for A/B parity tests).  Returns the previous setting.
+ * The environment variable MELOGAN_DISABLE_TC=1 sets the initial value to 0. */
+int mg_tc_enable(int on);
+
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
 

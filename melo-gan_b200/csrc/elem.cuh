@@ -29,7 +29,7 @@ struct ColReduceArgs {
     int rows_per_chunk;
 };
 
-template <typename T, int OP>
+template <typename T, typename TY, int OP>
 __global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
     constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
     __shared__ float red[NOUT][8][33];
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
     float a0 = 0.f, a1 = 0.f;
     if (c < P.C) {
         const T* x = static_cast<const T*>(P.x);
-        const T* y = static_cast<const T*>(P.y);
+        const TY* y = static_cast<const TY*>(P.y);
         float mu = 0.f, is = 0.f;
         if (OP == COL_BN_BWD) { mu = P.mean[c]; is = P.invstd[c]; }
         for (long long r = rb + ry; r < re; r += 8) {
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const T* __restrict_
 }
 
 // dx = gamma*invstd*(dy - s1/R - xhat*s2/R), sums = [s1 | s2] (dy already carries the ReLU mask)
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+template <typename T, typename TD>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ x, const TD* __restrict__ dy,
                                                            T* __restrict__ dx, long long n4, int C, float invR,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ invstd,

@@ -59,7 +59,7 @@ void layout(mg_gan* c, char* base) {
     c->g_xcat = b.get<float>("g.xcat", B * c->zin);
     c->g_ha = b.get<float>("g.ha", B * f.gen_hidden);
     c->g_lat = b.get<float>("g.latent", B * f.latent_dim);
-    c->g_hb = b.get<float>("g.hb", B * 512);
+    c->g_hb = act("g.hb", B * 512);
     c->g_notes = b.get<float>("g.notes", B * T * 4);
     c->g_y0 = act("g.y0", B * L0 * 256);
     c->g_x1 = act("g.x1", B * 2 * L0 * 128);
@@ -73,9 +73,9 @@ void layout(mg_gan* c, char* base) {
     c->g_bn2_mean = b.get<float>("g.bn2.mean", 64);
     c->g_bn2_is = b.get<float>("g.bn2.invstd", 64);
     c->g_bn_sums = b.get<float>("g.bn.sums", 256);
-    c->g_dy2 = act("g.dy2", B * 4 * L0 * 64);
+    c->g_dy2 = b.get<float>("g.dy2", B * 4 * L0 * 64);     // float32: BatchNorm backward subtracts means
     c->g_dx2 = act("g.dx2", B * 4 * L0 * 64);
-    c->g_dy1 = act("g.dy1", B * 2 * L0 * 128);
+    c->g_dy1 = b.get<float>("g.dy1", B * 2 * L0 * 128);
     c->g_dx1 = act("g.dx1", B * 2 * L0 * 128);
     c->g_dy0 = act("g.dy0", B * L0 * 256);
     c->g_dhb = b.get<float>("g.dhb", B * 512);
@@ -238,10 +238,10 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
     }
     MG_TRY((linear_fwd<float, float>(c->g_xcat, c->g_ha, c->G.a_w, c->G.a_b, B, c->zin, f.gen_hidden, ACT_RELU, nullptr, st)));
     MG_TRY((linear_fwd<float, float>(c->g_ha, c->g_lat, c->G.l_w, c->G.l_b, B, f.gen_hidden, f.latent_dim, ACT_NONE, nullptr, st)));
-    MG_TRY((linear_fwd<float, float>(c->g_lat, c->g_hb, c->G.p0_w, c->G.p0_b, B, f.latent_dim, 512, ACT_RELU, nullptr, st)));
+    MG_TRY((linear_fwd<float, T>(c->g_lat, (T*)c->g_hb, c->G.p0_w, c->G.p0_b, B, f.latent_dim, 512, ACT_RELU, nullptr, st)));
     // pre.2 (+ReLU) written channels-last: logical column n = l*256 + c  <->  weight row c*L0 + l
-    MG_TRY((linear_fwd<float, T>(c->g_hb, (T*)c->g_y0, c->G.p2_w, c->G.p2_b, B, 512, 256 * L0, ACT_RELU, nullptr, st,
-                                 256, L0)));
+    MG_TRY((linear_fwd<T, T>((const T*)c->g_hb, (T*)c->g_y0, c->G.p2_w, c->G.p2_b, B, 512, 256 * L0, ACT_RELU, nullptr, st,
+                             256, L0)));
     // deconv.0 -> BN -> ReLU
     MG_TRY((upsample2_fwd<T, T>((const T*)c->g_y0, (T*)c->g_x1, c->G.d0_w, c->G.d0_b, B, L0, 256, 128, 5, 128 * 5,
                                 ACT_NONE, nullptr, MUL_NONE, 0, st)));
@@ -263,15 +263,15 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
 }
 
 template <typename T>
-int bn_backward(mg_gan* c, const T* x, const T* dy, T* dx, long long rows, int C, const float* mean,
+int bn_backward(mg_gan* c, const T* x, const float* dy, T* dx, long long rows, int C, const float* mean,
                 const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st) {
     // sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat
-    MG_TRY((colreduce<T, COL_BN_BWD>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
+    MG_TRY((colreduce<T, COL_BN_BWD, float>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
                                      0, st)));
     add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
     MG_LAUNCH_OK();
     const long long n4 = rows * C / 4;
-    bn_bwd_apply_kernel<T><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
+    bn_bwd_apply_kernel<T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
                                                          c->g_bn_sums);
     MG_LAUNCH_OK();
     return MG_OK;
@@ -285,18 +285,18 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     MG_TRY((colreduce<float, COL_SUM>(c, dnotes, 4, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, (long long)B * T4, 4,
                                       c->gG.d6_b, 0, 0, 0, 1.0f, 1, st)));
     MG_TRY((convT_wgrad<T, float>((const T*)c->g_y2, dnotes, c->gG.d6_w, B, 4 * L0, 64, 4, st)));
-    MG_TRY((conv_fwd<float, T>(dnotes, (T*)c->g_dy2, c->G.d6_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr,
+    MG_TRY((conv_fwd<float, float, T>(dnotes, c->g_dy2, c->G.d6_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr,
                                nullptr, c->g_y2, MUL_RELU_SIGN, st, /*w_nstride (n=ci)*/ 4 * 5, /*w_kstride (k=co)*/ 5)));
     // ---- BN2 backward ----
-    MG_TRY((bn_backward<T>(c, (const T*)c->g_x2, (const T*)c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
+    MG_TRY((bn_backward<T>(c, (const T*)c->g_x2, c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
                            c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->gG.bn2_w, c->gG.bn2_b, st)));
     // ---- deconv.3 ----
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx2, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
                                   (long long)B * 4 * L0, 64, c->gG.d3_b, 0, 0, 0, 1.0f, 1, st)));
     MG_TRY((convT_wgrad<T, T>((const T*)c->g_y1, (const T*)c->g_dx2, c->gG.d3_w, B, 2 * L0, 128, 64, st)));
-    MG_TRY((conv_fwd<T, T>((const T*)c->g_dx2, (T*)c->g_dy1, c->G.d3_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE,
-                           nullptr, nullptr, c->g_y1, MUL_RELU_SIGN, st, 64 * 5, 5)));
-    MG_TRY((bn_backward<T>(c, (const T*)c->g_x1, (const T*)c->g_dy1, (T*)c->g_dx1, (long long)B * 2 * L0, 128,
+    MG_TRY((conv_fwd<T, float, T>((const T*)c->g_dx2, c->g_dy1, c->G.d3_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE,
+                                  nullptr, nullptr, c->g_y1, MUL_RELU_SIGN, st, 64 * 5, 5)));
+    MG_TRY((bn_backward<T>(c, (const T*)c->g_x1, c->g_dy1, (T*)c->g_dx1, (long long)B * 2 * L0, 128,
                            c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->gG.bn1_w, c->gG.bn1_b, st)));
     // ---- deconv.0 ----
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx1, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
@@ -308,8 +308,8 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     const int N2 = 256 * L0;
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dy0, N2, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B, N2,
                                   c->gG.p2_b, 0, 256, L0, 1.0f, 1, st)));
-    MG_TRY((linear_wgrad<T, float>((const T*)c->g_dy0, c->g_hb, c->gG.p2_w, 0, B, 512, N2, st, 256, L0)));
-    MG_TRY((linear_dgrad<T, float>((const T*)c->g_dy0, c->g_dhb, c->G.p2_w, B, 512, N2, c->g_hb, MUL_RELU_SIGN, st, 256, L0)));
+    MG_TRY((linear_wgrad<T, T>((const T*)c->g_dy0, (const T*)c->g_hb, c->gG.p2_w, 0, B, 512, N2, st, 256, L0)));
+    MG_TRY((linear_dgrad<T, float, T>((const T*)c->g_dy0, c->g_dhb, c->G.p2_w, B, 512, N2, c->g_hb, MUL_RELU_SIGN, st, 256, L0)));
     // ---- pre.0 ----
     MG_TRY((colreduce<float, COL_SUM>(c, c->g_dhb, 512, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B, 512, c->gG.p0_b,
                                       0, 0, 0, 1.0f, 1, st)));
@@ -619,6 +619,12 @@ extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
     e = cudaMemset(c->arena, 0, c->arena_bytes);
     if (e != cudaSuccess) { cudaFree(c->arena); delete c; mg::set_error("gan_create: memset failed"); return MG_ERR_CUDA; }
     layout(c, c->arena);
+    if (c->bf16) {   // packed-weight scratch of the tensor-core kernels: the largest layer is decoder.pre.2
+        size_t need = (size_t)256 * c->L0 * 512;
+        if (need < (size_t)5 * 256 * 256) need = (size_t)5 * 256 * 256;
+        int rc = mg::tc::ensure_scratch(need);
+        if (rc != MG_OK) { cudaFree(c->arena); delete c; return rc; }
+    }
     *out = c;
     return MG_OK;
 }

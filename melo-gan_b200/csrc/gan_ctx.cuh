@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "elem.cuh"
+#include "gemm_tc.cuh"
 
 struct mg_gan {
     mg_gan_config cfg;
@@ -38,10 +39,11 @@ struct mg_gan {
     const float *e_mask1 = nullptr, *e_mask2 = nullptr;   // masks of the last train-mode forward (caller memory)
     const float* e_numeric = nullptr;
     // Generator
-    float *g_xcat, *g_ha, *g_lat, *g_hb, *g_notes;
-    void *g_y0, *g_x1, *g_y1, *g_x2, *g_y2;                 // activation dtype
+    float *g_xcat, *g_ha, *g_lat, *g_notes;
+    void *g_hb, *g_y0, *g_x1, *g_y1, *g_x2, *g_y2;                 // activation dtype
     float *g_bn1_stats, *g_bn1_mean, *g_bn1_is, *g_bn2_stats, *g_bn2_mean, *g_bn2_is, *g_bn_sums;
-    void *g_dy2, *g_dx2, *g_dy1, *g_dx1, *g_dy0;
+    float *g_dy2, *g_dy1;                                   // float32 even in bf16 mode (BN backward)
+    void *g_dx2, *g_dx1, *g_dy0;
     float *g_dhb, *g_dlat, *g_dha, *g_dxcat, *g_demb;
     // Critic (up to 3B rows)
     float *d_x3, *d_pool, *d_hf, *d_score, *d_seed, *d_dzf, *d_dp, *d_gx, *d_gp_ps, *d_q, *d_dnotes;
@@ -82,7 +84,7 @@ int linear_fwd(const TA* A, TO* Out, const float* W, const float* bias, int R, i
 }
 
 // ---- Linear dgrad: dX[R, K] = (dZ[R, N] W[N, K]) * f'(ref) ----
-template <typename TA, typename TO>
+template <typename TA, typename TO, typename TMSK = TO>
 int linear_dgrad(const TA* dZ, TO* dX, const float* W, int R, int K, int N, const void* mul_src, int mul_mode,
                  cudaStream_t st, int k_perm_q = 0, int k_perm_p = 0) {
     TapGemmArgs a = tap_defaults();
@@ -90,7 +92,7 @@ int linear_dgrad(const TA* dZ, TO* dX, const float* W, int R, int K, int N, cons
     a.W = W; a.w_nstride = 1; a.w_kstride = K; a.k_perm_q = k_perm_q; a.k_perm_p = k_perm_p;
     a.Out = dX; a.o_bstride = K; a.B = R; a.Mper = 1; a.N = K;
     a.mul_src = mul_src; a.mul_mode = mul_mode;
-    return launch_tapgemm<TA, TO>(a, st);
+    return launch_tapgemm<TA, TO, TMSK>(a, st);
 }
 
 // ---- Linear wgrad: dW[N, K] += dZ[R, N]^T A[R, K] ----
@@ -105,7 +107,7 @@ int linear_wgrad(const TG* dZ, const TA* A, float* dW, int r0, int r1, int K, in
 }
 
 // ---- Conv1d forward (channels-last): in [R, Lin, Cin] -> out [R, Lin/stride, Cout]; W [Cout][Cin][ks] ----
-template <typename TA, typename TO>
+template <typename TA, typename TO, typename TMSK = TO>
 int conv_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int Cin, int Cout, int ks,
              int stride, int pad, int act, const float* col_scale, void* aux, const void* mul_src, int mul_mode,
              cudaStream_t st, int w_nstride = -1, int w_kstride = -1) {
@@ -117,7 +119,7 @@ int conv_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, in
     a.W = W; a.w_nstride = w_nstride < 0 ? Cin * ks : w_nstride; a.w_kstride = w_kstride < 0 ? ks : w_kstride;
     a.Out = out; a.o_bstride = (long long)Lout * Cout; a.o_mstride = Cout; a.B = R; a.Mper = Lout; a.N = Cout;
     a.bias = bias; a.act = act; a.col_scale = col_scale; a.aux = aux; a.mul_src = mul_src; a.mul_mode = mul_mode;
-    return launch_tapgemm<TA, TO>(a, st);
+    return launch_tapgemm<TA, TO, TMSK>(a, st);
 }
 
 // ---- stride-1 conv dgrad: dIn[R, L, Cin] = sum_t dOut[R, l + pad - t, Cout] W[Cout][Cin][ks] ----
@@ -191,8 +193,8 @@ int convT_wgrad(const TG* in, const TA* dOut, float* dW, int R, int Lin, int Cin
 }
 
 // ---- column reductions ----
-template <typename T, int OP>
-int colreduce(mg_gan* c, const T* x, int ldx, const T* y, int ldy, const float* mean, const float* invstd,
+template <typename T, int OP, typename TY = T>
+int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const float* mean, const float* invstd,
               const float* roww, int roww_div, long long r0, long long r1, int C, float* out, int out_kstride,
               int perm_q, int perm_p, float alpha, int accumulate, cudaStream_t st) {
     constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
@@ -210,7 +212,7 @@ int colreduce(mg_gan* c, const T* x, int ldx, const T* y, int ldy, const float* 
     a.roww_div = roww_div > 0 ? roww_div : 1; a.r0 = r0; a.r1 = r1; a.C = C; a.partial = c->partial;
     a.rows_per_chunk = (int)rpc;
     dim3 grid((C + 31) / 32, nchunk);
-    colreduce_kernel<T, OP><<<grid, 256, 0, st>>>(a);
+    colreduce_kernel<T, TY, OP><<<grid, 256, 0, st>>>(a);
     MG_LAUNCH_OK();
     const int n = NOUT * C;
     colreduce_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->partial, nchunk, NOUT, C, out, out_kstride, perm_q,

@@ -39,7 +39,7 @@ struct TapGemmArgs {
     const float* bias;            // indexed by physical n
     const float* col_scale;       // optional per-n multiplier applied to the accumulator (folded BatchNorm)
     int act;
-    const void* mul_src; int mul_mode;   // same element type and indexing as Out
+    const void* mul_src; int mul_mode;   // same indexing as Out (element type TMSK, by default Out's)
     void* aux;                    // ACT_GELU only: gelu'(z) written with Out's indexing/type
     const float* row_scale;       // optional per-row (b*Mper+m) multiplier applied before everything else
     float alpha;
@@ -96,7 +96,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // ------------------------------------------------------------------------------------------------
 // tap-GEMM
 // ------------------------------------------------------------------------------------------------
-template <typename TA, typename TO, int BM, int BN, int TM, int TN, int NBUF, bool VEC>
+template <typename TA, typename TO, typename TMSK, int BM, int BN, int TM, int TN, int NBUF, bool VEC>
 __global__ void __launch_bounds__(256) tapgemm_kernel(const TapGemmArgs P) {
     constexpr int BK = 16;
     static_assert((BM / TM) * (BN / TN) == 256, "256 threads per CTA");
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) tapgemm_kernel(const TapGemmArgs P) {
 
     // ---- epilogue ----
     TO* __restrict__ Obase = static_cast<TO*>(P.Out);
-    const TO* __restrict__ Mbase = static_cast<const TO*>(P.mul_src);
+    const TMSK* __restrict__ Mbase = static_cast<const TMSK*>(P.mul_src);
     TO* __restrict__ Xbase = static_cast<TO*>(P.aux);
     const int nb = n0 + tx * TN;
     float bias[TN], cscale[TN];
@@ -294,27 +294,38 @@ __global__ void __launch_bounds__(256) tapgemm_kernel(const TapGemmArgs P) {
     }
 }
 
-template <typename TA, typename TO>
+namespace tc {   // tensor-core paths (gemm_tc.cuh); return 1 = launched, 0 = shape does not qualify, <0 = error
+template <typename TA, typename TO, typename TMSK>
+int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st);
+template <typename TG, typename TA>
+int try_tc_wgrad(const WgradArgs& P, cudaStream_t st);
+}  // namespace tc
+
+template <typename TA, typename TO, typename TMSK = TO>
 int launch_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     const long long rows = (long long)P.B * P.Mper;
     if (rows == 0 || P.N == 0) return MG_OK;
+    {
+        const int r = tc::try_tc_tapgemm<TA, TO, TMSK>(P, st);
+        if (r != 0) return r < 0 ? r : MG_OK;
+    }
     const size_t ea = sizeof(TA), eo = sizeof(TO);
     bool vec = (P.K % 4 == 0) && (P.a_mstride % 4 == 0) && (P.a_bstride % 4 == 0) && (P.a_valid % 4 == 0) &&
                (P.N % 4 == 0) && (P.o_mstride % 4 == 0) && (P.o_bstride % 4 == 0) && (P.o_off % 4 == 0) &&
                (((uintptr_t)P.A) % (4 * ea) == 0) && (((uintptr_t)P.Out) % (4 * eo) == 0);
     for (int t = 0; t < P.ntaps; ++t) vec = vec && (P.a_toff[t] % 4 == 0);
-    if (P.mul_src) vec = vec && (((uintptr_t)P.mul_src) % (4 * eo) == 0);
+    if (P.mul_src) vec = vec && (((uintptr_t)P.mul_src) % (4 * sizeof(TMSK)) == 0);
     if (P.aux) vec = vec && (((uintptr_t)P.aux) % (4 * eo) == 0);
     ProbeScope probe(PROBE_TAPGEMM, 2.0 * (double)rows * P.N * P.ntaps * P.K,
                      (double)rows * (P.K * ea + P.N * eo), st);
     if (P.N <= 8) {
         dim3 grid((unsigned)((rows + 511) / 512), (unsigned)((P.N + 7) / 8));
-        if (vec) tapgemm_kernel<TA, TO, 512, 8, 4, 4, 1, true><<<grid, 256, 0, st>>>(P);
-        else tapgemm_kernel<TA, TO, 512, 8, 4, 4, 1, false><<<grid, 256, 0, st>>>(P);
+        if (vec) tapgemm_kernel<TA, TO, TMSK, 512, 8, 4, 4, 1, true><<<grid, 256, 0, st>>>(P);
+        else tapgemm_kernel<TA, TO, TMSK, 512, 8, 4, 4, 1, false><<<grid, 256, 0, st>>>(P);
     } else {
         dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((P.N + 63) / 64));
-        if (vec) tapgemm_kernel<TA, TO, 128, 64, 8, 4, 2, true><<<grid, 256, 0, st>>>(P);
-        else tapgemm_kernel<TA, TO, 128, 64, 8, 4, 2, false><<<grid, 256, 0, st>>>(P);
+        if (vec) tapgemm_kernel<TA, TO, TMSK, 128, 64, 8, 4, 2, true><<<grid, 256, 0, st>>>(P);
+        else tapgemm_kernel<TA, TO, TMSK, 128, 64, 8, 4, 2, false><<<grid, 256, 0, st>>>(P);
     }
     MG_LAUNCH_OK();
     return MG_OK;
@@ -425,6 +436,10 @@ template <typename TG, typename TA>
 int launch_wgrad(const WgradArgs& P, cudaStream_t st) {
     const long long nrows = (long long)P.row_end - P.row_begin;
     if (nrows <= 0 || P.N == 0) return MG_OK;
+    {
+        const int r = tc::try_tc_wgrad<TG, TA>(P, st);
+        if (r != 0) return r < 0 ? r : MG_OK;
+    }
     const int Ktot = P.ntaps * P.K;
     const int tn = (P.N + 63) / 64, tk = (Ktot + 63) / 64;
     // enough splits for ~4 CTAs per SM, at least 64 positions per split

@@ -1,0 +1,101 @@
+// gemm_tc.cu -- host helpers of the tcgen05 kernels: TMA tensor-map encoding, packed-weight scratch ring.
+#include <stdlib.h>
+
+#include "gemm_tc.cuh"
+
+namespace mg {
+namespace tc {
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+Scratch g_scratch;
+}  // namespace
+
+Scratch& scratch() { return g_scratch; }
+
+int ensure_scratch(size_t elems) {
+    if (elems <= g_scratch.slot_elems) return MG_OK;
+    for (int i = 0; i < 4; ++i) {
+        if (g_scratch.slot[i]) MG_CUDA_OK(cudaFree(g_scratch.slot[i]));
+        g_scratch.slot[i] = nullptr;
+        MG_CUDA_OK(cudaMalloc(&g_scratch.slot[i], elems * sizeof(__nv_bfloat16)));
+    }
+    g_scratch.slot_elems = elems;
+    return MG_OK;
+}
+
+static int g_enabled = -1;
+bool enabled() {
+    if (g_enabled < 0) {
+        const char* e = getenv("MELOGAN_DISABLE_TC");
+        g_enabled = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_enabled == 1;
+}
+int set_enabled(int on) {
+    const int prev = enabled() ? 1 : 0;
+    g_enabled = on ? 1 : 0;
+    return prev;
+}
+
+int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
+                 int box_samples) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
+    const cuuint64_t row_bytes = (cuuint64_t)C * 2;
+    cuuint64_t gdim[4], gstr[3];
+    if (stride == 1) {
+        gdim[0] = (cuuint64_t)C; gdim[1] = 1; gdim[2] = (cuuint64_t)L; gdim[3] = (cuuint64_t)B;
+        gstr[0] = row_bytes; gstr[1] = row_bytes; gstr[2] = row_bytes * (cuuint64_t)L;
+    } else {
+        gdim[0] = (cuuint64_t)C; gdim[1] = 2; gdim[2] = (cuuint64_t)(L / 2); gdim[3] = (cuuint64_t)B;
+        gstr[0] = row_bytes; gstr[1] = 2 * row_bytes; gstr[2] = row_bytes * (cuuint64_t)L;
+    }
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, (cuuint32_t)box_samples};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(act C=%d L=%d B=%lld stride=%d box=%d,%d) failed: %d", C, L, B, stride, box_rows,
+                  box_samples, (int)r);
+        return MG_ERR_CUDA;
+    }
+    return MG_OK;
+}
+
+int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weight K=%d rows=%lld box=%d) failed: %d", K, rows, box_rows, (int)r);
+        return MG_ERR_CUDA;
+    }
+    return MG_OK;
+}
+
+}  // namespace tc
+}  // namespace mg
+
+// A/B switch between the tcgen05 kernels and the CUDA-core kernels in bf16 mode (tests, profiling).
+extern "C" int mg_tc_enable(int on) { return mg::tc::set_enabled(on); }

@@ -1,0 +1,579 @@
+// gemm_tc.cuh -- tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Same two contractions as gemm_simt.cuh, for the layers that are tensor-core shaped:
+//
+//   tc_tapgemm   Out[b, m, n] = epi( sum_t sum_k A[b, s*m + r_t, k] * Wp[t][n][k] )        (s = 1 or 2)
+//     A tiles come straight from the channels-last activation through ONE 4-D TMA tensor map
+//     (k, parity, row/stride, sample): a tap is a coordinate shift, the conv zero padding and the
+//     sample boundaries are TMA out-of-bounds zero fill, and a stride-2 conv reads the even/odd row
+//     plane it needs.  128 rows x 64 k bf16 tiles land in shared memory 128B-swizzled (K-major), the
+//     packed weight tile [BN n][64 k] likewise; one elected thread issues tcgen05.mma (M=128, N=BN,
+//     K=16) into a TMEM accumulator; four epilogue warps read it back with tcgen05.ld and apply
+//     bias / folded-BN scale / ReLU|LeakyReLU|GELU / derivative masks before the global store.
+//   tc_wgrad     dW[t][n][k] += sum_{b,m} G[b, m, n] * A[b, s*m + r_t, k]
+//     the reduction runs over positions, so BOTH operands are MN-major in shared memory (rows of
+//     128 B = 64 channels, one row per position); split over CTAs along the positions, fp32 atomics
+//     into the reference-layout gradient.
+//
+// Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  3-stage smem ring (full/empty mbarriers),
+// tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
+#pragma once
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "gemm_simt.cuh"
+
+namespace mg {
+namespace tc {
+
+constexpr int kStages = 3;
+constexpr int kTileM = 128;
+constexpr int kTileK = 64;      // bf16 elements = 128 bytes = one swizzle row
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && spins > (1u << 26)) asm volatile("trap;");   // a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread = its warp's lane = TMEM lane)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;        // LayoutType::SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tap-GEMM
+// ---------------------------------------------------------------------------------------------
+struct TcTapArgs {
+    int ntaps, kblocks;                 // kblocks = K / 64 per tap
+    int a_p[kMaxTaps], a_dm[kMaxTaps];  // per tap: parity plane (dim 1) and row shift (dim 2) of the A map
+    int b_row[kMaxTaps];                // per tap: first row of that tap's [N][K] block in the packed weight
+    int mpt, bpt;                       // tile = bpt samples x mpt rows, mpt * bpt = 128
+    int Mper, B, N;
+    int n_perm_q, n_perm_p;             // bias index permutation (the packed weight is already permuted)
+    void* Out; long long o_bstride; int o_mstride; int o_off;
+    const float* bias; const float* col_scale; int act;
+    const void* mul_src; int mul_mode; void* aux;
+    float alpha; int accumulate;
+};
+
+template <int BN>
+struct TapSmem {
+    __nv_bfloat16 a[kStages][kTileM * kTileK];
+    __nv_bfloat16 b[kStages][BN * kTileK];
+    uint64_t full[kStages], empty[kStages], tmem_full;
+    uint32_t tmem_base;
+};
+
+template <int BN, typename TO, typename TMSK>
+__global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                         const __grid_constant__ CUtensorMap b_map, const TcTapArgs P) {
+    extern __shared__ unsigned char smem_raw[];
+    TapSmem<BN>& S = *reinterpret_cast<TapSmem<BN>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+    constexpr uint32_t kStageBytes = (kTileM + BN) * kTileK * 2;
+
+    // tile coordinates
+    int b0, m0;
+    if (P.mpt == kTileM) {
+        const int tiles_m = P.Mper / kTileM;
+        b0 = blockIdx.x / tiles_m;
+        m0 = (blockIdx.x % tiles_m) * kTileM;
+    } else {
+        b0 = blockIdx.x * P.bpt;
+        m0 = 0;
+    }
+    const int n0 = blockIdx.y * BN;
+    const int nkb = P.ntaps * P.kblocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        mbar_init(&S.tmem_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(&S.tmem_base, kTmemCols);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&a_map); tma_prefetch_desc(&b_map); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages, it = kb / kStages;
+                mbar_wait(&S.empty[s], (it & 1) ^ 1);
+                const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
+                mbar_expect_tx(&S.full[s], kStageBytes);
+                tma_load_4d(&a_map, &S.full[s], S.a[s], kc * kTileK, P.a_p[t], m0 + P.a_dm[t], b0);
+                tma_load_2d(&b_map, &S.full[s], S.b[s], kc * kTileK, P.b_row[t] + n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kStages, it = kb / kStages;
+            mbar_wait(&S.full[s], it & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(S.a[s]), b_addr = smem_u32(S.b[s]);
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k) {
+                    const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+                    const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+                    umma_f16(tmem_acc, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&S.empty[s]);                       // frees the smem stage when these MMAs retire
+                if (kb == nkb - 1) umma_commit(&S.tmem_full);   // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(&S.tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;             // tile row
+        const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
+        const bool row_ok = bb < P.B;
+        TO* __restrict__ Ob = static_cast<TO*>(P.Out);
+        const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
+        TO* __restrict__ Xb = static_cast<TO*>(P.aux);
+        const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!row_ok) continue;
+#pragma unroll
+            for (int g4 = 0; g4 < 16; g4 += 4) {
+                const int n = n0 + c0 + g4;
+                float x[4], gd[4] = {0.f, 0.f, 0.f, 0.f}, ms[4];
+                if (P.mul_mode != MUL_NONE) ld4(Mb + o + c0 + g4, ms);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y = v[g4 + j] * P.alpha;
+                    if (P.col_scale) y *= __ldg(P.col_scale + n + j);
+                    if (P.bias) y += __ldg(P.bias + perm_index(n + j, P.n_perm_q, P.n_perm_p));
+                    if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
+                    else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
+                    else if (P.act == ACT_GELU) { gd[j] = gelu_grad_f(y); y = gelu_f(y); }
+                    if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[j] > 0.0f ? 1.0f : 0.2f);
+                    else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[j] > 0.0f ? 1.0f : 0.0f);
+                    else if (P.mul_mode == MUL_VALUE) y *= ms[j];
+                    x[j] = y;
+                }
+                if (P.accumulate) {
+                    float old[4];
+                    ld4(Ob + o + c0 + g4, old);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] += old[j];
+                }
+                st4(Ob + o + c0 + g4, x);
+                if (P.aux) st4(Xb + o + c0 + g4, gd);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_acc, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad
+// ---------------------------------------------------------------------------------------------
+struct TcWgradArgs {
+    int ntaps, K, N;                    // K, N: channel counts of A and G (multiples of 64 / 128)
+    int a_p[kMaxTaps], a_dm[kMaxTaps];
+    int rpt, spt;                       // reduction chunk = spt samples x rpt rows, rpt * spt = 64
+    int Mper;
+    long long row_begin, row_end;       // flattened (b, m) rows to reduce over
+    int rows_per_split;                 // multiple of 64
+    float* dW; int w_toff[kMaxTaps]; int w_nstride; int w_kstride; int n_perm_q, n_perm_p;
+    float alpha;
+};
+
+template <int BNK>
+struct WgradSmem {
+    __nv_bfloat16 g[kStages][2 * 64 * 64];          // two 64-channel boxes x 64 positions
+    __nv_bfloat16 a[kStages][(BNK / 64) * 64 * 64];
+    uint64_t full[kStages], empty[kStages], tmem_full;
+    uint32_t tmem_base;
+};
+
+template <int BNK>
+__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap g_map,
+                                                       const __grid_constant__ CUtensorMap a_map, const TcWgradArgs P) {
+    extern __shared__ unsigned char smem_raw[];
+    WgradSmem<BNK>& S = *reinterpret_cast<WgradSmem<BNK>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = BNK < 32 ? 32 : BNK;
+    constexpr uint32_t kStageBytes = (2 + BNK / 64) * 64 * 64 * 2;
+    constexpr uint32_t kBoxBytes = 64 * 64 * 2;     // one TMA box: 64 positions x 128 B
+
+    const int n0 = blockIdx.x * kTileM;
+    const int kpt = P.K / BNK;                      // column tiles per tap
+    const int t = blockIdx.y / kpt, k0 = (blockIdx.y % kpt) * BNK;
+    const long long r_begin = P.row_begin + (long long)blockIdx.z * P.rows_per_split;
+    long long r_end = r_begin + P.rows_per_split;
+    if (r_end > P.row_end) r_end = P.row_end;
+    const int nchunks = r_end > r_begin ? (int)((r_end - r_begin + 63) / 64) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        mbar_init(&S.tmem_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(&S.tmem_base, kTmemCols);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&g_map); tma_prefetch_desc(&a_map); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = S.tmem_base;
+
+    if (nchunks > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int c = 0; c < nchunks; ++c) {
+                    const int s = c % kStages, it = c / kStages;
+                    mbar_wait(&S.empty[s], (it & 1) ^ 1);
+                    const long long r = r_begin + (long long)c * 64;
+                    int bq, mq;
+                    if (P.rpt == 64) { bq = (int)(r / P.Mper); mq = (int)(r % P.Mper); }
+                    else { bq = (int)(r / P.Mper); mq = 0; }
+                    mbar_expect_tx(&S.full[s], kStageBytes);
+                    tma_load_4d(&g_map, &S.full[s], S.g[s], n0, 0, mq, bq);
+                    tma_load_4d(&g_map, &S.full[s], S.g[s] + 64 * 64, n0 + 64, 0, mq, bq);
+#pragma unroll
+                    for (int j = 0; j < BNK / 64; ++j)
+                        tma_load_4d(&a_map, &S.full[s], S.a[s] + j * 64 * 64, k0 + j * 64, P.a_p[t], mq + P.a_dm[t], bq);
+                }
+            }
+        } else if (warp == 1) {
+            constexpr uint32_t idesc = make_idesc(BNK, 1, 1);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages, it = c / kStages;
+                mbar_wait(&S.full[s], it & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t g_addr = smem_u32(S.g[s]), a_addr = smem_u32(S.a[s]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {       // 16 positions (= 16 rows of 128 B) per MMA
+                        const uint64_t gd = make_smem_desc(g_addr + k * 16 * 128, kBoxBytes, 1024);
+                        const uint64_t ad = make_smem_desc(a_addr + k * 16 * 128, kBoxBytes, 1024);
+                        umma_f16(tmem_acc, gd, ad, idesc, (c | k) ? 1u : 0u);
+                    }
+                    umma_commit(&S.empty[s]);
+                    if (c == nchunks - 1) umma_commit(&S.tmem_full);
+                }
+                __syncwarp();
+            }
+        } else {
+            mbar_wait(&S.tmem_full, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int n = n0 + q * 32 + lane;
+            const long long nphys = perm_index(n, P.n_perm_q, P.n_perm_p);
+            float* __restrict__ dst = P.dW + P.w_toff[t] + nphys * P.w_nstride;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BNK; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (n < P.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        atomicAdd(dst + (long long)(k0 + c0 + j) * P.w_kstride, P.alpha * v[j]);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_acc, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: Wp[(t*N + n)*K + k] (bf16) = W[w_toff[t] + nphys(n)*w_nstride + kphys(k)*w_kstride]
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float* W; int w_toff[kMaxTaps]; int w_nstride, w_kstride, n_perm_q, n_perm_p, k_perm_q, k_perm_p;
+    int ntaps, N, K;
+    __nv_bfloat16* out;
+};
+static __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs P) {
+    const long long total = (long long)P.ntaps * P.N * P.K;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int k = (int)(i % P.K);
+        const long long tn = i / P.K;
+        const int n = (int)(tn % P.N), t = (int)(tn / P.N);
+        const float w = __ldg(P.W + P.w_toff[t] + (long long)perm_index(n, P.n_perm_q, P.n_perm_p) * P.w_nstride +
+                              (long long)perm_index(k, P.k_perm_q, P.k_perm_p) * P.w_kstride);
+        P.out[i] = __float2bfloat16_rn(w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Scratch {             // ring of packed-weight slots (stream-ordered reuse)
+    __nv_bfloat16* slot[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t slot_elems = 0;
+    int next = 0;
+};
+Scratch& scratch();
+int ensure_scratch(size_t elems);   // allocate the ring (not capturable: call before any CUDA-graph capture)
+bool enabled();              // MELOGAN_DISABLE_TC=1 forces the CUDA-core kernels (A/B testing)
+
+// 4-D view (k, parity, row, sample) of a channels-last activation [B][L][C] (bf16):
+//   stride 1: dims (C, 1, L, B);  stride 2: dims (C, 2, L/2, B)
+int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
+                 int box_samples);
+// 2-D view (k, rows) of a packed weight [rows][K]
+int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows);
+
+template <int BN, typename TO, typename TMSK>
+int launch_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a, int mtiles, cudaStream_t st) {
+    static bool attr_done = false;
+    const size_t smem = sizeof(TapSmem<BN>) + 1024;
+    if (!attr_done) {
+        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_kernel<BN, TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(mtiles, a.N / BN);
+    tc_tapgemm_kernel<BN, TO, TMSK><<<grid, 192, smem, st>>>(am, bm, a);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+template <int BNK>
+int launch_tc_wgrad(const CUtensorMap& gm, const CUtensorMap& am, const TcWgradArgs& a, int splits, cudaStream_t st) {
+    static bool attr_done = false;
+    const size_t smem = sizeof(WgradSmem<BNK>) + 1024;
+    if (!attr_done) {
+        MG_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel<BNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(a.N / kTileM, a.ntaps * (a.K / BNK), splits);
+    tc_wgrad_kernel<BNK><<<grid, 192, smem, st>>>(gm, am, a);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// Try to run a tap-GEMM described in SIMT terms on the tensor cores.  Returns 1 if launched, 0 if the shape
+// does not qualify (caller falls back to the CUDA-core kernel), or a negative mg_status on error.
+template <typename TA, typename TO, typename TMSK>
+int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
+    if (!std::is_same<TA, __nv_bfloat16>::value || !enabled()) return 0;
+    if (P.K % 64 || P.N % 64 || P.row_scale || P.ntaps < 1 || P.ntaps > kMaxTaps) return 0;
+    if (!is_pow2(P.Mper) || (P.Mper > 128 && P.Mper % 128)) return 0;
+    int stride;
+    if (P.Mper == 1) stride = 1;
+    else if (P.a_mstride == P.K) stride = 1;
+    else if (P.a_mstride == 2 * P.K) stride = 2;
+    else return 0;
+    if (P.a_valid % P.K || P.a_bstride != P.a_valid) return 0;
+    const int LA = P.a_valid / P.K;                         // rows per sample of the A tensor
+    if (stride == 2 && (LA % 2)) return 0;
+    if (((uintptr_t)P.A) % 16 || ((uintptr_t)P.Out) % 16) return 0;
+    if (P.o_off % 8 || P.o_mstride % 8 || P.o_bstride % 8) return 0;
+    TcTapArgs a{};
+    a.ntaps = P.ntaps; a.kblocks = P.K / 64;
+    for (int t = 0; t < P.ntaps; ++t) {
+        if (P.a_toff[t] % P.K) return 0;
+        const int r = P.a_toff[t] / P.K;                    // row shift in A rows
+        if (stride == 1) { a.a_p[t] = 0; a.a_dm[t] = r; }
+        else { const int p = ((r % 2) + 2) % 2; a.a_p[t] = p; a.a_dm[t] = (r - p) / 2; }
+        a.b_row[t] = t * P.N;
+    }
+    a.mpt = P.Mper >= 128 ? 128 : P.Mper; a.bpt = 128 / a.mpt;
+    a.Mper = P.Mper; a.B = P.B; a.N = P.N;
+    a.Out = P.Out; a.o_bstride = P.o_bstride; a.o_mstride = P.o_mstride; a.o_off = P.o_off;
+    a.bias = P.bias; a.col_scale = P.col_scale; a.act = P.act; a.mul_src = P.mul_src; a.mul_mode = P.mul_mode;
+    a.aux = P.aux; a.alpha = P.alpha; a.accumulate = P.accumulate;
+    a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
+
+    // pack the weight taps [ntaps][N][K] bf16 into the next scratch slot
+    Scratch& sc = scratch();
+    const size_t need = (size_t)P.ntaps * P.N * P.K;
+    if (need > sc.slot_elems) return 0;
+    __nv_bfloat16* wp = sc.slot[sc.next];
+    sc.next = (sc.next + 1) & 3;
+    PackArgs pk{};
+    pk.W = P.W; pk.w_nstride = P.w_nstride; pk.w_kstride = P.w_kstride; pk.n_perm_q = P.n_perm_q; pk.n_perm_p = P.n_perm_p;
+    pk.k_perm_q = P.k_perm_q; pk.k_perm_p = P.k_perm_p; pk.ntaps = P.ntaps; pk.N = P.N; pk.K = P.K; pk.out = wp;
+    for (int t = 0; t < P.ntaps; ++t) pk.w_toff[t] = P.w_toff[t];
+    long long blocks = ((long long)need + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    pack_weight_kernel<<<(int)blocks, 256, 0, st>>>(pk);
+    MG_LAUNCH_OK();
+
+    CUtensorMap am, bm;
+    const int BN = (P.N % 128 == 0) ? 128 : 64;
+    int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt);
+    if (rc != MG_OK) return rc;
+    rc = make_weight_map(&bm, wp, P.K, (long long)P.ntaps * P.N, BN);
+    if (rc != MG_OK) return rc;
+    const long long rows = (long long)P.B * P.Mper;
+    const int mtiles = (int)((rows + 127) / 128);
+    ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * P.N * P.ntaps * P.K,
+                     (double)rows * (P.K * 2.0 + P.N * sizeof(TO)), st);
+    rc = (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
+    return rc == MG_OK ? 1 : rc;
+}
+
+template <typename TG, typename TA>
+int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
+    if (!std::is_same<TG, __nv_bfloat16>::value || !std::is_same<TA, __nv_bfloat16>::value || !enabled()) return 0;
+    if (P.K % 64 || P.N % 128 || P.ntaps < 1 || P.ntaps > kMaxTaps || P.g_off) return 0;
+    if (!is_pow2(P.Mper) || (P.Mper > 64 && P.Mper % 64)) return 0;
+    int stride;
+    if (P.Mper == 1) stride = 1;
+    else if (P.a_mstride == P.K) stride = 1;
+    else if (P.a_mstride == 2 * P.K) stride = 2;
+    else return 0;
+    if (P.a_valid % P.K || P.a_bstride != P.a_valid) return 0;
+    const int LA = P.a_valid / P.K;
+    if (stride == 2 && (LA % 2)) return 0;
+    if (P.Mper > 1 && (P.g_mstride != P.N || P.g_bstride != (long long)P.Mper * P.N)) return 0;
+    if (P.Mper == 1 && P.g_bstride != P.N) return 0;
+    if (((uintptr_t)P.A) % 16 || ((uintptr_t)P.G) % 16) return 0;
+    if (P.row_begin % 64) return 0;
+    TcWgradArgs a{};
+    a.ntaps = P.ntaps; a.K = P.K; a.N = P.N;
+    for (int t = 0; t < P.ntaps; ++t) {
+        if (P.a_toff[t] % P.K) return 0;
+        const int r = P.a_toff[t] / P.K;
+        if (stride == 1) { a.a_p[t] = 0; a.a_dm[t] = r; }
+        else { const int p = ((r % 2) + 2) % 2; a.a_p[t] = p; a.a_dm[t] = (r - p) / 2; }
+        a.w_toff[t] = P.w_toff[t];
+    }
+    a.rpt = P.Mper >= 64 ? 64 : P.Mper; a.spt = 64 / a.rpt; a.Mper = P.Mper;
+    a.row_begin = P.row_begin; a.row_end = P.row_end;
+    a.dW = P.dW; a.w_nstride = P.w_nstride; a.w_kstride = P.w_kstride; a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
+    a.alpha = P.alpha;
+    const long long nrows = P.row_end - P.row_begin;
+    if (nrows <= 0) return 1;
+    const int BNK = (P.K % 128 == 0) ? 128 : 64;
+    const int tiles = (P.N / 128) * P.ntaps * (P.K / BNK);
+    long long want = ((long long)num_sms() * 3 + tiles - 1) / tiles;
+    long long maxs = (nrows + 255) / 256;                    // at least 4 chunks per CTA
+    long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+    if (splits > 65535) splits = 65535;
+    long long rps = (nrows + splits - 1) / splits;
+    rps = (rps + 63) / 64 * 64;
+    splits = (nrows + rps - 1) / rps;
+    a.rows_per_split = (int)rps;
+    // samples covered by the maps: rows are (b, m) with Mper rows per sample
+    const long long nsamples = (P.row_end + P.Mper - 1) / P.Mper;
+    CUtensorMap gm, am;
+    int rc = make_act_map(&gm, P.G, P.N, P.Mper, nsamples, 1, a.rpt, a.spt);
+    if (rc != MG_OK) return rc;
+    rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, nsamples, stride, a.rpt, a.spt);
+    if (rc != MG_OK) return rc;
+    ProbeScope probe(PROBE_TC_WGRAD, 2.0 * (double)nrows * P.N * P.ntaps * P.K, (double)nrows * (P.N + P.K) * 2.0, st);
+    rc = (BNK == 128) ? launch_tc_wgrad<128>(gm, am, a, (int)splits, st) : launch_tc_wgrad<64>(gm, am, a, (int)splits, st);
+    return rc == MG_OK ? 1 : rc;
+}
+
+}  // namespace tc
+}  // namespace mg

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "mg_launch_count": ([], _ll),
     "mg_probe_begin": ([_i], _i),
     "mg_probe_end": ([_vp], _i),
+    "mg_tc_enable": ([_i], _i),
     "mg_device_copy": ([_vp, _vp, _ll, _vp], _i),
     "mg_rng_fill": ([_vp, _ll, _i, _f, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp], _i),
     "mg_rng_fill_counter": ([_vp, _ll, _i, _f, ctypes.c_ulonglong, _vp, ctypes.c_ulonglong, _vp], _i),

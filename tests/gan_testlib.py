@@ -31,6 +31,21 @@ def assert_close(got, want, tol, what, want64=None):
     return e
 
 
+def rel_l2(got, want):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return ((got - want).norm() / want.norm().clamp_min(1e-300)).item()
+
+
+def assert_close_l2(got, want, tol, what):
+    """Relative L2 error.  Used for bf16-mode gradients: a bf16 forward flips the sign of a few near-zero
+    pre-activations relative to the fp32 oracle, which changes single gradient elements by O(1) (LeakyReLU /
+    ReLU masks) while the tensor as a whole stays within rounding."""
+    assert tuple(got.shape) == tuple(want.shape), (what, got.shape, want.shape)
+    e = rel_l2(got, want)
+    assert e <= tol, f"{what}: ||diff||/||ref|| = {e:.3e} > {tol:.1e}"
+    return e
+
+
 def to_double(obj):
     if isinstance(obj, dict):
         return {k: to_double(v) for k, v in obj.items()}

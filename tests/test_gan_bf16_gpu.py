@@ -1,0 +1,57 @@
+"""bf16 mode (tensor-core operands, fp32 accumulation): activations and per-step losses within 1e-2
+relative of the fp32 oracle (BASELINE.json north_star tolerance for bf16 mode)."""
+import pytest
+import torch
+
+from gan_testlib import assert_close, assert_close_l2, cuda_batch, make_engine
+from oracle import gan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2          # losses: relative; activation tensors: relative L2 (and 2x that in max-norm)
+# Gradients (relative L2): a bf16 forward moves ~0.3% of the near-zero pre-activations across zero relative to the
+# fp32 oracle; each such LeakyReLU/ReLU mask flip changes one activation-gradient element by O(1), i.e. about
+# 0.8*sqrt(0.003) = 4% in L2 per masked layer, compounding along the backward chain ("bf16 mode").
+# Exactness of the kernels themselves is pinned by the fp32-mode tests and by test_tc_vs_simt_gpu.py.
+GRAD_TOL = 0.15
+
+
+@pytest.mark.parametrize("B,fan,pseed", [(8, True, 4), (32, False, 2), (160, True, 7)])
+def test_bf16_critic_step(B, fan, pseed):
+    params = O.make_params(pseed, fan_in_scale=fan)
+    batch = O.make_batch(10 * pseed, B)
+    eng, cp, grads = make_engine(B, params, precision="bf16")
+    cb = cuda_batch(batch)
+    ref = O.critic_step(O.clone_params(params), batch, {}, update=False)
+    m = eng.critic_step(cb["notes_real"], cb["numeric"], cb["noise_d"], cb["alpha"], cb["mask1_d"], cb["mask2_d"]).cpu()
+    assert abs(m[0].item() - ref["loss_d"].item()) <= TOL * abs(ref["loss_d"].item())
+    assert abs(m[1].item() - ref["gp"].item()) <= TOL * max(abs(ref["gp"].item()), 1.0)
+    assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), ref["fake"], TOL, "fake notes")
+    assert_close(eng.buffer("g.notes").view(B, 512, 4), ref["fake"], 2 * TOL, "fake notes (max-norm)")
+    for k, g in ref["grads"].items():
+        if k.startswith("real_fake"):
+            continue
+        if k.endswith("bias"):
+            continue      # sums of +1/B and -1/B weighted terms: cancellation-dominated (see fp32 tests)
+        assert_close_l2(grads["D"][k], g, GRAD_TOL, "D grad " + k)
+
+
+@pytest.mark.parametrize("B,fan,pseed", [(8, True, 4), (32, False, 2), (160, True, 7)])
+def test_bf16_generator_step(B, fan, pseed):
+    params = O.make_params(pseed, fan_in_scale=fan)
+    batch = O.make_batch(10 * pseed + 3, B)
+    eng, cp, grads = make_engine(B, params, precision="bf16")
+    cb = cuda_batch(batch)
+    ref = O.generator_step(O.clone_params(params), batch, {}, update=False)
+    m = eng.generator_step(cb["numeric"], cb["noise_g"], cb["emot_idx"], cb["mask1_g"], cb["mask2_g"]).cpu()
+    assert abs(m[0].item() - ref["loss_g_adv"].item()) <= TOL * max(abs(ref["loss_g_adv"].item()), 0.05)
+    assert abs(m[1].item() - ref["loss_g_emo"].item()) <= TOL * abs(ref["loss_g_emo"].item())
+    assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), ref["notes"], TOL, "notes")
+    assert_close(eng.buffer("g.notes").view(B, 512, 4), ref["notes"], 2 * TOL, "notes (max-norm)")
+    assert_close(eng.buffer("ed.logits")[:B * 4].view(B, 4), ref["logits"], TOL, "logits")
+    for k, g in ref["grads_G"].items():
+        if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias"):
+            continue
+        assert_close_l2(grads["G"][k], g, GRAD_TOL, "G grad " + k)
+    for k, g in ref["grads_E"].items():
+        assert_close_l2(grads["E"][k], g, GRAD_TOL, "E grad " + k)

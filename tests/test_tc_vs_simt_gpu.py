@@ -1,0 +1,57 @@
+"""tcgen05 kernels against the CUDA-core kernels on identical bf16 operands (same math, different
+summation order): every activation and gradient of the two step bodies must agree to ~1e-3."""
+import pytest
+import torch
+
+from gan_testlib import assert_close, assert_close_l2, cuda_batch, make_engine
+from melogan import _native
+from oracle import gan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ACT_BUFFERS_D = [("d.h2", torch.bfloat16), ("d.h3", torch.bfloat16), ("d.dz2", torch.bfloat16), ("d.dz1", torch.bfloat16)]
+ACT_BUFFERS_G = [("g.y0", torch.bfloat16), ("g.x1", torch.bfloat16), ("g.x2", torch.bfloat16), ("ed.h1", torch.bfloat16),
+                 ("ed.h2", torch.bfloat16), ("ed.h3", torch.bfloat16), ("g.dy1", torch.float32), ("g.dy0", torch.bfloat16),
+                 ("g.dhb", torch.float32), ("d.dnotes", torch.float32)]
+
+
+def _run(B, which, tc_on):
+    prev = _native.lib().mg_tc_enable(1 if tc_on else 0)
+    try:
+        params = O.make_params(4, fan_in_scale=True)
+        # weights that are exactly representable in bf16: the tensor-core path rounds its packed weights to bf16,
+        # the CUDA-core path reads the fp32 master weights; with pre-rounded weights both see identical operands
+        params = {m: {k: v.to(torch.bfloat16).to(torch.float32) for k, v in P.items()} for m, P in params.items()}
+        batch = O.make_batch(40, B)
+        eng, cp, grads = make_engine(B, params, precision="bf16")
+        cb = cuda_batch(batch)
+        if which == "d":
+            m = eng.critic_step(cb["notes_real"], cb["numeric"], cb["noise_d"], cb["alpha"], cb["mask1_d"], cb["mask2_d"])
+            bufs = {n: eng.buffer(n, dt).float() for n, dt in ACT_BUFFERS_D}
+            g = {k: v.clone() for k, v in grads["D"].items()}
+        else:
+            m = eng.generator_step(cb["numeric"], cb["noise_g"], cb["emot_idx"], cb["mask1_g"], cb["mask2_g"])
+            bufs = {n: eng.buffer(n, dt).float() for n, dt in ACT_BUFFERS_G}
+            g = {k: v.clone() for k, v in grads["G"].items()}
+            g.update({"E." + k: v.clone() for k, v in grads["E"].items()})
+        torch.cuda.synchronize()
+        return m.clone(), bufs, g
+    finally:
+        _native.lib().mg_tc_enable(prev)
+
+
+@pytest.mark.parametrize("B", [8, 96, 130])
+@pytest.mark.parametrize("which", ["d", "g"])
+def test_tensor_core_path_equals_cuda_core_path(B, which):
+    m0, b0, g0 = _run(B, which, tc_on=False)
+    m1, b1, g1 = _run(B, which, tc_on=True)
+    fwd = {"d.h2", "d.h3", "g.y0", "g.x1", "g.x2", "ed.h1", "ed.h2", "ed.h3"}
+    for name in b0:
+        # forward activations: bf16 storage rounding of slightly different fp32 sums.  Backward buffers additionally
+        # see a few LeakyReLU/ReLU mask flips where a near-zero activation changed sign between the two paths.
+        assert_close_l2(b1[name], b0[name], 5e-3 if name in fwd else 5e-2, f"{which}:{name}")
+    assert torch.allclose(m1, m0, rtol=2e-3, atol=1e-5), (m1, m0)
+    for k in g0:
+        if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias") or k.startswith("real_fake"):
+            continue
+        assert_close_l2(g1[k], g0[k], 5e-2, f"{which}: grad {k}")
