@@ -181,6 +181,11 @@ int mg_discriminator_backward_ex(mg_gan* ctx, const float* notes, const float* d
 int mg_critic_loss_backward(mg_gan* ctx, const float* real, const float* fake, const float* emb,
                             const float* alpha, float* metrics_out, void* stream);
 
+/* A-6 alone  compute_gradient_penalty (src/gan/utils.py:75-90): metrics_out[1] = GP (unweighted); adds
+ * d(GP)/d(theta_D) -- the double backward through the critic -- into the bound critic grads. */
+int mg_gradient_penalty(mg_gan* ctx, const float* real, const float* fake, const float* emb, const float* alpha,
+                        float* metrics_out, void* stream);
+
 /* A-8  EmotionDiscriminator.forward in eval mode + input gradient (frozen weights)
  *      src/emotion_discriminator/ed_model.py:147-165 */
 int mg_emotion_forward(mg_gan* ctx, const float* notes, float* logits_out, void* stream);

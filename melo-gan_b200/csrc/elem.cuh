@@ -412,10 +412,10 @@ __global__ void critic_demb_kernel(const float* seed, const float* w, int B, int
     const float v = seed[i / E] * w[F + i % E];
     demb[i] = accumulate ? demb[i] + v : v;
 }
-__global__ void critic_seed_kernel(float* seed, int B) {
+__global__ void critic_seed_kernel(float* seed, int B, float w_real, float w_fake) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * B) return;
-    seed[i] = i < B ? -1.0f / (float)B : (i < 2 * B ? 1.0f / (float)B : 1.0f);
+    seed[i] = i < B ? w_real / (float)B : (i < 2 * B ? w_fake / (float)B : 1.0f);
 }
 
 __global__ void fill_kernel(float* p, long long n, float v) {

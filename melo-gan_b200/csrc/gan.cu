@@ -429,9 +429,12 @@ int disc_wgrad(mg_gan* c, const float* x_in, const float* seed, int R, int Rb, c
 }
 
 // A-6 + A-7 loss part
+// loss = w_fake * mean(D(fake)) + w_real * mean(D(real)) + lambda * GP   (the critic loss has w = +1, -1, LAMBDA_GP)
 template <typename T>
 int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const float* emb, const float* alpha,
-                         float* metrics_out, cudaStream_t st) {
+                         float* metrics_out, cudaStream_t st, float w_real = -1.0f, float w_fake = 1.0f,
+                         float lambda = -1.0f) {
+    if (lambda < 0.0f) lambda = (float)c->cfg.lambda_gp;
     const int B = c->B, L0 = c->L0, T4 = c->T;
     const size_t per = (size_t)L0 * 256, pern = (size_t)T4 * 4;
     assemble_critic_input_kernel<<<grid_for((long long)B * pern / 4), 256, 0, st>>>(
@@ -439,15 +442,15 @@ int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const 
         reinterpret_cast<float4*>(c->d_x3), B, (int)(pern / 4));
     MG_LAUNCH_OK();
     MG_TRY((disc_forward<T>(c, c->d_x3, emb, 3 * B, nullptr, st)));
-    critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->d_seed, B);
+    critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->d_seed, B, w_real, w_fake);
     MG_LAUNCH_OK();
     // one dgrad chain for all 3B rows; the x_hat rows continue to grad_x
     MG_TRY((disc_dgrad<T>(c, c->d_seed, 3 * B, c->d_gx, 2 * B, B, 0, st)));
     // penalty and u = dL/d(grad_x), written over the x_hat rows of X3
     float* u = c->d_x3 + (size_t)2 * B * pern;
-    gp_norm_kernel<<<B, 256, 0, st>>>(c->d_gx, u, (int)pern, (float)(c->cfg.lambda_gp / (double)B), c->d_gp_ps, nullptr);
+    gp_norm_kernel<<<B, 256, 0, st>>>(c->d_gx, u, (int)pern, lambda / (float)B, c->d_gp_ps, nullptr);
     MG_LAUNCH_OK();
-    critic_loss_kernel<<<1, 256, 0, st>>>(c->d_score, c->d_gp_ps, B, (float)c->cfg.lambda_gp, metrics_out ? metrics_out : c->metrics);
+    critic_loss_kernel<<<1, 256, 0, st>>>(c->d_score, c->d_gp_ps, B, lambda, metrics_out ? metrics_out : c->metrics);
     MG_LAUNCH_OK();
     // adjoint forward chain on the x_hat rows, overwriting their saved activations in place
     T* h1x = (T*)c->d_h1 + (size_t)2 * B * per;
@@ -780,6 +783,17 @@ extern "C" int mg_critic_loss_backward(mg_gan* c, const float* real, const float
     MG_NEED_GRADS(c, 2, "critic_loss_backward");
     MG_REQUIRE(real && fake && alpha, "critic_loss_backward: null pointer");
     return MG_DISPATCH(c, critic_loss_backward, c, real, fake, emb, alpha, metrics_out, as_stream(stream));
+}
+
+extern "C" int mg_gradient_penalty(mg_gan* c, const float* real, const float* fake, const float* emb,
+                                   const float* alpha, float* metrics_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 2, "gradient_penalty");
+    MG_NEED_GRADS(c, 2, "gradient_penalty");
+    MG_REQUIRE(real && fake && alpha, "gradient_penalty: null pointer");
+    // GP alone: zero seeds for the real/fake rows, unit weight on the penalty
+    return c->bf16 ? critic_loss_backward<__nv_bfloat16>(c, real, fake, emb, alpha, metrics_out, as_stream(stream), 0.f, 0.f, 1.f)
+                   : critic_loss_backward<float>(c, real, fake, emb, alpha, metrics_out, as_stream(stream), 0.f, 0.f, 1.f);
 }
 
 extern "C" int mg_emotion_forward(mg_gan* c, const float* notes, float* logits_out, void* stream) {

@@ -93,6 +93,20 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
     return cdf + x * pdf;
 }
 
+// bf16-mode epilogues: GELU and its derivative from ONE exp (erf by Abramowitz-Stegun 7.1.26, |err| < 1.5e-7,
+// which is far below the bf16 storage rounding of the result); about 4x fewer instructions than erff + expf.
+__device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
+    const float ax = fabsf(x) * 0.70710678118654752f;          // |x| / sqrt(2)
+    const float e = __expf(-ax * ax);                          // exp(-x^2 / 2)
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
+                                0.254829592f);
+    const float erf_abs = 1.0f - poly * e;
+    const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+    y = x * cdf;
+    dy = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
 // ------------------------------------------------------------------------------------------------
 // tap-GEMM
 // ------------------------------------------------------------------------------------------------

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
                     if (P.bias) y += __ldg(P.bias + perm_index(n + j, P.n_perm_q, P.n_perm_p));
                     if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
                     else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
-                    else if (P.act == ACT_GELU) { gd[j] = gelu_grad_f(y); y = gelu_f(y); }
+                    else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[j]); y = yy; }
                     if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[j] > 0.0f ? 1.0f : 0.2f);
                     else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[j] > 0.0f ? 1.0f : 0.0f);
                     else if (P.mul_mode == MUL_VALUE) y *= ms[j];

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "mg_discriminator_backward": ([_vp, _vp, _i, _vp, _vp, _vp], _i),
     "mg_discriminator_backward_ex": ([_vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_critic_loss_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_gradient_penalty": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_emotion_forward": ([_vp, _vp, _vp, _vp], _i),
     "mg_emotion_backward_input": ([_vp, _vp, _vp, _i, _vp], _i),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),

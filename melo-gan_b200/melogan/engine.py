@@ -188,6 +188,15 @@ class GanEngine:
         self._call("mg_critic_loss_backward", _ptr(real), _ptr(fake), _ptr(emb), _ptr(alpha), _ptr(metrics), self._stream())
         return metrics
 
+    def gradient_penalty(self, real, fake, emb, alpha, metrics=None):
+        """GP value (metrics[1]) and d(GP)/d(theta_D) added into the bound critic grads."""
+        _check_f32_cuda(real, "real", (self.B, self.T, self.note_dim))
+        _check_f32_cuda(fake, "fake", (self.B, self.T, self.note_dim))
+        _check_f32_cuda(alpha, "alpha", (self.B,))
+        metrics = metrics if metrics is not None else torch.empty(4, device=self.device)
+        self._call("mg_gradient_penalty", _ptr(real), _ptr(fake), _ptr(emb), _ptr(alpha), _ptr(metrics), self._stream())
+        return metrics
+
     # ---- A-8 ----
     def emotion_forward(self, notes):
         _check_f32_cuda(notes, "notes", (self.B, self.T, self.note_dim))
@@ -253,6 +262,7 @@ _GAN_SIGNATURES = {
     "mg_discriminator_backward": ([_vp, _vp, _i, _vp, _vp, _vp], _i),
     "mg_discriminator_backward_ex": ([_vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_critic_loss_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_gradient_penalty": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_emotion_forward": ([_vp, _vp, _vp, _vp], _i),
     "mg_emotion_backward_input": ([_vp, _vp, _vp, _i, _vp], _i),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),

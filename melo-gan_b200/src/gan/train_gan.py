@@ -1,0 +1,125 @@
+#!/usr/bin/env python3
+"""Train MELO-GAN (WGAN-GP + numeric conditioning + frozen emotion discriminator) on B200.
+
+    python -m src.gan.train_gan [--config config/gan_config.yaml] [--ed_config config/ed_config.yaml]
+                                [--ed_ckpt data/models/ed/ed_best.pth]
+
+Same CLI, config schema, loop schedule (every batch a critic step, every CRITIC_ITERS-th batch a generator
+step on that batch), epoch log line, TensorBoard scalar names and checkpoint layouts as the reference's
+src/gan/train_gan.py; each step body runs as one fused native call through melogan.trainer.GanTrainer
+(losses stay on the device until the epoch log).  Extra knobs come from the environment, never from the
+YAML: MELOGAN_PRECISION=fp32|bf16; under torchrun the batch is sharded over the ranks (NCCL all-reduce).
+"""
+import argparse
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+import yaml
+
+from melogan.trainer import GanTrainer
+from src.gan.utils import emotion_to_index
+
+
+def load_config(path):
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+def load_split_arrays(cfg, split_csv):
+    """Fast path of the reference's GANDataset (src/gan/dataset.py:30-56): <SPLITS_DIR>/<split>/{notes,emotion,
+    numeric_features}.npy.  The per-file .npz path is the data-loading row of SURVEY.md 8(f) and is not built."""
+    splits_dir = cfg.get('SPLITS_DIR', 'data/splits')
+    name = Path(split_csv).stem
+    base = os.path.join(splits_dir, name)
+    paths = [os.path.join(base, f) for f in ("notes.npy", "emotion.npy", "numeric_features.npy")]
+    if not all(os.path.exists(p) for p in paths):
+        raise FileNotFoundError(f"expected pre-saved arrays {paths} (the .npz-per-file loader is out of scope here)")
+    notes, emotions, numeric = (np.load(p, allow_pickle=True) for p in paths)
+    if not (len(notes) == len(emotions) == len(numeric)):
+        raise ValueError("NPY file length mismatch (notes, emotions, numeric_features)")
+    labels = np.array([emotion_to_index(e) for e in emotions], dtype=np.int64)
+    return notes.astype(np.float32), numeric.astype(np.float32), labels
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=str, default="config/gan_config.yaml", help="Path to the main GAN config")
+    ap.add_argument("--ed_config", type=str, default="config/ed_config.yaml", help="Path to the ED config")
+    ap.add_argument("--ed_ckpt", type=str, default="data/models/ed/ed_best.pth")
+    args = ap.parse_args(argv)
+    cfg, ed_cfg = load_config(args.config), load_config(args.ed_config)
+    if not torch.cuda.is_available():
+        raise SystemExit("train_gan: a CUDA (sm_100a) device is required; this implementation has no CPU fallback")
+
+    world, rank, local, pg = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), \
+        int(os.environ.get("LOCAL_RANK", "0")), None
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        pg = torch.distributed.group.WORLD
+    device = torch.device(f"cuda:{local}")
+    print(f"Using main device: {device}")
+
+    notes, numeric, labels = load_split_arrays(cfg, cfg['TRAIN_SPLIT'])
+    print(f"Train set size: {len(notes)}")
+    ed_state = None
+    if os.path.exists(args.ed_ckpt):
+        print(f"[INFO] Loading pre-trained Emotion Discriminator from {args.ed_ckpt}")
+        ck = torch.load(args.ed_ckpt, map_location="cpu")
+        ed_state = ck['model'] if 'model' in ck else ck
+    else:
+        print(f"[WARN] ED checkpoint not found at {args.ed_ckpt}. ED will be random!")
+
+    B = int(cfg.get('BATCH_SIZE', 32))
+    if B % world:
+        raise SystemExit(f"BATCH_SIZE {B} must be divisible by the world size {world}")
+    tr = GanTrainer(cfg, ed_cfg, batch=B // world, precision=os.environ.get("MELOGAN_PRECISION", "fp32"), device=device,
+                    ed_state_dict=ed_state, process_group=pg, seed_offset=rank)
+    d_notes, d_numeric, d_labels = (torch.from_numpy(a).to(device) for a in (notes, numeric, labels))   # 7 MB: resident
+
+    writer = None
+    if rank == 0:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(log_dir=cfg['LOG_DIR'])
+        except Exception:
+            writer = None
+        os.makedirs(cfg['CHECKPOINT_DIR'], exist_ok=True)
+        os.makedirs(cfg['SAMPLE_DIR'], exist_ok=True)
+    critic_iters = int(cfg.get('CRITIC_ITERS', 5))
+    gen = torch.Generator(device="cpu").manual_seed(int(cfg.get("SEED", 42)))
+    print("Starting WGAN-GP Training with Emotion Guidance...")
+    steps = len(notes) // B                       # drop_last=True
+    for epoch in range(1, cfg['EPOCHS'] + 1):
+        perm = torch.randperm(len(notes), generator=gen).to(device)          # shuffle=True, same order on every rank
+        for batch_idx in range(steps):
+            idx = perm[batch_idx * B:(batch_idx + 1) * B].view(world, -1)[rank]
+            real, num, lab = d_notes[idx].contiguous(), d_numeric[idx].contiguous(), d_labels[idx].contiguous()
+            tr.critic_step(real, num)
+            if (batch_idx + 1) % critic_iters == 0:
+                tr.generator_step(num, lab)
+        d_loss, g_adv, g_emo = tr.epoch_means()
+        if rank == 0:
+            print(f"Epoch {epoch}/{cfg['EPOCHS']} | D_loss: {d_loss:.4f} | G_adv: {g_adv:.4f} | G_emo: {g_emo:.4f}")
+            if writer is not None:
+                writer.add_scalar("Loss/Critic", d_loss, epoch)
+                writer.add_scalar("Loss/Generator_Adv", g_adv, epoch)
+                writer.add_scalar("Loss/Generator_Emo", g_emo, epoch)
+            if epoch % cfg.get('SAVE_FREQ', 5) == 0:
+                ck = {'epoch': epoch}
+                ck.update(tr.state_dict())
+                torch.save(ck, os.path.join(cfg['CHECKPOINT_DIR'], f"gan_epoch{epoch:04d}.pth"))
+    if rank == 0:
+        torch.save({'G': tr.G.state_dict(), 'E_num': tr.E_num.state_dict()},
+                   os.path.join(cfg['CHECKPOINT_DIR'], "gan_final.pth"))
+        if writer is not None:
+            writer.close()
+        print("Training Complete.")
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
