@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _native
+from . import dist as D_
 from . import engine as E
 from .optim import FlatParams, FusedAdam
 
@@ -147,7 +148,7 @@ class GanTrainer:
 
     def _allreduce(self, flat):
         if self.world > 1:
-            torch.distributed.all_reduce(flat.grad, group=self.pg)
+            D_.allreduce_sum_(flat.grad, self.pg)      # the 1/world factor is folded into Adam's grad_scale
 
     # ---- the two step bodies ----
     def critic_step(self, real, numeric, noise=None, alpha=None, mask1=None, mask2=None):
@@ -191,20 +192,61 @@ class GanTrainer:
     # ---- whole-cycle CUDA graph ----
     def capture_cycle(self):
         """Captures train_cycle over static input buffers; returns them.  Run at least one eager cycle first
-        (first calls allocate scratch, which capture forbids)."""
+        (first calls allocate scratch, which capture forbids).
+        Single GPU: the whole cycle is ONE graph.  Data parallel: NCCL all-reduces stay outside the graphs (capturing
+        them deadlocked on this stack), so every step is two graphs -- [zero grads, draw, step body] and [Adam, loss
+        accumulation] -- with the eager all-reduce of the flat gradient buffer between them on the same stream."""
         K, B, dev = self.critic_iters, self.B, self.device
         self.s_reals = torch.zeros((K, B, self.cfg['MAX_NOTES'], self.cfg['NOTE_DIM']), device=dev)
         self.s_numerics = torch.zeros((K, B, self.cfg.get('NUMERIC_INPUT_DIM', 6)), device=dev)
         self.s_labels = torch.zeros(B, dtype=torch.int64, device=dev)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.train_cycle(self.s_reals, self.s_numerics, self.s_labels)
-        self._graph = g
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.train_cycle(self.s_reals, self.s_numerics, self.s_labels)
+            self._graph = g
+            return self.s_reals, self.s_numerics, self.s_labels
+        pool = torch.cuda.graph_pool_handle()
+        self._g_pre, self._g_post = [], []
+        bns = (self.G.decoder.deconv[1], self.G.decoder.deconv[4])
+        for i in range(K + 1):
+            pre, post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(pre, pool=pool):
+                if i < K:
+                    self._draw(critic=True)
+                    self.opt_D.zero_grad()
+                    self.engine.critic_step(self.s_reals[i], self.s_numerics[i], self.noise, self.alpha, self.mask1,
+                                            self.mask2, metrics=self.m_d)
+                else:
+                    self._draw(critic=False)
+                    self.opt_G.zero_grad()
+                    self.engine.generator_step(self.s_numerics[K - 1], self.noise, self.s_labels, self.mask1, self.mask2,
+                                               metrics=self.m_g)
+                for bn in bns:
+                    bn.num_batches_tracked += 1
+            with torch.cuda.graph(post, pool=pool):
+                if i < K:
+                    self.opt_D.step()
+                    self.loss_acc[0:4] += self.m_d
+                    self.loss_acc[6] += 1
+                else:
+                    self.opt_G.step()
+                    self.loss_acc[4:6] += self.m_g
+                    self.loss_acc[7] += 1
+            self._g_pre.append(pre); self._g_post.append(post)
+        self._graph = True
         return self.s_reals, self.s_numerics, self.s_labels
 
     def replay_cycle(self):
-        self._graph.replay()
+        if self.world == 1:
+            self._graph.replay()
+            return
+        K = self.critic_iters
+        for i in range(K + 1):
+            self._g_pre[i].replay()
+            self._allreduce(self.flat_d if i < K else self.flat_g)
+            self._g_post[i].replay()
 
     def launches_per_cycle(self):
         return None
