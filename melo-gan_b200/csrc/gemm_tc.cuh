@@ -149,6 +149,7 @@ struct TapSmem {
     __nv_bfloat16 b[kStages][BN * kTileK];
     uint64_t full[kStages], empty[kStages], tmem_full;
     uint32_t tmem_base;
+    float bias[BN], scale[BN];          // this tile's bias (permuted) and alpha * folded-BN scale
 };
 
 template <int BN, typename TO, typename TMSK>
@@ -220,8 +221,14 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(&S.tmem_full, 0);
-        tc_fence_after();
+        // While the main loop runs: stage this tile's bias / BN scale in shared memory and prefetch this thread's
+        // row of the mask tensor (f'(saved activation)) into registers, so that nothing in the drain loop waits
+        // on a dependent global load.
+        const int et = threadIdx.x - 64;             // 0..127
+        for (int i = et; i < BN; i += 128) {
+            S.bias[i] = P.bias ? __ldg(P.bias + perm_index(n0 + i, P.n_perm_q, P.n_perm_p)) : 0.0f;
+            S.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
+        }
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;             // tile row
         const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
@@ -230,34 +237,66 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
         const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
         TO* __restrict__ Xb = static_cast<TO*>(P.aux);
         const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
+        constexpr bool kPrefetchMask = sizeof(TMSK) == 2;
+        constexpr int kMaskVecs = kPrefetchMask ? BN / 8 : 1;
+        uint4 mreg[kMaskVecs];
+        if (kPrefetchMask && P.mul_mode != MUL_NONE && row_ok) {
+#pragma unroll
+            for (int i = 0; i < kMaskVecs; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o) + i);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // bias/scale staged (epilogue warps only)
+        mbar_wait(&S.tmem_full, 0);
+        tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (!row_ok) continue;
+            float ms[16];
+            if (P.mul_mode != MUL_NONE) {
+                if (kPrefetchMask) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint4 mv = mreg[(c0 >> 3) + h];
+                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            ms[h * 8 + 2 * e] = __uint_as_float(w[e] << 16);
+                            ms[h * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int g4 = 0; g4 < 16; g4 += 4) {
+                        float t4[4];
+                        ld4(Mb + o + c0 + g4, t4);
+                        ms[g4] = t4[0]; ms[g4 + 1] = t4[1]; ms[g4 + 2] = t4[2]; ms[g4 + 3] = t4[3];
+                    }
+                }
+            }
+            float old[16];
+            if (P.accumulate) {
+#pragma unroll
+                for (int g4 = 0; g4 < 16; g4 += 4) {
+                    float t4[4];
+                    ld4(Ob + o + c0 + g4, t4);
+                    old[g4] = t4[0]; old[g4 + 1] = t4[1]; old[g4 + 2] = t4[2]; old[g4 + 3] = t4[3];
+                }
+            }
 #pragma unroll
             for (int g4 = 0; g4 < 16; g4 += 4) {
-                const int n = n0 + c0 + g4;
-                float x[4], gd[4] = {0.f, 0.f, 0.f, 0.f}, ms[4];
-                if (P.mul_mode != MUL_NONE) ld4(Mb + o + c0 + g4, ms);
+                float x[4], gd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float y = v[g4 + j] * P.alpha;
-                    if (P.col_scale) y *= __ldg(P.col_scale + n + j);
-                    if (P.bias) y += __ldg(P.bias + perm_index(n + j, P.n_perm_q, P.n_perm_p));
+                    float y = fmaf(v[g4 + j], S.scale[c0 + g4 + j], S.bias[c0 + g4 + j]);
                     if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
                     else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
                     else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[j]); y = yy; }
-                    if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[j] > 0.0f ? 1.0f : 0.2f);
-                    else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[j] > 0.0f ? 1.0f : 0.0f);
-                    else if (P.mul_mode == MUL_VALUE) y *= ms[j];
+                    if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.2f);
+                    else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.0f);
+                    else if (P.mul_mode == MUL_VALUE) y *= ms[g4 + j];
+                    if (P.accumulate) y += old[g4 + j];
                     x[j] = y;
-                }
-                if (P.accumulate) {
-                    float old[4];
-                    ld4(Ob + o + c0 + g4, old);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] += old[j];
                 }
                 st4(Ob + o + c0 + g4, x);
                 if (P.aux) st4(Xb + o + c0 + g4, gd);
