@@ -104,8 +104,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, long 
 }
 
 // y = relu((x - mean) * invstd * gamma + beta)      (eval mode: mean/invstd come from running stats)
-template <typename T>
-__global__ void __launch_bounds__(256) bn_relu_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4,
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __restrict__ x, T* __restrict__ y, long long n4,
                                                             int C, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma,
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const T* __restrict_
 }
 
 // dx = gamma*invstd*(dy - s1/R - xhat*s2/R), sums = [s1 | s2] (dy already carries the ReLU mask)
-template <typename T, typename TD>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ x, const TD* __restrict__ dy,
+template <typename TX, typename T, typename TD>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy,
                                                            T* __restrict__ dx, long long n4, int C, float invR,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ invstd,

@@ -62,9 +62,10 @@ void layout(mg_gan* c, char* base) {
     c->g_hb = act("g.hb", B * 512);
     c->g_notes = b.get<float>("g.notes", B * T * 4);
     c->g_y0 = act("g.y0", B * L0 * 256);
-    c->g_x1 = act("g.x1", B * 2 * L0 * 128);
+    c->g_x1 = b.get<float>("g.x1", B * 2 * L0 * 128);     // pre-BatchNorm outputs stay float32: |mean| >> std would
+                                                              // otherwise eat the bf16 mantissa (x - mean is what BN uses)
     c->g_y1 = act("g.y1", B * 2 * L0 * 128);
-    c->g_x2 = act("g.x2", B * 4 * L0 * 64);
+    c->g_x2 = b.get<float>("g.x2", B * 4 * L0 * 64);
     c->g_y2 = act("g.y2", B * 4 * L0 * 64);
     c->g_bn1_stats = b.get<float>("g.bn1.stats", 256);
     c->g_bn1_mean = b.get<float>("g.bn1.mean", 128);
@@ -209,10 +210,10 @@ int fe_backward(mg_gan* c, const float* demb, cudaStream_t st) {
 // A-2..A-4 Generator
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-int bn_train_or_eval(mg_gan* c, const T* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
+int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
                      const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st) {
     if (train) {
-        MG_TRY((colreduce<T, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
+        MG_TRY((colreduce<float, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
                                          1.0f, 0, st)));
         bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows, (float)c->cfg.bn_eps,
                                                             (float)c->cfg.bn_momentum, mean, invstd, rm, rv, 1);
@@ -221,7 +222,7 @@ int bn_train_or_eval(mg_gan* c, const T* x, T* y, long long rows, int C, float* 
     }
     MG_LAUNCH_OK();
     const long long n4 = rows * C / 4;
-    bn_relu_apply_kernel<T><<<grid_for(n4), 256, 0, st>>>(x, y, n4, C, mean, invstd, gamma, beta);
+    bn_relu_apply_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(x, y, n4, C, mean, invstd, gamma, beta);
     MG_LAUNCH_OK();
     return MG_OK;
 }
@@ -243,14 +244,14 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
     MG_TRY((linear_fwd<T, T>((const T*)c->g_hb, (T*)c->g_y0, c->G.p2_w, c->G.p2_b, B, 512, 256 * L0, ACT_RELU, nullptr, st,
                              256, L0)));
     // deconv.0 -> BN -> ReLU
-    MG_TRY((upsample2_fwd<T, T>((const T*)c->g_y0, (T*)c->g_x1, c->G.d0_w, c->G.d0_b, B, L0, 256, 128, 5, 128 * 5,
-                                ACT_NONE, nullptr, MUL_NONE, 0, st)));
-    MG_TRY((bn_train_or_eval<T>(c, (const T*)c->g_x1, (T*)c->g_y1, (long long)B * 2 * L0, 128, c->g_bn1_stats,
+    MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y0, c->g_x1, c->G.d0_w, c->G.d0_b, B, L0, 256, 128, 5, 128 * 5,
+                                    ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    MG_TRY((bn_train_or_eval<T>(c, c->g_x1, (T*)c->g_y1, (long long)B * 2 * L0, 128, c->g_bn1_stats,
                                 c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->G.bn1_b, c->G.bn1_rm, c->G.bn1_rv, train, st)));
     // deconv.3 -> BN -> ReLU
-    MG_TRY((upsample2_fwd<T, T>((const T*)c->g_y1, (T*)c->g_x2, c->G.d3_w, c->G.d3_b, B, 2 * L0, 128, 64, 5, 64 * 5,
-                                ACT_NONE, nullptr, MUL_NONE, 0, st)));
-    MG_TRY((bn_train_or_eval<T>(c, (const T*)c->g_x2, (T*)c->g_y2, (long long)B * 4 * L0, 64, c->g_bn2_stats,
+    MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y1, c->g_x2, c->G.d3_w, c->G.d3_b, B, 2 * L0, 128, 64, 5, 64 * 5,
+                                    ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    MG_TRY((bn_train_or_eval<T>(c, c->g_x2, (T*)c->g_y2, (long long)B * 4 * L0, 64, c->g_bn2_stats,
                                 c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st)));
     // deconv.6 -> notes (B, T, 4) float32, already in the reference's permuted (B, notes, 4) order
     float* notes = notes_out ? notes_out : c->g_notes;
@@ -263,15 +264,15 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
 }
 
 template <typename T>
-int bn_backward(mg_gan* c, const T* x, const float* dy, T* dx, long long rows, int C, const float* mean,
+int bn_backward(mg_gan* c, const float* x, const float* dy, T* dx, long long rows, int C, const float* mean,
                 const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st) {
     // sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat
-    MG_TRY((colreduce<T, COL_BN_BWD, float>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
+    MG_TRY((colreduce<float, COL_BN_BWD, float>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
                                      0, st)));
     add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
     MG_LAUNCH_OK();
     const long long n4 = rows * C / 4;
-    bn_bwd_apply_kernel<T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
+    bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
                                                          c->g_bn_sums);
     MG_LAUNCH_OK();
     return MG_OK;
@@ -288,7 +289,7 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     MG_TRY((conv_fwd<float, float, T>(dnotes, c->g_dy2, c->G.d6_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr,
                                nullptr, c->g_y2, MUL_RELU_SIGN, st, /*w_nstride (n=ci)*/ 4 * 5, /*w_kstride (k=co)*/ 5)));
     // ---- BN2 backward ----
-    MG_TRY((bn_backward<T>(c, (const T*)c->g_x2, c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
+    MG_TRY((bn_backward<T>(c, c->g_x2, c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
                            c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->gG.bn2_w, c->gG.bn2_b, st)));
     // ---- deconv.3 ----
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx2, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
@@ -296,7 +297,7 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     MG_TRY((convT_wgrad<T, T>((const T*)c->g_y1, (const T*)c->g_dx2, c->gG.d3_w, B, 2 * L0, 128, 64, st)));
     MG_TRY((conv_fwd<T, float, T>((const T*)c->g_dx2, c->g_dy1, c->G.d3_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE,
                                   nullptr, nullptr, c->g_y1, MUL_RELU_SIGN, st, 64 * 5, 5)));
-    MG_TRY((bn_backward<T>(c, (const T*)c->g_x1, c->g_dy1, (T*)c->g_dx1, (long long)B * 2 * L0, 128,
+    MG_TRY((bn_backward<T>(c, c->g_x1, c->g_dy1, (T*)c->g_dx1, (long long)B * 2 * L0, 128,
                            c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->gG.bn1_w, c->gG.bn1_b, st)));
     // ---- deconv.0 ----
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx1, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,

@@ -5,6 +5,7 @@
 
 #include "elem.cuh"
 #include "gemm_tc.cuh"
+#include "thin.cuh"
 
 struct mg_gan {
     mg_gan_config cfg;
@@ -39,8 +40,8 @@ struct mg_gan {
     const float *e_mask1 = nullptr, *e_mask2 = nullptr;   // masks of the last train-mode forward (caller memory)
     const float* e_numeric = nullptr;
     // Generator
-    float *g_xcat, *g_ha, *g_lat, *g_notes;
-    void *g_hb, *g_y0, *g_x1, *g_y1, *g_x2, *g_y2;                 // activation dtype
+    float *g_xcat, *g_ha, *g_lat, *g_notes, *g_x1, *g_x2;
+    void *g_hb, *g_y0, *g_y1, *g_y2;                 // activation dtype
     float *g_bn1_stats, *g_bn1_mean, *g_bn1_is, *g_bn2_stats, *g_bn2_mean, *g_bn2_is, *g_bn_sums;
     float *g_dy2, *g_dy1;                                   // float32 even in bf16 mode (BN backward)
     void *g_dx2, *g_dx1, *g_dy0;

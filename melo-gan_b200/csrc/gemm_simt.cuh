@@ -314,13 +314,20 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st);
 template <typename TG, typename TA>
 int try_tc_wgrad(const WgradArgs& P, cudaStream_t st);
 }  // namespace tc
+namespace thin {   // bandwidth-class kernels for the 4-channel layers (thin.cuh); same return convention
+template <typename TA, typename TO, typename TMSK>
+int try_thin_tapgemm(const TapGemmArgs& P, cudaStream_t st);
+template <typename TG, typename TA>
+int try_thin_wgrad(const WgradArgs& P, cudaStream_t st);
+}  // namespace thin
 
 template <typename TA, typename TO, typename TMSK = TO>
 int launch_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     const long long rows = (long long)P.B * P.Mper;
     if (rows == 0 || P.N == 0) return MG_OK;
     {
-        const int r = tc::try_tc_tapgemm<TA, TO, TMSK>(P, st);
+        int r = tc::try_tc_tapgemm<TA, TO, TMSK>(P, st);
+        if (r == 0) r = thin::try_thin_tapgemm<TA, TO, TMSK>(P, st);
         if (r != 0) return r < 0 ? r : MG_OK;
     }
     const size_t ea = sizeof(TA), eo = sizeof(TO);
@@ -451,7 +458,8 @@ int launch_wgrad(const WgradArgs& P, cudaStream_t st) {
     const long long nrows = (long long)P.row_end - P.row_begin;
     if (nrows <= 0 || P.N == 0) return MG_OK;
     {
-        const int r = tc::try_tc_wgrad<TG, TA>(P, st);
+        int r = tc::try_tc_wgrad<TG, TA>(P, st);
+        if (r == 0) r = thin::try_thin_wgrad<TG, TA>(P, st);
         if (r != 0) return r < 0 ? r : MG_OK;
     }
     const int Ktot = P.ntaps * P.K;

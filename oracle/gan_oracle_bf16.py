@@ -1,0 +1,92 @@
+"""bf16-storage emulation of the GAN-step oracle (TEST INFRASTRUCTURE ONLY, same rules as gan_oracle.py).
+
+The CUDA path's bf16 mode stores activations (and the tensor-core layers' weights) in bfloat16 and accumulates in
+float32.  This module restates gan_oracle's forwards with a straight-through bfloat16 rounding `q` at exactly those
+storage points, everything else in float32 on the CPU.  It answers "what does bf16 storage
+alone do to the step?" so that the CUDA bf16 path can be held to a TIGHT tolerance against it, while its distance
+to the float32 oracle documents the accepted bf16-mode error (north_star: 1e-2 on activations and losses).
+"""
+import torch
+import torch.nn.functional as F
+
+from oracle import gan_oracle as O
+
+
+def q(t):
+    """Round to bfloat16 storage, identity for autograd (also under double backward)."""
+    return t + (t.to(torch.bfloat16).to(torch.float32) - t).detach()
+
+
+def gen_forward(P, noise, emb, bn_state):
+    x = torch.cat([noise, emb], 1)
+    h = F.relu(F.linear(x, P["noise_to_latent.net.0.weight"], P["noise_to_latent.net.0.bias"]))
+    latent = F.linear(h, P["noise_to_latent.net.2.weight"], P["noise_to_latent.net.2.bias"])
+    y = q(F.relu(F.linear(latent, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"])))
+    y = q(F.relu(F.linear(y, q(P["decoder.pre.2.weight"]), P["decoder.pre.2.bias"])))
+    y = y.view(y.shape[0], 256, -1)
+    for conv, bn in (("decoder.deconv.0", "decoder.deconv.1"), ("decoder.deconv.3", "decoder.deconv.4")):
+        y = F.conv_transpose1d(y, q(P[conv + ".weight"]), P[conv + ".bias"], stride=2, padding=2, output_padding=1)
+        y = F.batch_norm(y, bn_state[bn + ".running_mean"], bn_state[bn + ".running_var"], P[bn + ".weight"],
+                         P[bn + ".bias"], training=True, momentum=0.1, eps=1e-5)     # pre-BN output stays float32
+        y = q(F.relu(y))
+    y = F.conv_transpose1d(y, P["decoder.deconv.6.weight"], P["decoder.deconv.6.bias"], stride=2, padding=2,
+                           output_padding=1)                                          # C_out = 4: float32 weights
+    return y.permute(0, 2, 1), latent
+
+
+def disc_forward(P, notes, emb):
+    h = notes.permute(0, 2, 1)
+    for i, name in enumerate(("conv.0", "conv.2", "conv.4")):
+        w = P[name + ".weight"] if i == 0 else q(P[name + ".weight"])                 # conv.0 (C_in = 4) is not a TC layer
+        h = q(F.leaky_relu(F.conv1d(h, w, P[name + ".bias"], stride=2, padding=2), 0.2))
+    h = F.adaptive_avg_pool1d(h, 1)
+    feat = F.leaky_relu(F.linear(h.view(h.size(0), -1), P["fc.1.weight"], P["fc.1.bias"]), 0.2)
+    feat = torch.cat([feat, emb], 1)
+    return F.linear(feat, P["real_fake.weight"], P["real_fake.bias"]).squeeze(1)
+
+
+def ed_forward(P, notes):
+    x = notes.permute(0, 2, 1)
+    for i in range(4):
+        pre = f"encoder.conv.{i}.net."
+        w = P[pre + "0.weight"] if i == 0 else q(P[pre + "0.weight"])
+        x = F.conv1d(x, w, P[pre + "0.bias"], stride=1, padding=2 if i == 0 else 1)
+        x = F.batch_norm(x, P[pre + "1.running_mean"], P[pre + "1.running_var"], P[pre + "1.weight"], P[pre + "1.bias"],
+                         training=False, eps=1e-5)
+        x = q(F.gelu(x))
+    x = F.adaptive_avg_pool1d(x, 1).squeeze(-1)
+    x = F.linear(x, P["encoder.project.weight"], P["encoder.project.bias"])
+    x = F.gelu(F.linear(x, P["classifier.net.0.weight"], P["classifier.net.0.bias"]))
+    x = F.gelu(F.linear(x, P["classifier.net.3.weight"], P["classifier.net.3.bias"]))
+    return F.linear(x, P["classifier.head.weight"], P["classifier.head.bias"])
+
+
+def generator_step(params, batch, cfg=O.CFG):
+    PE, PG, PD, PED = params["E"], params["G"], params["D"], params["ED"]
+    El, Gl = O._leaves(PE), O._leaves(PG)
+    bn_state = {k: v.clone() for k, v in PG.items() if O.is_buffer(k)}
+    emb = O.fe_forward(El, batch["numeric"], batch["mask1_g"], batch["mask2_g"], train=True, p_drop=cfg["ENC_DROPOUT"])
+    notes, latent = gen_forward(Gl, batch["noise_g"], emb, bn_state)
+    loss_adv = -disc_forward(PD, notes, emb).mean()
+    logits = ed_forward(PED, notes)
+    loss_emo = F.cross_entropy(logits, batch["emot_idx"])
+    g = torch.autograd.grad(loss_adv + cfg["LAMBDA_EMOTION"] * loss_emo, list(Gl.values()) + list(El.values()))
+    return {"loss_g_adv": loss_adv.detach(), "loss_g_emo": loss_emo.detach(), "notes": notes.detach(),
+            "grads_G": dict(zip(Gl.keys(), g[:len(Gl)])), "grads_E": dict(zip(El.keys(), g[len(Gl):]))}
+
+
+def critic_step(params, batch, cfg=O.CFG):
+    PE, PG, PD = params["E"], params["G"], params["D"]
+    with torch.no_grad():
+        emb = O.fe_forward(PE, batch["numeric"], batch["mask1_d"], batch["mask2_d"], train=True, p_drop=cfg["ENC_DROPOUT"])
+        fake, _ = gen_forward(PG, batch["noise_d"], emb, {k: v.clone() for k, v in PG.items() if O.is_buffer(k)})
+        fake = fake.contiguous()
+    Dl = O._leaves(PD)
+    real = batch["notes_real"]
+    a = batch["alpha"].view(-1, 1, 1).expand_as(real)
+    interp = (a * real + (1 - a) * fake).requires_grad_(True)
+    gr = torch.autograd.grad(disc_forward(Dl, interp, emb).sum(), interp, create_graph=True)[0].reshape(real.size(0), -1)
+    gp = ((gr.norm(2, dim=1) - 1) ** 2).mean()
+    loss = disc_forward(Dl, fake, emb).mean() - disc_forward(Dl, real, emb).mean() + cfg["LAMBDA_GP"] * gp
+    return {"loss_d": loss.detach(), "gp": gp.detach(), "fake": fake,
+            "grads": dict(zip(Dl.keys(), torch.autograd.grad(loss, list(Dl.values()))))}

@@ -8,12 +8,16 @@ from oracle import gan_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+from oracle import gan_oracle_bf16 as OB
+
 TOL = 1e-2          # losses: relative; activation tensors: relative L2 (and 2x that in max-norm)
+EMU_TOL = 4e-2      # gradients against the bf16-STORAGE-EMULATING oracle (same rounding points, CPU float32 math):
+                    # what is left is the bf16 rounding of activation gradients and summation order
 # Gradients (relative L2): a bf16 forward moves ~0.3% of the near-zero pre-activations across zero relative to the
 # fp32 oracle; each such LeakyReLU/ReLU mask flip changes one activation-gradient element by O(1), i.e. about
 # 0.8*sqrt(0.003) = 4% in L2 per masked layer, compounding along the backward chain ("bf16 mode").
 # Exactness of the kernels themselves is pinned by the fp32-mode tests and by test_tc_vs_simt_gpu.py.
-GRAD_TOL = 0.15
+GRAD_TOL = 0.3      # against the float32 oracle: documents the bf16-mode error, see above and gan_oracle_bf16.py
 
 
 @pytest.mark.parametrize("B,fan,pseed", [(8, True, 4), (32, False, 2), (160, True, 7)])
@@ -28,12 +32,14 @@ def test_bf16_critic_step(B, fan, pseed):
     assert abs(m[1].item() - ref["gp"].item()) <= TOL * max(abs(ref["gp"].item()), 1.0)
     assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), ref["fake"], TOL, "fake notes")
     assert_close(eng.buffer("g.notes").view(B, 512, 4), ref["fake"], 2 * TOL, "fake notes (max-norm)")
+    emu = OB.critic_step(O.clone_params(params), batch)
     for k, g in ref["grads"].items():
         if k.startswith("real_fake"):
             continue
         if k.endswith("bias"):
             continue      # sums of +1/B and -1/B weighted terms: cancellation-dominated (see fp32 tests)
         assert_close_l2(grads["D"][k], g, GRAD_TOL, "D grad " + k)
+        assert_close_l2(grads["D"][k], emu["grads"][k], EMU_TOL, "D grad vs bf16-emulating oracle " + k)
 
 
 @pytest.mark.parametrize("B,fan,pseed", [(8, True, 4), (32, False, 2), (160, True, 7)])
@@ -49,10 +55,13 @@ def test_bf16_generator_step(B, fan, pseed):
     assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), ref["notes"], TOL, "notes")
     assert_close(eng.buffer("g.notes").view(B, 512, 4), ref["notes"], 2 * TOL, "notes (max-norm)")
     assert_close(eng.buffer("ed.logits")[:B * 4].view(B, 4), ref["logits"], TOL, "logits")
+    emu = OB.generator_step(O.clone_params(params), batch)
+    assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), emu["notes"], 2e-3, "notes vs bf16-emulating oracle")
     for k, g in ref["grads_G"].items():
         if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias"):
             continue
-        # the small bias vectors at the far end of the chain (64..512 elements, B samples) average fewer flips
-        assert_close_l2(grads["G"][k], g, 2 * GRAD_TOL if k.endswith("bias") else GRAD_TOL, "G grad " + k)
+        assert_close_l2(grads["G"][k], g, GRAD_TOL, "G grad " + k)
+        assert_close_l2(grads["G"][k], emu["grads_G"][k], EMU_TOL, "G grad vs bf16-emulating oracle " + k)
     for k, g in ref["grads_E"].items():
         assert_close_l2(grads["E"][k], g, GRAD_TOL, "E grad " + k)
+        assert_close_l2(grads["E"][k], emu["grads_E"][k], EMU_TOL, "E grad vs bf16-emulating oracle " + k)

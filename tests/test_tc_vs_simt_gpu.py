@@ -10,7 +10,7 @@ from oracle import gan_oracle as O
 pytestmark = pytest.mark.gpu
 
 ACT_BUFFERS_D = [("d.h2", torch.bfloat16), ("d.h3", torch.bfloat16), ("d.dz2", torch.bfloat16), ("d.dz1", torch.bfloat16)]
-ACT_BUFFERS_G = [("g.y0", torch.bfloat16), ("g.x1", torch.bfloat16), ("g.x2", torch.bfloat16), ("ed.h1", torch.bfloat16),
+ACT_BUFFERS_G = [("g.y0", torch.bfloat16), ("g.x1", torch.float32), ("g.x2", torch.float32), ("ed.h1", torch.bfloat16),
                  ("ed.h2", torch.bfloat16), ("ed.h3", torch.bfloat16), ("g.dy1", torch.float32), ("g.dy0", torch.bfloat16),
                  ("g.dhb", torch.float32), ("d.dnotes", torch.float32)]
 
