@@ -45,6 +45,14 @@ bool enabled() {
     }
     return g_enabled == 1;
 }
+bool ws_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MELOGAN_DISABLE_WS");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
 int set_enabled(int on) {
     const int prev = enabled() ? 1 : 0;
     g_enabled = on ? 1 : 0;

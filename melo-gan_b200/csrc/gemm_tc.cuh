@@ -143,6 +143,87 @@ struct TcTapArgs {
     float alpha; int accumulate;
 };
 
+// Drain one 128 x BN accumulator tile: TMEM -> registers -> bias/scale/activation/mask -> global.
+// `wait_bar`/`wait_parity`: the MMA->epilogue barrier of this accumulator.  The mask row is prefetched BEFORE the wait.
+// NC = number of accumulator columns this warp drains, starting at column c_begin (two epilogue warpgroups split a tile).
+template <int BN, int NC, typename TO, typename TMSK>
+__device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bias, const float* s_scale, uint32_t tmem_acc,
+                                           int b0, int m0, int n0, int warp, int lane, uint64_t* wait_bar,
+                                           uint32_t wait_parity, int c_begin = 0) {
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;             // tile row
+        const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
+        const bool row_ok = bb < P.B;
+        TO* __restrict__ Ob = static_cast<TO*>(P.Out);
+        const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
+        TO* __restrict__ Xb = static_cast<TO*>(P.aux);
+        const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
+        constexpr bool kPrefetchMask = sizeof(TMSK) == 2;
+        constexpr int kMaskVecs = kPrefetchMask ? NC / 8 : 1;
+        uint4 mreg[kMaskVecs];
+        if (kPrefetchMask && P.mul_mode != MUL_NONE && row_ok) {
+#pragma unroll
+            for (int i = 0; i < kMaskVecs; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o + c_begin) + i);
+        }
+        mbar_wait(wait_bar, wait_parity);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_begin + NC; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!row_ok) continue;
+            float ms[16];
+            if (P.mul_mode != MUL_NONE) {
+                if (kPrefetchMask) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint4 mv = mreg[((c0 - c_begin) >> 3) + h];
+                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            ms[h * 8 + 2 * e] = __uint_as_float(w[e] << 16);
+                            ms[h * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int g4 = 0; g4 < 16; g4 += 4) {
+                        float t4[4];
+                        ld4(Mb + o + c0 + g4, t4);
+                        ms[g4] = t4[0]; ms[g4 + 1] = t4[1]; ms[g4 + 2] = t4[2]; ms[g4 + 3] = t4[3];
+                    }
+                }
+            }
+            float old[16];
+            if (P.accumulate) {
+#pragma unroll
+                for (int g4 = 0; g4 < 16; g4 += 4) {
+                    float t4[4];
+                    ld4(Ob + o + c0 + g4, t4);
+                    old[g4] = t4[0]; old[g4 + 1] = t4[1]; old[g4 + 2] = t4[2]; old[g4 + 3] = t4[3];
+                }
+            }
+#pragma unroll
+            for (int g4 = 0; g4 < 16; g4 += 4) {
+                float x[4], gd[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y = fmaf(v[g4 + j], s_scale[c0 + g4 + j], s_bias[c0 + g4 + j]);
+                    if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
+                    else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
+                    else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[j]); y = yy; }
+                    if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.2f);
+                    else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.0f);
+                    else if (P.mul_mode == MUL_VALUE) y *= ms[g4 + j];
+                    if (P.accumulate) y += old[g4 + j];
+                    x[j] = y;
+                }
+                st4(Ob + o + c0 + g4, x);
+                if (P.aux) st4(Xb + o + c0 + g4, gd);
+            }
+        }
+}
+
 template <int BN>
 struct TapSmem {
     __nv_bfloat16 a[kStages][kTileM * kTileK];
@@ -229,85 +310,144 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
             S.bias[i] = P.bias ? __ldg(P.bias + perm_index(n0 + i, P.n_perm_q, P.n_perm_p)) : 0.0f;
             S.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
         }
-        const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int r = q * 32 + lane;             // tile row
-        const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
-        const bool row_ok = bb < P.B;
-        TO* __restrict__ Ob = static_cast<TO*>(P.Out);
-        const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
-        TO* __restrict__ Xb = static_cast<TO*>(P.aux);
-        const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
-        constexpr bool kPrefetchMask = sizeof(TMSK) == 2;
-        constexpr int kMaskVecs = kPrefetchMask ? BN / 8 : 1;
-        uint4 mreg[kMaskVecs];
-        if (kPrefetchMask && P.mul_mode != MUL_NONE && row_ok) {
-#pragma unroll
-            for (int i = 0; i < kMaskVecs; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o) + i);
-        }
         asm volatile("bar.sync 1, 128;" ::: "memory");    // bias/scale staged (epilogue warps only)
-        mbar_wait(&S.tmem_full, 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (!row_ok) continue;
-            float ms[16];
-            if (P.mul_mode != MUL_NONE) {
-                if (kPrefetchMask) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint4 mv = mreg[(c0 >> 3) + h];
-                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            ms[h * 8 + 2 * e] = __uint_as_float(w[e] << 16);
-                            ms[h * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int g4 = 0; g4 < 16; g4 += 4) {
-                        float t4[4];
-                        ld4(Mb + o + c0 + g4, t4);
-                        ms[g4] = t4[0]; ms[g4 + 1] = t4[1]; ms[g4 + 2] = t4[2]; ms[g4 + 3] = t4[3];
-                    }
-                }
-            }
-            float old[16];
-            if (P.accumulate) {
-#pragma unroll
-                for (int g4 = 0; g4 < 16; g4 += 4) {
-                    float t4[4];
-                    ld4(Ob + o + c0 + g4, t4);
-                    old[g4] = t4[0]; old[g4 + 1] = t4[1]; old[g4 + 2] = t4[2]; old[g4 + 3] = t4[3];
-                }
-            }
-#pragma unroll
-            for (int g4 = 0; g4 < 16; g4 += 4) {
-                float x[4], gd[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float y = fmaf(v[g4 + j], S.scale[c0 + g4 + j], S.bias[c0 + g4 + j]);
-                    if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
-                    else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
-                    else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[j]); y = yy; }
-                    if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.2f);
-                    else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.0f);
-                    else if (P.mul_mode == MUL_VALUE) y *= ms[g4 + j];
-                    if (P.accumulate) y += old[g4 + j];
-                    x[j] = y;
-                }
-                st4(Ob + o + c0 + g4, x);
-                if (P.aux) st4(Xb + o + c0 + g4, gd);
-            }
-        }
+        drain_tile<BN, BN, TO, TMSK>(P, S.bias, S.scale, tmem_acc, b0, m0, n0, warp, lane, &S.tmem_full, 0);
         tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_acc, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-stationary persistent tap-GEMM
+// ---------------------------------------------------------------------------------------------
+// The conv layers here are skinny (C = 64..256): a 128 x BN output tile re-fetching its weight tile per k-block moves
+// as many bytes from L2 as its activation tile and the kernel is L2-bound at ~10 % tensor utilisation.  In this form
+// a CTA owns one BN-wide slab of output channels for its whole life: the packed weights of ALL taps for that slab are
+// TMA-loaded into shared memory once (<= 192 KB), the CTA then walks M tiles (grid-strided), streaming only activation
+// tiles through a small ring, with two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+constexpr int kWsMaxStages = 8;
+constexpr int kWsThreads = 320;      // TMA warp, MMA warp, 2 x 4 epilogue warps (each warpgroup drains half the columns)
+template <int BN>
+struct WsHeader {
+    uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+    float bias[BN], scale[BN];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, typename TO, typename TMSK>
+__global__ void __launch_bounds__(kWsThreads) tc_tapgemm_ws_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                            const __grid_constant__ CUtensorMap b_map, const TcTapArgs P,
+                                                            int mtiles, int nstages) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    WsHeader<BN>& H = *reinterpret_cast<WsHeader<BN>*>(base);
+    const int nkb = P.ntaps * P.kblocks;
+    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(base + 2048);                       // [nkb][BN][64]
+    __nv_bfloat16* asm_ = wsm + (size_t)nkb * BN * kTileK;                                    // [nstages][128][64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BN;
+    constexpr uint32_t kABytes = kTileM * kTileK * 2, kWBytes = BN * kTileK * 2;
+    const int n0 = blockIdx.y * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstages; ++s) { mbar_init(&H.full[s], 1); mbar_init(&H.empty[s], 1); }
+        mbar_init(&H.wfull, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&H.tmem_full[a], 1); mbar_init(&H.tmem_empty[a], 1); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(&H.tmem_base, kTmemCols);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&a_map); tma_prefetch_desc(&b_map); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = H.tmem_base;
+
+    auto tile_coords = [&](int tile, int& b0, int& m0) {
+        if (P.mpt == kTileM) { const int tm = P.Mper / kTileM; b0 = tile / tm; m0 = (tile % tm) * kTileM; }
+        else { b0 = tile * P.bpt; m0 = 0; }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&H.wfull, (uint32_t)nkb * kWBytes);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
+                tma_load_2d(&b_map, &H.wfull, wsm + (size_t)kb * BN * kTileK, kc * kTileK, P.b_row[t] + n0);
+            }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
+                int b0, m0;
+                tile_coords(tile, b0, m0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % nstages, ph = (it / nstages) & 1;
+                    mbar_wait(&H.empty[s], ph ^ 1);
+                    const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
+                    mbar_expect_tx(&H.full[s], kABytes);
+                    tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * kTileM * kTileK, kc * kTileK, P.a_p[t],
+                                m0 + P.a_dm[t], b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        mbar_wait(&H.wfull, 0);
+        int it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
+            const int acc = tcount & 1;
+            mbar_wait(&H.tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem0 + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % nstages, ph = (it / nstages) & 1;
+                mbar_wait(&H.full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(asm_ + (size_t)s * kTileM * kTileK);
+                    const uint32_t b_addr = smem_u32(wsm + (size_t)kb * BN * kTileK);
+#pragma unroll
+                    for (int k = 0; k < kTileK / 16; ++k)
+                        umma_f16(tacc, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
+                                 idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&H.empty[s]);
+                    if (kb == nkb - 1) umma_commit(&H.tmem_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int et = threadIdx.x - 64;                 // 0..255
+        const int half = et >> 7;                        // which half of the BN columns this warpgroup drains
+        for (int i = et; i < BN; i += 256) {
+            H.bias[i] = P.bias ? __ldg(P.bias + perm_index(n0 + i, P.n_perm_q, P.n_perm_p)) : 0.0f;
+            H.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
+            const int acc = tcount & 1;
+            int b0, m0;
+            tile_coords(tile, b0, m0);
+            drain_tile<BN, BN / 2, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
+                                             &H.tmem_full[acc], (tcount >> 1) & 1, half * (BN / 2));
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // every epilogue thread has read its TMEM lanes
+            if (et == 0) mbar_arrive(&H.tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem0, kTmemCols);
     }
 }
 
@@ -460,6 +600,7 @@ struct Scratch {             // ring of packed-weight slots (stream-ordered reus
 Scratch& scratch();
 int ensure_scratch(size_t elems);   // allocate the ring (not capturable: call before any CUDA-graph capture)
 bool enabled();              // MELOGAN_DISABLE_TC=1 forces the CUDA-core kernels (A/B testing)
+bool ws_enabled();           // MELOGAN_DISABLE_WS=1 keeps the non-persistent tensor-core kernel (A/B profiling)
 
 // 4-D view (k, parity, row, sample) of a channels-last activation [B][L][C] (bf16):
 //   stride 1: dims (C, 1, L, B);  stride 2: dims (C, 2, L/2, B)
@@ -478,6 +619,21 @@ int launch_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs&
     }
     dim3 grid(mtiles, a.N / BN);
     tc_tapgemm_kernel<BN, TO, TMSK><<<grid, 192, smem, st>>>(am, bm, a);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+template <int BN, typename TO, typename TMSK>
+int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a, int mtiles, int nstages,
+                     int ctas_x, size_t smem, cudaStream_t st) {
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_ws_kernel<BN, TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(227 * 1024)));
+        attr_smem = 227 * 1024;
+    }
+    dim3 grid(ctas_x, a.N / BN);
+    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, kWsThreads, smem, st>>>(am, bm, a, mtiles, nstages);
     MG_LAUNCH_OK();
     return MG_OK;
 }
@@ -556,6 +712,24 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     const int mtiles = (int)((rows + 127) / 128);
     ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * P.N * P.ntaps * P.K,
                      (double)rows * (P.K * 2.0 + P.N * sizeof(TO)), st);
+    // weight-stationary persistent form when the slab's weights fit in shared memory next to >= 2 activation stages
+    // and every CTA gets at least 4 tiles to amortise loading them
+    {
+        const int nslabs = P.N / BN;
+        const size_t wbytes = (size_t)P.ntaps * (P.K / 64) * BN * 128;
+        const size_t avail = (size_t)227 * 1024 - 1024 - 2048;
+        int ctas_x = num_sms() / nslabs;
+        if (ctas_x < 1) ctas_x = 1;
+        if (ctas_x > mtiles) ctas_x = mtiles;
+        if (ws_enabled() && wbytes + 4 * 16384 <= avail && mtiles >= 4 * ctas_x) {
+            int nstages = (int)((avail - wbytes) / 16384);
+            if (nstages > kWsMaxStages) nstages = kWsMaxStages;
+            const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * 16384;
+            rc = (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st)
+                             : launch_tc_tap_ws<64, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st);
+            return rc == MG_OK ? 1 : rc;
+        }
+    }
     rc = (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
     return rc == MG_OK ? 1 : rc;
 }
