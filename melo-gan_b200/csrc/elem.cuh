@@ -68,6 +68,66 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
     }
 }
 
+// vectorised form: every thread owns 4 consecutive columns (one 8/16-byte load per row), 8 row lanes per CTA
+template <typename T, typename TY, int OP>
+__global__ void __launch_bounds__(256) colreduce_vec4_kernel(const ColReduceArgs P) {
+    constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
+    __shared__ float red[NOUT][8][32][4 + 1];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + cx) * 4;
+    const long long rb = P.r0 + (long long)blockIdx.y * P.rows_per_chunk;
+    long long re = rb + P.rows_per_chunk;
+    if (re > P.r1) re = P.r1;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < P.C) {
+        const T* x = static_cast<const T*>(P.x);
+        const TY* y = static_cast<const TY*>(P.y);
+        float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {0.f, 0.f, 0.f, 0.f};
+        if (OP == COL_BN_BWD) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { mu[e] = P.mean[c + e]; is[e] = P.invstd[c + e]; }
+        }
+#pragma unroll 4
+        for (long long r = rb + ry; r < re; r += 8) {
+            float xv[4];
+            ld4(x + r * P.ldx + c, xv);
+            if (OP == COL_SUM) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a0[e] += xv[e];
+            } else if (OP == COL_SUM_SQ) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a0[e] += xv[e]; a1[e] = fmaf(xv[e], xv[e], a1[e]); }
+            } else if (OP == COL_BN_BWD) {
+                float dy[4];
+                ld4(y + r * P.ldy + c, dy);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a0[e] += dy[e]; a1[e] = fmaf(dy[e], (xv[e] - mu[e]) * is[e], a1[e]); }
+            } else {
+                const float w = P.roww[r / P.roww_div];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a0[e] = fmaf(w, xv[e], a0[e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        red[0][ry][cx][e] = a0[e];
+        if (NOUT == 2) red[1][ry][cx][e] = a1[e];
+    }
+    __syncthreads();
+    // 32 column groups x 4 columns x NOUT outputs = up to 256 sums: one per thread
+    {
+        const int k = threadIdx.x / 128, rem = threadIdx.x % 128, gx = rem / 4, e = rem % 4;
+        const int cc = (blockIdx.x * 32 + gx) * 4 + e;
+        if (k < NOUT && cc < P.C) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += red[k][j][gx][e];
+            P.partial[((long long)blockIdx.y * NOUT + k) * P.C + cc] = s;
+        }
+    }
+}
+
 // out[k*out_kstride + perm(c)] (+)= alpha * sum_chunks partial[chunk][k][c]   (float64 accumulation)
 __global__ void colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout, int C, float* out,
                                         int out_kstride, int perm_q, int perm_p, float alpha, int accumulate) {
@@ -151,41 +211,62 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __restrict_
 // pooling and broadcast
 // ---------------------------------------------------------------------------------------------
 // out[s, c] = scale * sum_l x[s, l, c]        (AdaptiveAvgPool1d(1): scale = 1/L)
+// thread = (sample, 4 channels, row lane); C/4 * RL threads per sample, RL row lanes combined through shared memory
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) pool_rows_kernel(const T* __restrict__ x, TO* __restrict__ out, int S, int L,
                                                         int C, float scale) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
-    if (c >= C || s >= S) return;
-    const T* p = x + ((long long)s * L) * C + c;
-    float a = 0.f;
-    for (int l = 0; l < L; ++l) a += ld_as_float(p + (long long)l * C);
-    st_from_float(out + (long long)s * C + c, a * scale);
+    __shared__ float red[256][4 + 1];
+    const int c4n = C / 4;                       // channel groups (C % 4 == 0, c4n <= 256)
+    const int RL = 256 / c4n;                    // row lanes
+    const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+    const int s = blockIdx.x;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rl < RL) {
+        const T* p = x + ((long long)s * L) * C + cg * 4;
+#pragma unroll 4
+        for (int l = rl; l < L; l += RL) {
+            float v[4];
+            ld4(p + (long long)l * C, v);
+            a[0] += v[0]; a[1] += v[1]; a[2] += v[2]; a[3] += v[3];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[threadIdx.x][e] = a[e];
+    __syncthreads();
+    if (rl == 0) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < RL; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t[e] += red[j * c4n + cg][e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) st_from_float(out + (long long)s * C + cg * 4 + e, t[e] * scale);
+    }
 }
 
 // out[s, l, c] = src[s, c] * scale * colscale[c] * f'(ref[s, l, c])
 //   mode MUL_LRELU_SIGN / MUL_RELU_SIGN: derivative from the sign of the saved activation; MUL_VALUE: ref holds f'
+// grid = (chunks, samples): all index arithmetic is 32-bit and per-sample
 template <typename TS, typename T>
 __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __restrict__ src, const T* __restrict__ ref,
-                                                             T* __restrict__ out, long long n4, int L, int C,
-                                                             float scale, const float* __restrict__ colscale,
-                                                             int mode) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long LC = (long long)L * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const long long e0 = i * 4;
-        const long long s = e0 / LC;
-        const int c = (int)(e0 % C);
+                                                             T* __restrict__ out, int L, int C, float scale,
+                                                             const float* __restrict__ colscale, int mode) {
+    const int s = blockIdx.y;
+    const int n4 = L * C / 4;
+    const T* r0 = ref + (long long)s * L * C;
+    T* o0 = out + (long long)s * L * C;
+    const TS* sp = src + (long long)s * C;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+        const int c = (i * 4) % C;
         float r[4], o[4];
-        ld4(ref + e0, r);
+        ld4(r0 + i * 4, r);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float d = (mode == MUL_LRELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.2f)
-                      : (mode == MUL_RELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.f) : r[e];
+            const float d = (mode == MUL_LRELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.2f)
+                            : (mode == MUL_RELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.f) : r[e];
             const float cs = colscale ? colscale[c + e] : 1.0f;
-            o[e] = ld_as_float(src + s * C + c + e) * scale * cs * d;
+            o[e] = ld_as_float(sp + c + e) * (scale * cs) * d;
         }
-        st4(out + e0, o);
+        st4(o0 + i * 4, o);
     }
 }
 

@@ -127,14 +127,16 @@ __global__ void __launch_bounds__(256) tapgemm_kernel(const TapGemmArgs P) {
     const int Ktot = P.ntaps * P.K;
     const TA* __restrict__ Abase = static_cast<const TA*>(P.A);
 
-    // ---- A loader: thread owns (BM*BK)/256 elements: ROWS_PER_THREAD rows x 8 consecutive kk ----
-    constexpr int A_ROWS_PT = BM / 128;            // BM=128 -> 1 row, BM=512 -> 4 rows
-    const int a_kk = (tid >> 7) * 8;               // 0 or 8
+    // ---- A loader: thread owns (BM*BK)/256 elements: ROWS_PER_THREAD rows x A_KPT consecutive kk ----
+    constexpr int A_ROWS_PT = BM >= 128 ? BM / 128 : 1;   // BM=64/128 -> 1 row, BM=512 -> 4 rows
+    constexpr int A_RSPAN = BM >= 128 ? 128 : 64;         // rows covered by one pass of the CTA's threads
+    constexpr int A_KPT = BM >= 128 ? 8 : 4;              // consecutive kk per thread
+    const int a_kk = (tid / A_RSPAN) * A_KPT;
     long long a_rowoff[A_ROWS_PT];                 // base element offset (b*a_bstride), or -1 if row is out of range
     int a_midx[A_ROWS_PT];
 #pragma unroll
     for (int i = 0; i < A_ROWS_PT; ++i) {
-        const long long r = row0 + (tid & 127) + i * 128;
+        const long long r = row0 + (tid % A_RSPAN) + i * A_RSPAN;
         if (r < rows) {
             const long long b = r / P.Mper;
             a_rowoff[i] = b * P.a_bstride;
@@ -156,10 +158,10 @@ __global__ void __launch_bounds__(256) tapgemm_kernel(const TapGemmArgs P) {
         // A tile
 #pragma unroll
         for (int i = 0; i < A_ROWS_PT; ++i) {
-            const int rloc = (tid & 127) + i * 128;
-            float v[8];
+            const int rloc = (tid % A_RSPAN) + i * A_RSPAN;
+            float v[A_KPT];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < A_KPT / 4; ++h) {
                 const int kk = kk0 + a_kk + h * 4;
                 float q[4] = {0.f, 0.f, 0.f, 0.f};
                 if (a_rowoff[i] >= 0 && kk < Ktot) {
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(256) tapgemm_kernel(const TapGemmArgs P) {
                 for (int e = 0; e < 4; ++e) v[h * 4 + e] = q[e];
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) As[buf][a_kk + e][rloc] = v[e];
+            for (int e = 0; e < A_KPT; ++e) As[buf][a_kk + e][rloc] = v[e];
         }
         // B tile: element (kk, n) = W[w_toff[t] + nphys*w_nstride + kphys*w_kstride]
         if (B_PT >= 1) {
@@ -343,6 +345,11 @@ int launch_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
         dim3 grid((unsigned)((rows + 511) / 512), (unsigned)((P.N + 7) / 8));
         if (vec) tapgemm_kernel<TA, TO, TMSK, 512, 8, 4, 4, 1, true><<<grid, 256, 0, st>>>(P);
         else tapgemm_kernel<TA, TO, TMSK, 512, 8, 4, 4, 1, false><<<grid, 256, 0, st>>>(P);
+    } else if (((rows + 127) / 128) * ((P.N + 63) / 64) < 2LL * num_sms()) {
+        // small problem (the MLPs of E_num / G / the critic and classifier heads): 64-row tiles for twice the CTAs
+        dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((P.N + 63) / 64));
+        if (vec) tapgemm_kernel<TA, TO, TMSK, 64, 64, 4, 4, 2, true><<<grid, 256, 0, st>>>(P);
+        else tapgemm_kernel<TA, TO, TMSK, 64, 64, 4, 4, 2, false><<<grid, 256, 0, st>>>(P);
     } else {
         dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((P.N + 63) / 64));
         if (vec) tapgemm_kernel<TA, TO, TMSK, 128, 64, 8, 4, 2, true><<<grid, 256, 0, st>>>(P);
