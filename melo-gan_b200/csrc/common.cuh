@@ -40,6 +40,12 @@ struct ProbeScope {
         }                                     \
     } while (0)
 
+#define MG_TRY(expr)                    \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != MG_OK) return _rc;   \
+    } while (0)
+
 #define MG_LAUNCH_OK()                      \
     do {                                    \
         MG_CUDA_OK(cudaGetLastError());     \

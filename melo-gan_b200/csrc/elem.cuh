@@ -129,16 +129,27 @@ __global__ void __launch_bounds__(256) colreduce_vec4_kernel(const ColReduceArgs
 }
 
 // out[k*out_kstride + perm(c)] (+)= alpha * sum_chunks partial[chunk][k][c]   (float64 accumulation)
-__global__ void colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout, int C, float* out,
-                                        int out_kstride, int perm_q, int perm_p, float alpha, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nout * C) return;
-    const int k = i / C, c = i - k * C;
+// 32 outputs per CTA, 8 chunk lanes each, combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout,
+                                                               int C, float* out, int out_kstride, int perm_q,
+                                                               int perm_p, float alpha, int accumulate) {
+    __shared__ double red[8][33];
+    const int cx = threadIdx.x & 31, jl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cx;
     double s = 0.0;
-    for (int j = 0; j < nchunk; ++j) s += (double)partial[((long long)j * nout + k) * C + c];
-    float* o = out + (long long)k * out_kstride + perm_index(c, perm_q, perm_p);
-    const float v = (float)(s * (double)alpha);
-    *o = accumulate ? *o + v : v;
+    if (i < nout * C)
+        for (int j = jl; j < nchunk; j += 8) s += (double)partial[(long long)j * nout * C + i];
+    red[jl][cx] = s;
+    __syncthreads();
+    if (jl == 0 && i < nout * C) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += red[j][cx];
+        const int k = i / C, c = i - k * C;
+        float* o = out + (long long)k * out_kstride + perm_index(c, perm_q, perm_p);
+        const float v = (float)(t * (double)alpha);
+        *o = accumulate ? *o + v : v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -128,6 +128,16 @@ void layout(mg_gan* c, char* base) {
     c->ed_d128 = b.get<float>("ed.d128", B * 128);
     c->ed_d256a = b.get<float>("ed.d256a", B * 256);
     c->ed_d256b = b.get<float>("ed.d256b", B * 256);
+    if (c->bf16) {
+        const size_t LP = T * 4 + mg::banded::kPadTotal;
+        c->d_xp = b.get<__nv_bfloat16>("d.xp", R * LP);
+        c->g_np = b.get<__nv_bfloat16>("g.np", B * LP);
+        c->d_dnp = b.get<__nv_bfloat16>("d.dnp", B * LP);
+        c->band.wb = b.get<__nv_bfloat16>("band.wb", 20 * 64 * 64);
+        c->band.vec_a = b.get<float>("band.vec_a", 256);
+        c->band.vec_b = b.get<float>("band.vec_b", 256);
+        c->band.dwb = b.get<float>("band.dwb", 256 * 64);
+    }
     // misc
     c->partial_floats = (size_t)128 * 2 * 256 * L0 > (size_t)1 << 20 ? (size_t)128 * 2 * 256 * L0 : (size_t)1 << 20;
     c->partial = b.get<float>("partial", c->partial_floats);
@@ -135,6 +145,12 @@ void layout(mg_gan* c, char* base) {
     c->seed_g = b.get<float>("seed_g", B);
     c->arena_bytes = b.off;
 }
+
+template <typename T>
+inline bool use_banded(const mg_gan* c) {
+    return std::is_same<T, __nv_bfloat16>::value && c->bf16 && tc::enabled() && c->T % 64 == 0;
+}
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
 // ------------------------------------------------------------------------------------------------
 // A-1 FeatureEncoder
@@ -255,8 +271,12 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
                                 c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st)));
     // deconv.6 -> notes (B, T, 4) float32, already in the reference's permuted (B, notes, 4) order
     float* notes = notes_out ? notes_out : c->g_notes;
-    MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y2, notes, c->G.d6_w, c->G.d6_b, B, 4 * L0, 64, 4, 5, 4 * 5,
-                                    ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    if (use_banded<T>(c)) {
+        MG_TRY(banded::up_n_fwd(c->band, BF(c->g_y2), B, 4 * L0, c->G.d6_w, 5, 20, 1, c->G.d6_b, notes, 0, st));
+    } else {
+        MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y2, notes, c->G.d6_w, c->G.d6_b, B, 4 * L0, 64, 4, 5, 4 * 5,
+                                        ACT_NONE, nullptr, MUL_NONE, 0, st)));
+    }
     if (latent_out)
         MG_CUDA_OK(cudaMemcpyAsync(latent_out, c->g_lat, sizeof(float) * B * f.latent_dim, cudaMemcpyDeviceToDevice, st));
     c->fwd_state |= FWD_G;
@@ -285,9 +305,16 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     // ---- deconv.6: bias, wgrad, dgrad (strided conv of dnotes with W[ci][co][t]) masked by ReLU(y2) ----
     MG_TRY((colreduce<float, COL_SUM>(c, dnotes, 4, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, (long long)B * T4, 4,
                                       c->gG.d6_b, 0, 0, 0, 1.0f, 1, st)));
-    MG_TRY((convT_wgrad<T, float>((const T*)c->g_y2, dnotes, c->gG.d6_w, B, 4 * L0, 64, 4, st)));
-    MG_TRY((conv_fwd<float, float, T>(dnotes, c->g_dy2, c->G.d6_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr,
-                               nullptr, c->g_y2, MUL_RELU_SIGN, st, /*w_nstride (n=ci)*/ 4 * 5, /*w_kstride (k=co)*/ 5)));
+    if (use_banded<T>(c)) {
+        MG_TRY(banded::pad_convert(dnotes, c->d_dnp, B, T4, st));
+        MG_TRY(banded::conv_k_wgrad(c->band, BF(c->g_y2), c->d_dnp, B, T4, 2, c->gG.d6_w, 20, 5, 1, st));
+        MG_TRY((banded::conv_k_fwd<float, __nv_bfloat16>(c->band, c->d_dnp, B, T4, 2, c->G.d6_w, 20, 5, 1, nullptr, nullptr,
+                                                       ACT_NONE, nullptr, c->g_y2, MUL_RELU_SIGN, c->g_dy2, st)));
+    } else {
+        MG_TRY((convT_wgrad<T, float>((const T*)c->g_y2, dnotes, c->gG.d6_w, B, 4 * L0, 64, 4, st)));
+        MG_TRY((conv_fwd<float, float, T>(dnotes, c->g_dy2, c->G.d6_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr,
+                                          nullptr, c->g_y2, MUL_RELU_SIGN, st, /*w_nstride (n=ci)*/ 4 * 5, /*w_kstride (k=co)*/ 5)));
+    }
     // ---- BN2 backward ----
     MG_TRY((bn_backward<T>(c, c->g_x2, c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
                            c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->gG.bn2_w, c->gG.bn2_b, st)));
@@ -346,8 +373,15 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
 template <typename T>
 int disc_forward(mg_gan* c, const float* notes, const float* emb, int R, float* score_out, cudaStream_t st) {
     const int L0 = c->L0, T4 = c->T;
-    MG_TRY((conv_fwd<float, T>(notes, (T*)c->d_h1, c->D.c0_w, c->D.c0_b, R, T4, 4, 64, 5, 2, 2, ACT_LRELU, nullptr,
-                               nullptr, nullptr, MUL_NONE, st)));
+    if (use_banded<T>(c)) {
+        MG_TRY(banded::pad_convert(notes, c->d_xp, R, T4, st));
+        MG_TRY((banded::conv_k_fwd<__nv_bfloat16, __nv_bfloat16>(c->band, c->d_xp, R, T4, 2, c->D.c0_w, 20, 5, 1, c->D.c0_b,
+                                                               nullptr, ACT_LRELU, nullptr, nullptr, MUL_NONE,
+                                                               (__nv_bfloat16*)c->d_h1, st)));
+    } else {
+        MG_TRY((conv_fwd<float, T>(notes, (T*)c->d_h1, c->D.c0_w, c->D.c0_b, R, T4, 4, 64, 5, 2, 2, ACT_LRELU, nullptr,
+                                   nullptr, nullptr, MUL_NONE, st)));
+    }
     MG_TRY((conv_fwd<T, T>((const T*)c->d_h1, (T*)c->d_h2, c->D.c2_w, c->D.c2_b, R, 4 * L0, 64, 128, 5, 2, 2, ACT_LRELU,
                            nullptr, nullptr, nullptr, MUL_NONE, st)));
     MG_TRY((conv_fwd<T, T>((const T*)c->d_h2, (T*)c->d_h3, c->D.c4_w, c->D.c4_b, R, 2 * L0, 128, 256, 5, 2, 2, ACT_LRELU,
@@ -389,8 +423,12 @@ int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int x
                                 ACT_NONE, c->d_h1, MUL_LRELU_SIGN, 0, st)));
     if (dnotes && xn > 0) {
         const T* dz1 = (const T*)c->d_dz1 + (size_t)x0 * per;
-        MG_TRY((upsample2_fwd<T, float>(dz1, dnotes, c->D.c0_w, nullptr, xn, 4 * L0, 64, 4, 5, 4 * 5, ACT_NONE, nullptr,
-                                        MUL_NONE, accumulate, st)));
+        if (use_banded<T>(c)) {
+            MG_TRY(banded::up_n_fwd(c->band, BF(dz1), xn, 4 * L0, c->D.c0_w, 5, 20, 1, nullptr, dnotes, accumulate, st));
+        } else {
+            MG_TRY((upsample2_fwd<T, float>(dz1, dnotes, c->D.c0_w, nullptr, xn, 4 * L0, 64, 4, 5, 4 * 5, ACT_NONE, nullptr,
+                                            MUL_NONE, accumulate, st)));
+        }
     }
     return MG_OK;
 }
@@ -423,7 +461,11 @@ int disc_wgrad(mg_gan* c, const float* x_in, const float* seed, int R, int Rb, c
                              5, 2, 2, st)));
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz2, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
                                   (long long)Rb * 2 * L0, 128, c->gD.c2_b, 0, 0, 0, 1.0f, 1, st)));
-    MG_TRY((conv_wgrad<T, float>((const T*)c->d_dz1, x_in, c->gD.c0_w, 0, (long long)R * 4 * L0, T4, 4, 64, 5, 2, 2, st)));
+    if (use_banded<T>(c)) {   // d_xp holds the padded bf16 copy of x_in (written by the forward / the adjoint pass)
+        MG_TRY(banded::conv_k_wgrad(c->band, BF(c->d_dz1), c->d_xp, R, T4, 2, c->gD.c0_w, 20, 5, 1, st));
+    } else {
+        MG_TRY((conv_wgrad<T, float>((const T*)c->d_dz1, x_in, c->gD.c0_w, 0, (long long)R * 4 * L0, T4, 4, 64, 5, 2, 2, st)));
+    }
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz1, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
                                   (long long)Rb * 4 * L0, 64, c->gD.c0_b, 0, 0, 0, 1.0f, 1, st)));
     return MG_OK;
@@ -457,8 +499,16 @@ int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const 
     T* h1x = (T*)c->d_h1 + (size_t)2 * B * per;
     T* h2x = (T*)c->d_h2 + (size_t)2 * B * per;
     T* h3x = (T*)c->d_h3 + (size_t)2 * B * per;
-    MG_TRY((conv_fwd<float, T>(u, h1x, c->D.c0_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr, nullptr, h1x,
-                               MUL_LRELU_SIGN, st)));
+    if (use_banded<T>(c)) {
+        __nv_bfloat16* up = c->d_xp + (size_t)2 * B * (pern + mg::banded::kPadTotal);
+        MG_TRY(banded::pad_convert(u, up, B, T4, st));
+        MG_TRY((banded::conv_k_fwd<__nv_bfloat16, __nv_bfloat16>(c->band, up, B, T4, 2, c->D.c0_w, 20, 5, 1, nullptr, nullptr,
+                                                               ACT_NONE, nullptr, h1x, MUL_LRELU_SIGN,
+                                                               (__nv_bfloat16*)h1x, st)));
+    } else {
+        MG_TRY((conv_fwd<float, T>(u, h1x, c->D.c0_w, nullptr, B, T4, 4, 64, 5, 2, 2, ACT_NONE, nullptr, nullptr, h1x,
+                                   MUL_LRELU_SIGN, st)));
+    }
     MG_TRY((conv_fwd<T, T>(h1x, h2x, c->D.c2_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE, nullptr, nullptr, h2x,
                            MUL_LRELU_SIGN, st)));
     MG_TRY((conv_fwd<T, T>(h2x, h3x, c->D.c4_w, nullptr, B, 2 * L0, 128, 256, 5, 2, 2, ACT_NONE, nullptr, nullptr, h3x,
@@ -497,8 +547,15 @@ template <typename T>
 int ed_forward(mg_gan* c, const float* notes, float* logits_out, cudaStream_t st) {
     const int B = c->B, T4 = c->T, NC = c->cfg.n_classes;
     if (!c->ed_folded) MG_TRY(ed_fold(c, st));
-    MG_TRY((conv_fwd<float, T>(notes, (T*)c->ed_h[0], c->ED.conv[0].w, c->ed_shift[0], B, T4, 4, 64, 5, 1, 2, ACT_GELU,
-                               c->ed_scale[0], c->ed_g[0], nullptr, MUL_NONE, st)));
+    if (use_banded<T>(c)) {
+        MG_TRY(banded::pad_convert(notes, c->g_np, B, T4, st));
+        MG_TRY((banded::conv_k_fwd<__nv_bfloat16, __nv_bfloat16>(c->band, c->g_np, B, T4, 1, c->ED.conv[0].w, 20, 5, 1,
+                                                               c->ed_shift[0], c->ed_scale[0], ACT_GELU, c->ed_g[0], nullptr,
+                                                               MUL_NONE, (__nv_bfloat16*)c->ed_h[0], st)));
+    } else {
+        MG_TRY((conv_fwd<float, T>(notes, (T*)c->ed_h[0], c->ED.conv[0].w, c->ed_shift[0], B, T4, 4, 64, 5, 1, 2, ACT_GELU,
+                                   c->ed_scale[0], c->ed_g[0], nullptr, MUL_NONE, st)));
+    }
     const int ci[4] = {4, 64, 128, 256}, co[4] = {64, 128, 256, 256};
     for (int i = 1; i < 4; ++i)
         MG_TRY((conv_fwd<T, T>((const T*)c->ed_h[i - 1], (T*)c->ed_h[i], c->ED.conv[i].w, c->ed_shift[i], B, T4, ci[i],
@@ -535,8 +592,12 @@ int ed_backward_input(mg_gan* c, const float* dlogits, float* dnotes, int accumu
                                 c->ed_g[1], MUL_VALUE, 0, st)));
     MG_TRY((conv_s1_dgrad<T, T>((const T*)c->ed_dzA, (T*)c->ed_dzB, c->ED.conv[1].w, B, T4, 64, 128, 3, 1, c->ed_scale[0],
                                 c->ed_g[0], MUL_VALUE, 0, st)));
-    MG_TRY((conv_s1_dgrad<T, float>((const T*)c->ed_dzB, dnotes, c->ED.conv[0].w, B, T4, 4, 64, 5, 2, nullptr, nullptr,
-                                    MUL_NONE, accumulate, st)));
+    if (use_banded<T>(c)) {
+        MG_TRY(banded::s1_n_dgrad(c->band, BF(c->ed_dzB), B, T4, c->ED.conv[0].w, 5, 20, 1, dnotes, accumulate, st));
+    } else {
+        MG_TRY((conv_s1_dgrad<T, float>((const T*)c->ed_dzB, dnotes, c->ED.conv[0].w, B, T4, 4, 64, 5, 2, nullptr, nullptr,
+                                        MUL_NONE, accumulate, st)));
+    }
     return MG_OK;
 }
 

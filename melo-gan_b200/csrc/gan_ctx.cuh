@@ -6,6 +6,7 @@
 #include "elem.cuh"
 #include "gemm_tc.cuh"
 #include "thin.cuh"
+#include "banded.cuh"
 
 struct mg_gan {
     mg_gan_config cfg;
@@ -55,6 +56,9 @@ struct mg_gan {
     void *ed_h[4], *ed_g[4], *ed_dzA, *ed_dzB;
     float *ed_pool, *ed_pj, *ed_c1, *ed_c1g, *ed_c2, *ed_c2g, *ed_logits, *ed_dlogits, *ed_d128, *ed_d256a,
         *ed_d256b, *ed_scale[4], *ed_shift[4];
+    // banded tensor-core forms of the 4-channel layers (bf16 mode): zero-padded bf16 note copies + scratch
+    __nv_bfloat16 *d_xp = nullptr, *g_np = nullptr, *d_dnp = nullptr;
+    mg::banded::Scratch2 band{};
     // misc
     float *partial, *metrics, *seed_g;
     size_t partial_floats = 0;
@@ -205,7 +209,7 @@ int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const floa
     {   // enough CTAs to fill the machine: (column groups) x (row chunks) ~ 4 per SM
         long long want = (long long)num_sms() * 4 / ((C / 4 + 31) / 32 > 0 ? (C / 4 + 31) / 32 : 1);
         if (want < 16) want = 16;
-        if (want > 1024) want = 1024;
+        if (want > 256) want = 256;
         if (maxchunks > want) maxchunks = want;
     }
     MG_REQUIRE(maxchunks >= 1, "colreduce: scratch too small for C=%d", C);
@@ -228,7 +232,7 @@ int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const floa
     }
     MG_LAUNCH_OK();
     const int n = NOUT * C;
-    colreduce_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->partial, nchunk, NOUT, C, out, out_kstride, perm_q,
+    colreduce_finish_kernel<<<(n + 31) / 32, 256, 0, st>>>(c->partial, nchunk, NOUT, C, out, out_kstride, perm_q,
                                                              perm_p, alpha, accumulate);
     MG_LAUNCH_OK();
     return MG_OK;
@@ -240,11 +244,5 @@ inline int grid_for(long long n, int threads = 256, int max_per_sm = 8) {
     if (b > cap) b = cap;
     return (int)(b < 1 ? 1 : b);
 }
-
-#define MG_TRY(expr)                    \
-    do {                                \
-        int _rc = (expr);               \
-        if (_rc != MG_OK) return _rc;   \
-    } while (0)
 
 }  // namespace mg

@@ -85,6 +85,26 @@ int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, 
     return MG_OK;
 }
 
+int make_view_map(CUtensorMap* map, const void* base, long long inner, long long planes, long long plane_stride,
+                  long long rows, long long row_stride, long long samples, long long sample_stride, int box_rows,
+                  int box_samples) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
+    const cuuint64_t gdim[4] = {(cuuint64_t)inner, (cuuint64_t)planes, (cuuint64_t)rows, (cuuint64_t)samples};
+    const cuuint64_t gstr[3] = {(cuuint64_t)plane_stride * 2, (cuuint64_t)row_stride * 2, (cuuint64_t)sample_stride * 2};
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, (cuuint32_t)box_samples};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(view inner=%lld planes=%lld rows=%lld samples=%lld) failed: %d", inner, planes,
+                  rows, samples, (int)r);
+        return MG_ERR_CUDA;
+    }
+    return MG_OK;
+}
+
 int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }

@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "gemm_simt.cuh"
@@ -29,6 +31,7 @@ namespace mg {
 namespace tc {
 
 constexpr int kStages = 3;
+constexpr int kTcMaxTaps = 20;  // banded forms of the 4-channel layers use up to 20 row taps (banded.cuh)
 constexpr int kTileM = 128;
 constexpr int kTileK = 64;      // bf16 elements = 128 bytes = one swizzle row
 
@@ -132,8 +135,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_m
 // ---------------------------------------------------------------------------------------------
 struct TcTapArgs {
     int ntaps, kblocks;                 // kblocks = K / 64 per tap
-    int a_p[kMaxTaps], a_dm[kMaxTaps];  // per tap: parity plane (dim 1) and row shift (dim 2) of the A map
-    int b_row[kMaxTaps];                // per tap: first row of that tap's [N][K] block in the packed weight
+    int a_p[kTcMaxTaps], a_dm[kTcMaxTaps];  // per tap: plane (dim 1) and row shift (dim 2) of the A map
+    int b_row[kTcMaxTaps];                  // per tap: first row of that tap's [N][K] block in the packed weight
     int mpt, bpt;                       // tile = bpt samples x mpt rows, mpt * bpt = 128
     int Mper, B, N;
     int n_perm_q, n_perm_p;             // bias index permutation (the packed weight is already permuted)
@@ -606,6 +609,11 @@ bool ws_enabled();           // MELOGAN_DISABLE_WS=1 keeps the non-persistent te
 //   stride 1: dims (C, 1, L, B);  stride 2: dims (C, 2, L/2, B)
 int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
                  int box_samples);
+// general 4-D bf16 view: dims (64-wide inner box over `inner` elements, planes, rows, samples) with explicit
+// element strides; used for the overlapping note windows and the row-mod-P planes of the banded layers
+int make_view_map(CUtensorMap* map, const void* base, long long inner, long long planes, long long plane_stride,
+                  long long rows, long long row_stride, long long samples, long long sample_stride, int box_rows,
+                  int box_samples);
 // 2-D view (k, rows) of a packed weight [rows][K]
 int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows);
 
@@ -653,6 +661,29 @@ int launch_tc_wgrad(const CUtensorMap& gm, const CUtensorMap& am, const TcWgradA
 }
 
 static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// Launch a tap-GEMM whose tensor maps and TcTapArgs are ready: weight-stationary persistent form when the slab's
+// weights fit in shared memory next to >= 4 activation stages and every CTA gets >= 4 tiles, else one tile per CTA.
+template <typename TO, typename TMSK>
+int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a, int BN, int K, cudaStream_t st) {
+    const long long rows = (long long)a.B * a.Mper;
+    const int mtiles = (int)((rows + 127) / 128);
+    ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * a.N * a.ntaps * K, (double)rows * (K * 2.0 + a.N * sizeof(TO)), st);
+    const int nslabs = a.N / BN;
+    const size_t wbytes = (size_t)a.ntaps * (K / 64) * BN * 128;
+    const size_t avail = (size_t)227 * 1024 - 1024 - 2048;
+    int ctas_x = num_sms() / nslabs;
+    if (ctas_x < 1) ctas_x = 1;
+    if (ctas_x > mtiles) ctas_x = mtiles;
+    if (ws_enabled() && wbytes + 4 * 16384 <= avail && mtiles >= 4 * ctas_x) {
+        int nstages = (int)((avail - wbytes) / 16384);
+        if (nstages > kWsMaxStages) nstages = kWsMaxStages;
+        const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * 16384;
+        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st)
+                           : launch_tc_tap_ws<64, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st);
+    }
+    return (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
+}
 
 // Try to run a tap-GEMM described in SIMT terms on the tensor cores.  Returns 1 if launched, 0 if the shape
 // does not qualify (caller falls back to the CUDA-core kernel), or a negative mg_status on error.
@@ -703,34 +734,19 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     MG_LAUNCH_OK();
 
     CUtensorMap am, bm;
-    const int BN = (P.N % 128 == 0) ? 128 : 64;
+    int BN = (P.N % 128 == 0) ? 128 : 64;
+    if (BN == 128) {   // a 128-wide slab whose taps do not fit in shared memory: take 64-wide slabs if THOSE can stay resident
+        const size_t avail = (size_t)227 * 1024 - 1024 - 2048 - 4 * 16384;
+        const size_t w128 = (size_t)P.ntaps * (P.K / 64) * 128 * 128;
+        const long long mt = ((long long)P.B * P.Mper + 127) / 128;
+        static const bool narrow = getenv("MELOGAN_WS_NARROW") != nullptr;   // measured slower on B200 (A re-read 4x): off
+        if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64))) BN = 64;
+    }
     int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt);
     if (rc != MG_OK) return rc;
     rc = make_weight_map(&bm, wp, P.K, (long long)P.ntaps * P.N, BN);
     if (rc != MG_OK) return rc;
-    const long long rows = (long long)P.B * P.Mper;
-    const int mtiles = (int)((rows + 127) / 128);
-    ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * P.N * P.ntaps * P.K,
-                     (double)rows * (P.K * 2.0 + P.N * sizeof(TO)), st);
-    // weight-stationary persistent form when the slab's weights fit in shared memory next to >= 2 activation stages
-    // and every CTA gets at least 4 tiles to amortise loading them
-    {
-        const int nslabs = P.N / BN;
-        const size_t wbytes = (size_t)P.ntaps * (P.K / 64) * BN * 128;
-        const size_t avail = (size_t)227 * 1024 - 1024 - 2048;
-        int ctas_x = num_sms() / nslabs;
-        if (ctas_x < 1) ctas_x = 1;
-        if (ctas_x > mtiles) ctas_x = mtiles;
-        if (ws_enabled() && wbytes + 4 * 16384 <= avail && mtiles >= 4 * ctas_x) {
-            int nstages = (int)((avail - wbytes) / 16384);
-            if (nstages > kWsMaxStages) nstages = kWsMaxStages;
-            const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * 16384;
-            rc = (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st)
-                             : launch_tc_tap_ws<64, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st);
-            return rc == MG_OK ? 1 : rc;
-        }
-    }
-    rc = (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
+    rc = run_tc_tap<TO, TMSK>(am, bm, a, BN, P.K, st);
     return rc == MG_OK ? 1 : rc;
 }
 

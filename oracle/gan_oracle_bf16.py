@@ -29,16 +29,15 @@ def gen_forward(P, noise, emb, bn_state):
         y = F.batch_norm(y, bn_state[bn + ".running_mean"], bn_state[bn + ".running_var"], P[bn + ".weight"],
                          P[bn + ".bias"], training=True, momentum=0.1, eps=1e-5)     # pre-BN output stays float32
         y = q(F.relu(y))
-    y = F.conv_transpose1d(y, P["decoder.deconv.6.weight"], P["decoder.deconv.6.bias"], stride=2, padding=2,
-                           output_padding=1)                                          # C_out = 4: float32 weights
+    y = F.conv_transpose1d(y, q(P["decoder.deconv.6.weight"]), P["decoder.deconv.6.bias"], stride=2, padding=2,
+                           output_padding=1)                                          # banded tensor-core form: bf16 weights
     return y.permute(0, 2, 1), latent
 
 
 def disc_forward(P, notes, emb):
-    h = notes.permute(0, 2, 1)
+    h = q(notes).permute(0, 2, 1)                 # conv.0 reads a zero-padded bf16 copy of the notes (banded.cuh)
     for i, name in enumerate(("conv.0", "conv.2", "conv.4")):
-        w = P[name + ".weight"] if i == 0 else q(P[name + ".weight"])                 # conv.0 (C_in = 4) is not a TC layer
-        h = q(F.leaky_relu(F.conv1d(h, w, P[name + ".bias"], stride=2, padding=2), 0.2))
+        h = q(F.leaky_relu(F.conv1d(h, q(P[name + ".weight"]), P[name + ".bias"], stride=2, padding=2), 0.2))
     h = F.adaptive_avg_pool1d(h, 1)
     feat = F.leaky_relu(F.linear(h.view(h.size(0), -1), P["fc.1.weight"], P["fc.1.bias"]), 0.2)
     feat = torch.cat([feat, emb], 1)
@@ -46,11 +45,10 @@ def disc_forward(P, notes, emb):
 
 
 def ed_forward(P, notes):
-    x = notes.permute(0, 2, 1)
+    x = q(notes).permute(0, 2, 1)
     for i in range(4):
         pre = f"encoder.conv.{i}.net."
-        w = P[pre + "0.weight"] if i == 0 else q(P[pre + "0.weight"])
-        x = F.conv1d(x, w, P[pre + "0.bias"], stride=1, padding=2 if i == 0 else 1)
+        x = F.conv1d(x, q(P[pre + "0.weight"]), P[pre + "0.bias"], stride=1, padding=2 if i == 0 else 1)
         x = F.batch_norm(x, P[pre + "1.running_mean"], P[pre + "1.running_var"], P[pre + "1.weight"], P[pre + "1.bias"],
                          training=False, eps=1e-5)
         x = q(F.gelu(x))
