@@ -141,7 +141,8 @@ long long mg_gan_workspace_bytes(const mg_gan* ctx);
  *   CRITIC    (10): conv.{0,2,4}.{w,b} fc.1.{w,b} real_fake.{w,b}                 models.py:140-156
  *   EMOTION   (32): for i in 0..3: encoder.conv.i.net.0.{w,b} net.1.{w,b,running_mean,running_var};
  *                   encoder.project.{w,b} classifier.net.{0,3}.{w,b} classifier.head.{w,b}
- * grads has the same order and length as the trainable prefix (8 / 18 / 10); NULL = no gradients. */
+ * grads has the same order and length as the trainable prefix (8 / 18 / 10; EMOTION: the 24 trainable tensors,
+ * i.e. the parameter list without the running statistics); NULL = no gradients. */
 int mg_gan_bind(mg_gan* ctx, int module, void* const* params, int nparams, void* const* grads, int ngrads);
 /* The frozen emotion discriminator's BatchNorm is folded once per bind; call again after loading new weights. */
 
@@ -190,6 +191,18 @@ int mg_gradient_penalty(mg_gan* ctx, const float* real, const float* fake, const
  *      src/emotion_discriminator/ed_model.py:147-165 */
 int mg_emotion_forward(mg_gan* ctx, const float* notes, float* logits_out, void* stream);
 int mg_emotion_backward_input(mg_gan* ctx, const float* dlogits, float* dnotes_out, int accumulate, void* stream);
+
+/* A-13  EmotionDiscriminator in TRAIN mode (BASELINE config #3): BatchNorm batch statistics (running statistics
+ *       updated), MLP dropout with caller-supplied keep-masks (B,256) and (B,128), full backward.
+ *       reference src/emotion_discriminator/train_ed.py:61-74, ed_model.py:35-42,63-69,92-95.
+ *       Bind the module with 24 gradient pointers: for i in 0..3 conv.i.net.0.{w,b} net.1.{w,b}; then project,
+ *       classifier.net.0, classifier.net.3, classifier.head {w,b}.  backward adds into them; dnotes_out may be NULL.
+ *       mg_cross_entropy: out2 = [mean CE, accuracy], dlogits = (softmax - onehot)/batch (may be NULL). */
+int mg_emotion_train_forward(mg_gan* ctx, const float* notes, const float* mask1, const float* mask2, double dropout_p,
+                             float* logits_out, void* stream);
+int mg_emotion_train_backward(mg_gan* ctx, const float* notes, const float* dlogits, float* dnotes_out, void* stream);
+int mg_cross_entropy(const float* logits, const long long* labels, int batch, int n_classes, float* dlogits, float* out2,
+                     void* stream);
 
 /* A-7 composite: the whole critic step body up to (not including) opt_D.step()
  *      src/gan/train_gan.py:185-203: E_num and G forward without grad (dropout on, BN batch stats,

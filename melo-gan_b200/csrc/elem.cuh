@@ -195,6 +195,29 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __restrict
     }
 }
 
+// y = gelu(v), g = gelu'(v) with v = (x - mean) * invstd * gamma + beta      (train-mode ConvBlock1D, ed_model.py:35-42)
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) bn_gelu_apply_kernel(const TX* __restrict__ x, T* __restrict__ y, T* __restrict__ g,
+                                                            long long n4, int C, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = (int)((i * 4) % C);
+        float v[4], o[4], d[4];
+        ld4(x + i * 4, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float u = fmaf(v[e] - mean[c + e], invstd[c + e] * gamma[c + e], beta[c + e]);
+            o[e] = gelu_f(u);
+            d[e] = gelu_grad_f(u);
+        }
+        st4(y + i * 4, o);
+        st4(g + i * 4, d);
+    }
+}
+
 // dx = gamma*invstd*(dy - s1/R - xhat*s2/R), sums = [s1 | s2] (dy already carries the ReLU mask)
 template <typename TX, typename T, typename TD>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy,
@@ -257,14 +280,14 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const T* __restrict__ x,
 // out[s, l, c] = src[s, c] * scale * colscale[c] * f'(ref[s, l, c])
 //   mode MUL_LRELU_SIGN / MUL_RELU_SIGN: derivative from the sign of the saved activation; MUL_VALUE: ref holds f'
 // grid = (chunks, samples): all index arithmetic is 32-bit and per-sample
-template <typename TS, typename T>
+template <typename TS, typename T, typename TOUT = T>
 __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __restrict__ src, const T* __restrict__ ref,
-                                                             T* __restrict__ out, int L, int C, float scale,
+                                                             TOUT* __restrict__ out, int L, int C, float scale,
                                                              const float* __restrict__ colscale, int mode) {
     const int s = blockIdx.y;
     const int n4 = L * C / 4;
     const T* r0 = ref + (long long)s * L * C;
-    T* o0 = out + (long long)s * L * C;
+    TOUT* o0 = out + (long long)s * L * C;
     const TS* sp = src + (long long)s * C;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
         const int c = (i * 4) % C;
@@ -508,6 +531,36 @@ __global__ void critic_seed_kernel(float* seed, int B, float w_real, float w_fak
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * B) return;
     seed[i] = i < B ? w_real / (float)B : (i < 2 * B ? w_fake / (float)B : 1.0f);
+}
+
+// classifier training loss: mean CE over B, accuracy, and dlogits = (softmax - onehot)/B    (train_ed.py:66-80)
+// out: [0] = loss, [1] = accuracy
+__global__ void ce_loss_acc_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int NC,
+                                   float* __restrict__ dlogits, float* __restrict__ out) {
+    __shared__ double red[2][32];
+    double ce = 0, hit = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float* l = logits + (long long)i * NC;
+        float mx = l[0];
+        int am = 0;
+        for (int k = 1; k < NC; ++k) if (l[k] > mx) { mx = l[k]; am = k; }
+        float se = 0.f;
+        for (int k = 0; k < NC; ++k) se += expf(l[k] - mx);
+        const float lse = mx + logf(se);
+        const int y = (int)labels[i];
+        ce += (double)(lse - l[y]);
+        hit += (am == y) ? 1.0 : 0.0;
+        if (dlogits)
+            for (int k = 0; k < NC; ++k) dlogits[(long long)i * NC + k] = (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) / (float)B;
+    }
+    for (int o = 16; o; o >>= 1) { ce += __shfl_xor_sync(0xffffffffu, ce, o); hit += __shfl_xor_sync(0xffffffffu, hit, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ce; red[1][threadIdx.x >> 5] = hit; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ce = hit = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ce += red[0][i]; hit += red[1][i]; }
+        out[0] = (float)(ce / B); out[1] = (float)(hit / B);
+    }
 }
 
 __global__ void fill_kernel(float* p, long long n, float v) {

@@ -73,7 +73,7 @@ void layout(mg_gan* c, char* base) {
     c->g_bn2_stats = b.get<float>("g.bn2.stats", 128);
     c->g_bn2_mean = b.get<float>("g.bn2.mean", 64);
     c->g_bn2_is = b.get<float>("g.bn2.invstd", 64);
-    c->g_bn_sums = b.get<float>("g.bn.sums", 256);
+    c->g_bn_sums = b.get<float>("g.bn.sums", 512);
     c->g_dy2 = b.get<float>("g.dy2", B * 4 * L0 * 64);     // float32: BatchNorm backward subtracts means
     c->g_dx2 = act("g.dx2", B * 4 * L0 * 64);
     c->g_dy1 = b.get<float>("g.dy1", B * 2 * L0 * 128);
@@ -602,6 +602,144 @@ int ed_backward_input(mg_gan* c, const float* dlogits, float* dnotes, int accumu
 }
 
 // ------------------------------------------------------------------------------------------------
+// A-13 EmotionDiscriminator in TRAIN mode (BatchNorm batch statistics, dropout) forward + full backward
+//      reference src/emotion_discriminator/train_ed.py:61-74 with ed_model.py:35-42,63-69,92-95
+// ------------------------------------------------------------------------------------------------
+int ed_train_alloc(mg_gan* c) {
+    if (c->ed_train_arena) return MG_OK;
+    const size_t B = c->B, T = c->T;
+    const int ch[4] = {64, 128, 256, 256};
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off += (floats * 4 + 255) / 256 * 256; return o; };
+    size_t oz[4], om[4], oi[4];
+    for (int i = 0; i < 4; ++i) { oz[i] = take(B * T * ch[i]); om[i] = take(256); oi[i] = take(256); }
+    const size_t ostats = take(512), odyb = take(B * T * 256);
+    const size_t oz1 = take(B * 256), oh1 = take(B * 256), oz2 = take(B * 128), oh2 = take(B * 128);
+    const size_t od1 = take(B * 256), od2 = take(B * 128), odpj = take(B * 256), odpool = take(B * 256);
+    MG_CUDA_OK(cudaMalloc(&c->ed_train_arena, off));
+    MG_CUDA_OK(cudaMemset(c->ed_train_arena, 0, off));
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(c->ed_train_arena + o); };
+    for (int i = 0; i < 4; ++i) { c->edt_z[i] = F(oz[i]); c->edt_mean[i] = F(om[i]); c->edt_is[i] = F(oi[i]); }
+    c->edt_stats = F(ostats); c->edt_dyb = F(odyb);
+    c->edt_z1 = F(oz1); c->edt_h1 = F(oh1); c->edt_z2 = F(oz2); c->edt_h2 = F(oh2);
+    c->edt_d1 = F(od1); c->edt_d2 = F(od2); c->edt_dpj = F(odpj); c->edt_dpool = F(odpool);
+    return MG_OK;
+}
+
+template <typename T>
+int ed_train_forward(mg_gan* c, const float* notes, const float* mask1, const float* mask2, float drop_p,
+                     float* logits_out, cudaStream_t st) {
+    const int B = c->B, T4 = c->T, NC = c->cfg.n_classes;
+    MG_TRY(ed_train_alloc(c));
+    const int ci[4] = {4, 64, 128, 256}, co[4] = {64, 128, 256, 256};
+    const long long rows = (long long)B * T4;
+    const float drop_scale = 1.0f / (1.0f - drop_p);          // MLPClassifier dropout (ed_config.yaml: 0.2)
+    c->edt_drop_scale = drop_scale;
+    for (int i = 0; i < 4; ++i) {
+        // conv (+bias) -> float32 pre-BN activation
+        if (i == 0) {
+            MG_TRY((conv_fwd<float, float>(notes, c->edt_z[0], c->ED.conv[0].w, c->ED.conv[0].b, B, T4, 4, 64, 5, 1, 2, ACT_NONE,
+                                           nullptr, nullptr, nullptr, MUL_NONE, st)));
+        } else {
+            MG_TRY((conv_fwd<T, float>((const T*)c->ed_h[i - 1], c->edt_z[i], c->ED.conv[i].w, c->ED.conv[i].b, B, T4, ci[i],
+                                       co[i], 3, 1, 1, ACT_NONE, nullptr, nullptr, nullptr, MUL_NONE, st)));
+        }
+        MG_TRY((colreduce<float, COL_SUM_SQ>(c, c->edt_z[i], co[i], nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, co[i],
+                                             c->edt_stats, co[i], 0, 0, 1.0f, 0, st)));
+        bn_finalize_kernel<<<(co[i] + 127) / 128, 128, 0, st>>>(c->edt_stats, co[i], rows, 1e-5f, 0.1f, c->edt_mean[i],
+                                                                c->edt_is[i], c->ED.conv[i].rm, c->ED.conv[i].rv, 1);
+        MG_LAUNCH_OK();
+        const long long n4 = rows * co[i] / 4;
+        bn_gelu_apply_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(c->edt_z[i], (T*)c->ed_h[i], (T*)c->ed_g[i], n4, co[i],
+                                                                    c->edt_mean[i], c->edt_is[i], c->ED.conv[i].g,
+                                                                    c->ED.conv[i].be);
+        MG_LAUNCH_OK();
+    }
+    pool_rows_kernel<T, float><<<B, 256, 0, st>>>((const T*)c->ed_h[3], c->ed_pool, B, T4, 256, 1.0f / (float)T4);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->ed_pool, c->ed_pj, c->ED.pj_w, c->ED.pj_b, B, 256, 256, ACT_NONE, nullptr, st)));
+    MG_TRY((linear_fwd<float, float>(c->ed_pj, c->edt_z1, c->ED.c0_w, c->ED.c0_b, B, 256, 256, ACT_NONE, nullptr, st)));
+    long long n = (long long)B * 256;
+    gelu_dropout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->edt_z1, mask1, drop_scale, c->edt_h1, n);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->edt_h1, c->edt_z2, c->ED.c3_w, c->ED.c3_b, B, 256, 128, ACT_NONE, nullptr, st)));
+    n = (long long)B * 128;
+    gelu_dropout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->edt_z2, mask2, drop_scale, c->edt_h2, n);
+    MG_LAUNCH_OK();
+    MG_TRY((linear_fwd<float, float>(c->edt_h2, logits_out ? logits_out : c->ed_logits, c->ED.hd_w, c->ED.hd_b, B, 128, NC,
+                                     ACT_NONE, nullptr, st)));
+    c->edt_mask1 = mask1; c->edt_mask2 = mask2;
+    c->ed_folded = false;      // running statistics moved: an eval-mode forward must re-fold
+    c->fwd_state |= 16;
+    return MG_OK;
+}
+
+template <typename T>
+int ed_train_backward(mg_gan* c, const float* notes, const float* dlogits, float* dnotes_out, cudaStream_t st) {
+    const int B = c->B, T4 = c->T, NC = c->cfg.n_classes;
+    const int ci[4] = {4, 64, 128, 256}, co[4] = {64, 128, 256, 256};
+    const long long rows = (long long)B * T4;
+    const float drop_scale = c->edt_drop_scale;
+    auto bias_grad = [&](const float* d, int N, float* gb) {
+        return colreduce<float, COL_SUM>(c, d, N, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, B, N, gb, 0, 0, 0, 1.0f, 1, st);
+    };
+    // head
+    MG_TRY((linear_wgrad<float, float>(dlogits, c->edt_h2, c->gED.hd_w, 0, B, 128, NC, st)));
+    MG_TRY(bias_grad(dlogits, NC, c->gED.hd_b));
+    MG_TRY((linear_dgrad<float, float>(dlogits, c->edt_d2, c->ED.hd_w, B, 128, NC, nullptr, MUL_NONE, st)));
+    long long n = (long long)B * 128;
+    gelu_dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->edt_d2, c->edt_z2, c->edt_mask2, drop_scale, c->edt_d2, n);
+    MG_LAUNCH_OK();
+    // classifier.net.3
+    MG_TRY((linear_wgrad<float, float>(c->edt_d2, c->edt_h1, c->gED.c3_w, 0, B, 256, 128, st)));
+    MG_TRY(bias_grad(c->edt_d2, 128, c->gED.c3_b));
+    MG_TRY((linear_dgrad<float, float>(c->edt_d2, c->edt_d1, c->ED.c3_w, B, 256, 128, nullptr, MUL_NONE, st)));
+    n = (long long)B * 256;
+    gelu_dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->edt_d1, c->edt_z1, c->edt_mask1, drop_scale, c->edt_d1, n);
+    MG_LAUNCH_OK();
+    // classifier.net.0, encoder.project
+    MG_TRY((linear_wgrad<float, float>(c->edt_d1, c->ed_pj, c->gED.c0_w, 0, B, 256, 256, st)));
+    MG_TRY(bias_grad(c->edt_d1, 256, c->gED.c0_b));
+    MG_TRY((linear_dgrad<float, float>(c->edt_d1, c->edt_dpj, c->ED.c0_w, B, 256, 256, nullptr, MUL_NONE, st)));
+    MG_TRY((linear_wgrad<float, float>(c->edt_dpj, c->ed_pool, c->gED.pj_w, 0, B, 256, 256, st)));
+    MG_TRY(bias_grad(c->edt_dpj, 256, c->gED.pj_b));
+    MG_TRY((linear_dgrad<float, float>(c->edt_dpj, c->edt_dpool, c->ED.pj_w, B, 256, 256, nullptr, MUL_NONE, st)));
+    // d(BN3 output) = dpool / T * gelu'(.)
+    {
+        const int chunks = (T4 * 256 / 4 + 1023) / 1024;
+        bcast_rows_mul_kernel<float, T, float><<<dim3(chunks, B), 256, 0, st>>>(c->edt_dpool, (const T*)c->ed_g[3], c->edt_dyb, T4,
+                                                                               256, 1.0f / (float)T4, nullptr, MUL_VALUE);
+        MG_LAUNCH_OK();
+    }
+    T* dz = (T*)c->ed_dzA;
+    for (int i = 3; i >= 0; --i) {
+        // BatchNorm backward: dyb (float32, d wrt BN output) -> dz (d wrt conv output), d gamma, d beta
+        MG_TRY((colreduce<float, COL_BN_BWD, float>(c, c->edt_z[i], co[i], c->edt_dyb, co[i], c->edt_mean[i], c->edt_is[i],
+                                                    nullptr, 1, 0, rows, co[i], c->g_bn_sums, co[i], 0, 0, 1.0f, 0, st)));
+        add2_kernel<<<(co[i] + 127) / 128, 128, 0, st>>>(c->gED.conv[i].be, c->g_bn_sums, c->gED.conv[i].g, c->g_bn_sums + co[i], co[i]);
+        MG_LAUNCH_OK();
+        const long long n4 = rows * co[i] / 4;
+        bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(c->edt_z[i], c->edt_dyb, dz, n4, co[i], 1.0f / (float)rows,
+                                                                          c->edt_mean[i], c->edt_is[i], c->ED.conv[i].g, c->g_bn_sums);
+        MG_LAUNCH_OK();
+        // conv bias / weight gradients
+        MG_TRY((colreduce<T, COL_SUM>(c, dz, co[i], nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, co[i], c->gED.conv[i].b, 0,
+                                      0, 0, 1.0f, 1, st)));
+        if (i == 0) {
+            MG_TRY((conv_wgrad<T, float>(dz, notes, c->gED.conv[0].w, 0, rows, T4, 4, 64, 5, 1, 2, st)));
+            if (dnotes_out)
+                MG_TRY((conv_s1_dgrad<T, float>(dz, dnotes_out, c->ED.conv[0].w, B, T4, 4, 64, 5, 2, nullptr, nullptr, MUL_NONE, 0, st)));
+        } else {
+            MG_TRY((conv_wgrad<T, T>(dz, (const T*)c->ed_h[i - 1], c->gED.conv[i].w, 0, rows, T4, ci[i], co[i], 3, 1, 1, st)));
+            // d(BN_{i-1} output) = (conv_i dgrad) * gelu'_{i-1}, float32
+            MG_TRY((conv_s1_dgrad<T, float, T>(dz, c->edt_dyb, c->ED.conv[i].w, B, T4, ci[i], co[i], 3, 1, nullptr, c->ed_g[i - 1],
+                                               MUL_VALUE, 0, st)));
+        }
+    }
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // composites
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -697,6 +835,7 @@ extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
 extern "C" void mg_gan_destroy(mg_gan* c) {
     if (!c) return;
     if (c->arena) cudaFree(c->arena);
+    if (c->ed_train_arena) cudaFree(c->ed_train_arena);
     delete c;
 }
 
@@ -714,7 +853,7 @@ extern "C" int mg_gan_buffer(mg_gan* c, const char* name, void** ptr, long long*
 extern "C" int mg_gan_bind(mg_gan* c, int module, void* const* params, int nparams, void* const* grads, int ngrads) {
     MG_CTX_CHECK(c);
     MG_REQUIRE(params, "gan_bind: null params");
-    static const int want_p[4] = {8, 22, 10, 32}, want_g[4] = {8, 18, 10, 0};
+    static const int want_p[4] = {8, 22, 10, 32}, want_g[4] = {8, 18, 10, 24};
     MG_REQUIRE(module >= 0 && module < 4, "gan_bind: module must be 0..3");
     MG_REQUIRE(nparams == want_p[module], "gan_bind: module %d expects %d parameter pointers, got %d", module,
                want_p[module], nparams);
@@ -745,6 +884,7 @@ extern "C" int mg_gan_bind(mg_gan* c, int module, void* const* params, int npara
         default: {
             float** d = reinterpret_cast<float**>(&c->ED);
             for (int i = 0; i < 32; ++i) d[i] = F(params[i]);
+            if (grads) { float** g = reinterpret_cast<float**>(&c->gED); for (int i = 0; i < 24; ++i) g[i] = F(grads[i]); }
             c->ed_folded = false;
             break;
         }
@@ -871,6 +1011,36 @@ extern "C" int mg_emotion_backward_input(mg_gan* c, const float* dlogits, float*
     MG_REQUIRE(dlogits && dnotes_out, "emotion_backward_input: null pointer");
     if (!(c->fwd_state & FWD_ED)) { mg::set_error("emotion_backward_input before forward"); return MG_ERR_STATE; }
     return MG_DISPATCH(c, ed_backward_input, c, dlogits, dnotes_out, accumulate, as_stream(stream));
+}
+
+extern "C" int mg_emotion_train_forward(mg_gan* c, const float* notes, const float* mask1, const float* mask2,
+                                        double dropout_p, float* logits_out, void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 3, "emotion_train_forward");
+    MG_REQUIRE(notes && logits_out, "emotion_train_forward: null pointer");
+    MG_REQUIRE(dropout_p >= 0.0 && dropout_p < 1.0, "emotion_train_forward: dropout must be in [0, 1)");
+    MG_REQUIRE(dropout_p == 0.0 || (mask1 && mask2), "emotion_train_forward: dropout masks required");
+    if (dropout_p == 0.0) { mask1 = mask2 = nullptr; }
+    return c->bf16 ? ed_train_forward<__nv_bfloat16>(c, notes, mask1, mask2, (float)dropout_p, logits_out, as_stream(stream))
+                   : ed_train_forward<float>(c, notes, mask1, mask2, (float)dropout_p, logits_out, as_stream(stream));
+}
+
+extern "C" int mg_emotion_train_backward(mg_gan* c, const float* notes, const float* dlogits, float* dnotes_out,
+                                         void* stream) {
+    MG_CTX_CHECK(c);
+    MG_NEED_BOUND(c, 3, "emotion_train_backward");
+    MG_NEED_GRADS(c, 3, "emotion_train_backward");
+    MG_REQUIRE(notes && dlogits, "emotion_train_backward: null pointer");
+    if (!(c->fwd_state & 16)) { mg::set_error("emotion_train_backward before emotion_train_forward"); return MG_ERR_STATE; }
+    return MG_DISPATCH(c, ed_train_backward, c, notes, dlogits, dnotes_out, as_stream(stream));
+}
+
+extern "C" int mg_cross_entropy(const float* logits, const long long* labels, int batch, int n_classes, float* dlogits,
+                                float* out2, void* stream) {
+    MG_REQUIRE(logits && labels && out2 && batch > 0 && n_classes > 1, "cross_entropy: bad arguments");
+    ce_loss_acc_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, labels, batch, n_classes, dlogits, out2);
+    MG_LAUNCH_OK();
+    return MG_OK;
 }
 
 extern "C" int mg_critic_step(mg_gan* c, const float* real, const float* numeric, const float* noise,

@@ -26,6 +26,10 @@ struct mg_gan {
         struct { float *w, *b, *g, *be, *rm, *rv; } conv[4];
         float *pj_w, *pj_b, *c0_w, *c0_b, *c3_w, *c3_b, *hd_w, *hd_b;
     } ED{};
+    struct EDG {   // gradients of the emotion discriminator (BASELINE config #3, training the classifier itself)
+        struct { float *w, *b, *g, *be; } conv[4];
+        float *pj_w, *pj_b, *c0_w, *c0_b, *c3_w, *c3_b, *hd_w, *hd_b;
+    } gED{};
     bool bound[4] = {false, false, false, false};
     bool has_grads[4] = {false, false, false, false};
     bool ed_folded = false;
@@ -59,6 +63,13 @@ struct mg_gan {
     // banded tensor-core forms of the 4-channel layers (bf16 mode): zero-padded bf16 note copies + scratch
     __nv_bfloat16 *d_xp = nullptr, *g_np = nullptr, *d_dnp = nullptr;
     mg::banded::Scratch2 band{};
+    // emotion-discriminator TRAINING workspaces (allocated on first use: mg_emotion_train_forward)
+    char* ed_train_arena = nullptr;
+    float *edt_z[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-BatchNorm conv outputs (float32)
+    float *edt_mean[4], *edt_is[4], *edt_stats, *edt_dyb;      // batch statistics, scratch, d(BN output) float32
+    float *edt_z1, *edt_h1, *edt_z2, *edt_h2, *edt_d1, *edt_d2, *edt_dpj, *edt_dpool;
+    const float *edt_mask1 = nullptr, *edt_mask2 = nullptr;
+    float edt_drop_scale = 1.0f;
     // misc
     float *partial, *metrics, *seed_g;
     size_t partial_floats = 0;
@@ -128,7 +139,7 @@ int conv_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, in
 }
 
 // ---- stride-1 conv dgrad: dIn[R, L, Cin] = sum_t dOut[R, l + pad - t, Cout] W[Cout][Cin][ks] ----
-template <typename TA, typename TO>
+template <typename TA, typename TO, typename TMSK = TO>
 int conv_s1_dgrad(const TA* dOut, TO* dIn, const float* W, int R, int L, int Cin, int Cout, int ks, int pad,
                   const float* col_scale, const void* mul_src, int mul_mode, int accumulate, cudaStream_t st) {
     TapGemmArgs a = tap_defaults();
@@ -138,7 +149,7 @@ int conv_s1_dgrad(const TA* dOut, TO* dIn, const float* W, int R, int L, int Cin
     a.W = W; a.w_nstride = ks; a.w_kstride = Cin * ks;      // n = ci, k = co
     a.Out = dIn; a.o_bstride = (long long)L * Cin; a.o_mstride = Cin; a.B = R; a.Mper = L; a.N = Cin;
     a.col_scale = col_scale; a.mul_src = mul_src; a.mul_mode = mul_mode; a.accumulate = accumulate;
-    return launch_tapgemm<TA, TO>(a, st);
+    return launch_tapgemm<TA, TO, TMSK>(a, st);
 }
 
 // ---- k5 s2 p2 op1 up-sampling contraction in two sub-pixel phases ----

@@ -57,6 +57,9 @@ _SIGNATURES = {
     "mg_gradient_penalty": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_emotion_forward": ([_vp, _vp, _vp, _vp], _i),
     "mg_emotion_backward_input": ([_vp, _vp, _vp, _i, _vp], _i),
+    "mg_emotion_train_forward": ([_vp, _vp, _vp, _vp, _d, _vp, _vp], _i),
+    "mg_emotion_train_backward": ([_vp, _vp, _vp, _vp, _vp], _i),
+    "mg_cross_entropy": ([_vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
 }

@@ -31,8 +31,10 @@ for _i in range(4):
 ED_KEYS += ["encoder.project.weight", "encoder.project.bias", "classifier.net.0.weight", "classifier.net.0.bias",
             "classifier.net.3.weight", "classifier.net.3.bias", "classifier.head.weight", "classifier.head.bias"]
 
+ED_GRAD_KEYS = [k for k in ED_KEYS if not k.endswith(("running_mean", "running_var"))]
+
 PARAM_KEYS = {MOD_E: E_KEYS, MOD_G: G_PARAM_KEYS + G_BUFFER_KEYS, MOD_D: D_KEYS, MOD_ED: ED_KEYS}
-GRAD_KEYS = {MOD_E: E_KEYS, MOD_G: G_PARAM_KEYS, MOD_D: D_KEYS, MOD_ED: []}
+GRAD_KEYS = {MOD_E: E_KEYS, MOD_G: G_PARAM_KEYS, MOD_D: D_KEYS, MOD_ED: ED_GRAD_KEYS}
 
 
 class _Config(ctypes.Structure):
@@ -117,7 +119,7 @@ class GanEngine:
         """params/grads: dict key -> CUDA float32 tensor using the reference's state_dict keys."""
         pk, gk = PARAM_KEYS[module], GRAD_KEYS[module]
         pt = [_check_f32_cuda(params[k], k) for k in pk]
-        gt = [_check_f32_cuda(grads[k], "grad " + k, pt[i].shape) for i, k in enumerate(gk)] if grads is not None else None
+        gt = [_check_f32_cuda(grads[k], "grad " + k, params[k].shape) for k in gk] if grads is not None else None
         parr = (ctypes.c_void_p * len(pt))(*[t.data_ptr() for t in pt])
         garr = (ctypes.c_void_p * len(gt))(*[t.data_ptr() for t in gt]) if gt else None
         self._call("mg_gan_bind", module, parr, len(pt), garr, len(gt) if gt else 0)
@@ -210,6 +212,22 @@ class GanEngine:
         self._call("mg_emotion_backward_input", _ptr(dlogits), _ptr(out), int(accumulate), self._stream())
         return out
 
+    # ---- A-13 ----
+    def emotion_train_forward(self, notes, mask1, mask2, dropout_p=0.2):
+        _check_f32_cuda(notes, "notes", (self.B, self.T, self.note_dim))
+        logits = torch.empty((self.B, self.n_classes), device=self.device)
+        self._keep["ed_train"] = (notes, mask1, mask2)
+        self._call("mg_emotion_train_forward", _ptr(notes), _ptr(mask1), _ptr(mask2), float(dropout_p), _ptr(logits),
+                   self._stream())
+        return logits
+
+    def emotion_train_backward(self, dlogits, want_dnotes=False):
+        notes = self._keep["ed_train"][0]
+        _check_f32_cuda(dlogits, "dlogits", (self.B, self.n_classes))
+        dnotes = torch.empty_like(notes) if want_dnotes else None
+        self._call("mg_emotion_train_backward", _ptr(notes), _ptr(dlogits), _ptr(dnotes), self._stream())
+        return dnotes
+
     # ---- composites ----
     def critic_step(self, real, numeric, noise, alpha, mask1, mask2, metrics=None):
         _check_f32_cuda(real, "real", (self.B, self.T, self.note_dim))
@@ -265,6 +283,8 @@ _GAN_SIGNATURES = {
     "mg_gradient_penalty": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_emotion_forward": ([_vp, _vp, _vp, _vp], _i),
     "mg_emotion_backward_input": ([_vp, _vp, _vp, _i, _vp], _i),
+    "mg_emotion_train_forward": ([_vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp], _i),
+    "mg_emotion_train_backward": ([_vp, _vp, _vp, _vp, _vp], _i),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
 }

@@ -4,7 +4,8 @@ Drop-in for the reference's src/emotion_discriminator/ed_model.py: ConvBlock1D, 
 MLPClassifier, EmotionDiscriminator with the same constructors, cfg keys and state_dict keys.  On the
 GAN hot path the module is frozen and in eval mode (src/gan/train_gan.py:131-133): BatchNorm is folded
 into the conv epilogue and the forward + input-gradient run behind mg_emotion_forward /
-mg_emotion_backward_input.  Training the classifier itself (BASELINE config #3) is a later row.
+mg_emotion_backward_input.  In train mode (BASELINE config #3: BatchNorm batch statistics, dropout, all parameter
+gradients) it runs behind mg_emotion_train_forward / mg_emotion_train_backward.
 """
 from typing import Dict
 
@@ -81,6 +82,40 @@ class _EmotionFn(torch.autograd.Function):
         return None, eng.emotion_backward_input(R.as_f32c(dlogits))
 
 
+class _EmotionTrainFn(torch.autograd.Function):
+    """Train-mode forward/backward (BASELINE config #3, reference train_ed.py:61-74): BatchNorm batch statistics,
+    MLP dropout with keep-masks drawn like nn.Dropout would, full parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, module, notes, mask1, mask2, *params):
+        eng = module._engine(notes)
+        P = R.params_of(module, E.ED_KEYS)
+        eng.bind(E.MOD_ED, P, None)
+        logits = eng.emotion_train_forward(R.as_f32c(notes), mask1, mask2, dropout_p=module.dropout)
+        for blk in module.encoder.conv:
+            blk.net[1].num_batches_tracked += 1
+        ctx.module = module
+        ctx.save_for_backward(notes, mask1, mask2)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        module = ctx.module
+        notes, mask1, mask2 = ctx.saved_tensors
+        eng = module._engine(notes)
+        P = dict(R.params_of(module, E.ED_KEYS))
+        for k in E.ED_KEYS:                      # recompute with batch statistics WITHOUT advancing the running stats again
+            if k.endswith(("running_mean", "running_var")):
+                P[k] = P[k].clone()
+        G = R.fresh_grads(P, E.ED_GRAD_KEYS)
+        eng.bind(E.MOD_ED, P, G)
+        eng.emotion_train_forward(R.as_f32c(notes), mask1, mask2, dropout_p=module.dropout)
+        dnotes = eng.emotion_train_backward(R.as_f32c(dlogits), want_dnotes=ctx.needs_input_grad[1])
+        named = dict(module.named_parameters())
+        grads = tuple(G[k] if named[k].requires_grad else None for k in E.ED_GRAD_KEYS)
+        return (None, dnotes, None, None) + grads
+
+
 class EmotionDiscriminator(nn.Module):
     """cfg keys: input_mode, n_classes, use_spectral_norm, dropout, latent_dim, note_dim, notes_hidden,
     notes_blocks, mlp_hidden (reference ed_model.py:115-145)."""
@@ -113,7 +148,7 @@ class EmotionDiscriminator(nn.Module):
                                       "(notes_hidden 256, 4 blocks, mlp_hidden [256,128], note_dim 4)")
         return R.engine_for(notes.device, notes.shape[0], max_notes=notes.shape[1], n_classes=self.n_classes)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, masks=None) -> torch.Tensor:
         if self.input_mode == 'latent':
             if x.dim() != 2:
                 raise ValueError(f"Expected latent input shape (B, latent_dim), got {x.shape}")
@@ -121,8 +156,13 @@ class EmotionDiscriminator(nn.Module):
         if x.dim() != 3:
             raise ValueError(f"Expected notes input shape (B, T, note_dim), got {x.shape}")
         if self.training:
-            raise NotImplementedError("train-mode EmotionDiscriminator (BASELINE config #3) is not built yet; "
-                                      "the GAN step uses it frozen in eval mode (train_gan.py:131-133)")
+            keep = 1.0 - self.dropout
+            B, dev = x.shape[0], x.device
+            if masks is None:      # the two bernoulli draws nn.Dropout would make, in order
+                masks = (torch.bernoulli(torch.full((B, 256), keep, device=dev)),
+                         torch.bernoulli(torch.full((B, 128), keep, device=dev)))
+            named = dict(self.named_parameters())
+            return _EmotionTrainFn.apply(self, x, masks[0], masks[1], *[named[k] for k in E.ED_GRAD_KEYS])
         if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
             raise NotImplementedError("the native emotion discriminator is frozen: set requires_grad=False on its "
                                       "parameters (train_gan.py:131-132) to get the input gradient")

@@ -318,3 +318,70 @@ def train_cycle(params, batches, opt_state_d, opt_state_g, cfg=CFG):
 
 def clone_params(params):
     return {m: {k: v.clone() for k, v in P.items()} for m, P in params.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# A-13: EmotionDiscriminator training step (BASELINE config #3)
+#       reference src/emotion_discriminator/train_ed.py:61-74 with ed_model.py in train mode
+# ------------------------------------------------------------------------------------------------
+ED_CFG = dict(lr=2e-4, betas=(0.5, 0.999), weight_decay=0.0, dropout=0.2, batch_size=64)
+
+
+def ed_train_forward(P, notes, mask1, mask2, bn_state, p_drop=0.2, keep=None):
+    """EmotionDiscriminator.forward in train mode: BatchNorm batch statistics (running stats in bn_state are
+    advanced in place), MLP dropout with injected keep-masks."""
+    x = notes.permute(0, 2, 1)
+    for i in range(4):
+        pre = f"encoder.conv.{i}.net."
+        x = F.conv1d(x, P[pre + "0.weight"], P[pre + "0.bias"], stride=1, padding=2 if i == 0 else 1)
+        x = F.batch_norm(x, bn_state[pre + "1.running_mean"], bn_state[pre + "1.running_var"], P[pre + "1.weight"],
+                         P[pre + "1.bias"], training=True, momentum=0.1, eps=1e-5)
+        x = F.gelu(x)
+        if keep is not None:
+            keep[f"conv{i}"] = x
+    x = F.adaptive_avg_pool1d(x, 1).squeeze(-1)
+    x = F.linear(x, P["encoder.project.weight"], P["encoder.project.bias"])
+    x = F.gelu(F.linear(x, P["classifier.net.0.weight"], P["classifier.net.0.bias"])) * (mask1 * (1.0 / (1.0 - p_drop)))
+    x = F.gelu(F.linear(x, P["classifier.net.3.weight"], P["classifier.net.3.bias"])) * (mask2 * (1.0 / (1.0 - p_drop)))
+    return F.linear(x, P["classifier.head.weight"], P["classifier.head.bias"])
+
+
+def adamw_update(params, grads, state, lr, beta1, beta2, weight_decay, eps=1e-8):
+    """torch.optim.AdamW single-tensor arithmetic (decoupled decay first, then the Adam update)."""
+    state["step"] = state.get("step", 0) + 1
+    t = state["step"]
+    bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
+    for name, p in params.items():
+        g = grads[name]
+        if name not in state:
+            state[name] = (torch.zeros_like(p), torch.zeros_like(p))
+        m, v = state[name]
+        p.mul_(1 - lr * weight_decay)
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+        p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+def make_ed_batch(seed, B, cfg=CFG):
+    from melogan import synth
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return {"x": t(synth.uniform(seed * 100 + 1, (B, cfg["MAX_NOTES"], cfg["NOTE_DIM"]))),
+            "y": t(synth.emotion_labels(B)),
+            "mask1": t((synth.uniform(seed * 100 + 2, (B, 256), 0.0, 1.0) < 0.8).astype(np.float32)),
+            "mask2": t((synth.uniform(seed * 100 + 3, (B, 128), 0.0, 1.0) < 0.8).astype(np.float32))}
+
+
+def ed_train_step(PED, batch, opt_state, update=True, cfg=ED_CFG):
+    """One train_ed.run_epoch iteration: logits -> CE -> backward -> AdamW.  Mutates PED (incl. running stats)."""
+    leaves = _leaves(PED)
+    bn_state = PED if update else {k: v.clone() for k, v in PED.items() if is_buffer(k)}
+    logits = ed_train_forward(leaves, batch["x"], batch["mask1"], batch["mask2"], bn_state, p_drop=cfg["dropout"])
+    loss = F.cross_entropy(logits, batch["y"])
+    grads = dict(zip(leaves.keys(), torch.autograd.grad(loss, list(leaves.values()))))
+    acc = (logits.argmax(dim=1) == batch["y"]).float().mean()
+    if update:
+        with torch.no_grad():
+            adamw_update({k: v for k, v in PED.items() if not is_buffer(k)}, grads, opt_state, cfg["lr"], cfg["betas"][0],
+                         cfg["betas"][1], cfg["weight_decay"])
+    return {"loss": loss.detach(), "acc": acc, "logits": logits.detach(), "grads": grads}

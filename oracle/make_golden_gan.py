@@ -209,6 +209,33 @@ def main():
         out["eval.latent"] = lat.numpy().copy()
         out["eval.score"] = D(notes, emb).numpy().copy()
         out["eval.logits"] = ED(notes).numpy().copy()
+    # ---- A-13: the reference's ED training iteration (train_ed.py:61-74) on its own module, 2 steps ----
+    params = O.make_params(5)
+    with open(os.path.join(REF, "config/ed_config.yaml")) as f:
+        ed_cfg = yaml.safe_load(f)
+    model = ref_ed.EmotionDiscriminator(ed_cfg)
+    missing, unexpected = model.load_state_dict(params["ED"], strict=False)
+    assert not unexpected
+    o = ed_cfg["optimizer"]
+    optimizer = optim.AdamW(model.parameters(), lr=float(o["lr"]), weight_decay=o.get("weight_decay", 0), betas=tuple(o["betas"]))
+    criterion = nn.CrossEntropyLoss()
+    model.train()
+    for i in range(2):
+        eb = O.make_ed_batch(50 + i, 16)
+        with Inject(masks=[eb["mask1"], eb["mask2"]]):
+            optimizer.zero_grad()
+            logits = model(eb["x"])
+            loss = criterion(logits, eb["y"])
+            loss.backward()
+            grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+            optimizer.step()
+        out[f"ED.s{i}.scalars"] = np.array([loss.item(), (logits.argmax(1) == eb["y"]).float().mean().item()])
+        out[f"ED.s{i}.logits"] = logits.detach().numpy().copy()
+        for k, g in grads.items():
+            out[f"ED.s{i}.grad.{k}"] = tstats(g)
+    for k, t in model.state_dict().items():
+        if not k.endswith("num_batches_tracked"):
+            out[f"ED.final.{k}"] = tstats(t)
     path = os.path.join(ROOT, "tests", "golden", "gan_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

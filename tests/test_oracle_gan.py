@@ -70,3 +70,19 @@ def test_eval_mode_forwards_match_reference(gold):
         np.testing.assert_allclose(lat.numpy(), gold["eval.latent"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(O.disc_forward(params["D"], notes, emb).numpy(), gold["eval.score"], rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(O.ed_forward(params["ED"], notes).numpy(), gold["eval.logits"], rtol=1e-4, atol=1e-6)
+
+
+def test_ed_training_steps_match_reference(gold):
+    """A-13: two iterations of train_ed.run_epoch's training branch on the reference's own module."""
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    params = O.make_params(5)
+    st = {}
+    for i in range(2):
+        eb = O.make_ed_batch(50 + i, 16)
+        r = O.ed_train_step(params["ED"], eb, st)
+        np.testing.assert_allclose([r["loss"].item(), r["acc"].item()], gold[f"ED.s{i}.scalars"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(r["logits"].numpy(), gold[f"ED.s{i}.logits"], rtol=1e-4, atol=2e-6)
+        for k, g in r["grads"].items():
+            close_stats(tstats(g), gold[f"ED.s{i}.grad.{k}"], 5e-4, ("ED", i, k))
+    for k, t in params["ED"].items():
+        close_stats(tstats(t), gold[f"ED.final.{k}"], 5e-4, ("ED final", k))
