@@ -204,6 +204,26 @@ int mg_emotion_train_backward(mg_gan* ctx, const float* notes, const float* dlog
 int mg_cross_entropy(const float* logits, const long long* labels, int batch, int n_classes, float* dlogits, float* out2,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * A-12  VAE (BASELINE config #2): reference src/ae/model.py:4-148 forward, its backward, and the loss of
+ *       src/ae/train_ae.py:35-51.  Own context (different widths from the GAN step).
+ * params (42) in state_dict order: encoder.conv.{0,3,6}.{w,b} each followed by its BatchNorm conv.{1,4,7}.{w,b};
+ *   encoder._linear.1.{w,b}; fc_mu.{w,b}; fc_log_var.{w,b}; decoder.pre.{0,2}.{w,b}; decoder.deconv.0.{w,b},
+ *   deconv.1.{w,b}, deconv.3.{w,b}, deconv.4.{w,b}, deconv.6.{w,b}  (32 trainable), then running_{mean,var} of
+ *   encoder.conv.{1,4,7} and decoder.deconv.{1,4} (10).  grads: the 32 trainable ones.
+ * eps (B, latent) is the reparameterisation noise (torch.randn_like in the reference).
+ * mg_vae_backward takes d(loss)/d(recon) (+ optional d/dz, d/dmu, d/dlog_var), adds parameter gradients.
+ * mg_vae_loss_step = forward + vae_loss + backward; metrics_out = [total, recon MSE, KLD]. */
+typedef struct mg_vae mg_vae;
+int mg_vae_create(int batch, int max_notes, int latent_dim, int precision, mg_vae** out);
+void mg_vae_destroy(mg_vae* ctx);
+int mg_vae_bind(mg_vae* ctx, void* const* params, int nparams, void* const* grads, int ngrads);
+int mg_vae_forward(mg_vae* ctx, const float* x, const float* eps, int train, float* recon_out, float* z_out,
+                   float* mu_out, float* logvar_out, void* stream);
+int mg_vae_backward(mg_vae* ctx, const float* x, const float* drecon, const float* dz, const float* dmu,
+                    const float* dlogvar, void* stream);
+int mg_vae_loss_step(mg_vae* ctx, const float* x, const float* eps, double beta, float* metrics_out, void* stream);
+
 /* A-7 composite: the whole critic step body up to (not including) opt_D.step()
  *      src/gan/train_gan.py:185-203: E_num and G forward without grad (dropout on, BN batch stats,
  *      running stats updated), then mg_critic_loss_backward.  Caller zeroes the critic grads first. */

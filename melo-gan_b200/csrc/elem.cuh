@@ -30,7 +30,7 @@ struct ColReduceArgs {
 };
 
 template <typename T, typename TY, int OP>
-__global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
+static __global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
     constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
     __shared__ float red[NOUT][8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const ColReduceArgs P) {
 
 // vectorised form: every thread owns 4 consecutive columns (one 8/16-byte load per row), 8 row lanes per CTA
 template <typename T, typename TY, int OP>
-__global__ void __launch_bounds__(256) colreduce_vec4_kernel(const ColReduceArgs P) {
+static __global__ void __launch_bounds__(256) colreduce_vec4_kernel(const ColReduceArgs P) {
     constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
     __shared__ float red[NOUT][8][32][4 + 1];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) colreduce_vec4_kernel(const ColReduceArgs
 
 // out[k*out_kstride + perm(c)] (+)= alpha * sum_chunks partial[chunk][k][c]   (float64 accumulation)
 // 32 outputs per CTA, 8 chunk lanes each, combined in a fixed order (deterministic)
-__global__ void __launch_bounds__(256) colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout,
+static __global__ void __launch_bounds__(256) colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout,
                                                                int C, float* out, int out_kstride, int perm_q,
                                                                int perm_p, float alpha, int accumulate) {
     __shared__ double red[8][33];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) colreduce_finish_kernel(const float* __re
 // BatchNorm1d (training) helpers for G's two BN layers        reference models.py:57,60
 // ---------------------------------------------------------------------------------------------
 // stats[0][c] = sum x, stats[1][c] = sum x^2 over R rows -> mean, invstd (biased var), running update
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, long long R, float eps, float momentum,
+static __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, long long R, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
                                    float* running_var, int update_running) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +176,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, long 
 
 // y = relu((x - mean) * invstd * gamma + beta)      (eval mode: mean/invstd come from running stats)
 template <typename TX, typename T>
-__global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __restrict__ x, T* __restrict__ y, long long n4,
+static __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __restrict__ x, T* __restrict__ y, long long n4,
                                                             int C, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma,
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __restrict
 
 // y = gelu(v), g = gelu'(v) with v = (x - mean) * invstd * gamma + beta      (train-mode ConvBlock1D, ed_model.py:35-42)
 template <typename TX, typename T>
-__global__ void __launch_bounds__(256) bn_gelu_apply_kernel(const TX* __restrict__ x, T* __restrict__ y, T* __restrict__ g,
+static __global__ void __launch_bounds__(256) bn_gelu_apply_kernel(const TX* __restrict__ x, T* __restrict__ y, T* __restrict__ g,
                                                             long long n4, int C, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma,
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) bn_gelu_apply_kernel(const TX* __restrict
 
 // dx = gamma*invstd*(dy - s1/R - xhat*s2/R), sums = [s1 | s2] (dy already carries the ReLU mask)
 template <typename TX, typename T, typename TD>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy,
+static __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy,
                                                            T* __restrict__ dx, long long n4, int C, float invR,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ invstd,
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __restrict_
 // out[s, c] = scale * sum_l x[s, l, c]        (AdaptiveAvgPool1d(1): scale = 1/L)
 // thread = (sample, 4 channels, row lane); C/4 * RL threads per sample, RL row lanes combined through shared memory
 template <typename T, typename TO>
-__global__ void __launch_bounds__(256) pool_rows_kernel(const T* __restrict__ x, TO* __restrict__ out, int S, int L,
+static __global__ void __launch_bounds__(256) pool_rows_kernel(const T* __restrict__ x, TO* __restrict__ out, int S, int L,
                                                         int C, float scale) {
     __shared__ float red[256][4 + 1];
     const int c4n = C / 4;                       // channel groups (C % 4 == 0, c4n <= 256)
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const T* __restrict__ x,
 //   mode MUL_LRELU_SIGN / MUL_RELU_SIGN: derivative from the sign of the saved activation; MUL_VALUE: ref holds f'
 // grid = (chunks, samples): all index arithmetic is 32-bit and per-sample
 template <typename TS, typename T, typename TOUT = T>
-__global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __restrict__ src, const T* __restrict__ ref,
+static __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __restrict__ src, const T* __restrict__ ref,
                                                              TOUT* __restrict__ out, int L, int C, float scale,
                                                              const float* __restrict__ colscale, int mode) {
     const int s = blockIdx.y;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __restric
 // FeatureEncoder pieces (tiny tensors, float only)          reference feature_encoder.py:17-41
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over D (<= 32) features per row; writes y and xhat
-__global__ void layernorm_small_kernel(const float* __restrict__ x, int B, int D, const float* __restrict__ w,
+static __global__ void layernorm_small_kernel(const float* __restrict__ x, int B, int D, const float* __restrict__ w,
                                        const float* __restrict__ b, float eps, float* __restrict__ y,
                                        float* __restrict__ xhat) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,7 +328,7 @@ __global__ void layernorm_small_kernel(const float* __restrict__ x, int B, int D
 }
 
 // h = gelu(z) * mask * scale   (mask == nullptr: eval mode, no dropout)
-__global__ void gelu_dropout_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mask, float scale,
+static __global__ void gelu_dropout_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mask, float scale,
                                         float* __restrict__ h, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -336,7 +336,7 @@ __global__ void gelu_dropout_fwd_kernel(const float* __restrict__ z, const float
     h[i] = mask ? g * (mask[i] * scale) : g;
 }
 // dz = dh * mask * scale * gelu'(z)
-__global__ void gelu_dropout_bwd_kernel(const float* dh, const float* __restrict__ z,
+static __global__ void gelu_dropout_bwd_kernel(const float* dh, const float* __restrict__ z,
                                         const float* __restrict__ mask, float scale, float* dz, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -345,7 +345,7 @@ __global__ void gelu_dropout_bwd_kernel(const float* dh, const float* __restrict
 }
 
 // xcat[b] = [a[b, 0:Da] | c[b, 0:Dc]]
-__global__ void concat2_kernel(const float* __restrict__ a, int Da, const float* __restrict__ c, int Dc,
+static __global__ void concat2_kernel(const float* __restrict__ a, int Da, const float* __restrict__ c, int Dc,
                                float* __restrict__ out, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int D = Da + Dc;
@@ -355,7 +355,7 @@ __global__ void concat2_kernel(const float* __restrict__ a, int Da, const float*
 }
 
 // out[b, j] (+)= src[b, off + j]  for j < D   (slice of a wider row)
-__global__ void slice_add_kernel(const float* __restrict__ src, int lds, int off, float* __restrict__ out, int D,
+static __global__ void slice_add_kernel(const float* __restrict__ src, int lds, int off, float* __restrict__ out, int D,
                                  int B, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * D) return;
@@ -368,7 +368,7 @@ __global__ void slice_add_kernel(const float* __restrict__ src, int lds, int off
 // critic head, gradient penalty, losses
 // ---------------------------------------------------------------------------------------------
 // score[r] = hf[r,:] . w[0:F] + emb[r % B,:] . w[F:F+E] + bias           reference models.py:164-169
-__global__ void critic_score_kernel(const float* __restrict__ hf, const float* __restrict__ emb,
+static __global__ void critic_score_kernel(const float* __restrict__ hf, const float* __restrict__ emb,
                                     const float* __restrict__ w, const float* __restrict__ bias, int R, int B, int F,
                                     int E, float* __restrict__ score) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -384,7 +384,7 @@ __global__ void critic_score_kernel(const float* __restrict__ hf, const float* _
 }
 
 // dzf[r, j] = seed[r] * w[j] * lrelu'(hf[r, j])
-__global__ void critic_head_bwd_kernel(const float* __restrict__ hf, const float* __restrict__ w,
+static __global__ void critic_head_bwd_kernel(const float* __restrict__ hf, const float* __restrict__ w,
                                        const float* __restrict__ seed, int R, int F, float* __restrict__ dzf) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)R * F) return;
@@ -393,7 +393,7 @@ __global__ void critic_head_bwd_kernel(const float* __restrict__ hf, const float
 }
 
 // X3 = [real | fake | alpha*real + (1-alpha)*fake]  (each segment B*per floats)   utils.py:76-78
-__global__ void __launch_bounds__(256) assemble_critic_input_kernel(const float4* __restrict__ real,
+static __global__ void __launch_bounds__(256) assemble_critic_input_kernel(const float4* __restrict__ real,
                                                                     const float4* __restrict__ fake,
                                                                     const float* __restrict__ alpha,
                                                                     float4* __restrict__ x3, int B, int per4) {
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256) assemble_critic_input_kernel(const float4
 }
 
 // per sample: n = ||g||_2 over `per` floats; gp_b = (n-1)^2; u = lambda * 2(n-1)/(B n) * g written to `u`
-__global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ g, float* __restrict__ u, int per,
+static __global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ g, float* __restrict__ u, int per,
                                                       float lambda_over_B, float* __restrict__ gp_per_sample,
                                                       float* __restrict__ norm_per_sample) {
     __shared__ float red[8];
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ 
 
 // metrics of the critic step, one thread block: means over B of score segments and gp
 // out: [0]=loss_d [1]=gp [2]=mean d_real [3]=mean d_fake
-__global__ void critic_loss_kernel(const float* __restrict__ score, const float* __restrict__ gp_ps, int B,
+static __global__ void critic_loss_kernel(const float* __restrict__ score, const float* __restrict__ gp_ps, int B,
                                    float lambda_gp, float* __restrict__ out) {
     __shared__ double red[3][32];
     double a = 0, f = 0, g = 0;
@@ -463,7 +463,7 @@ __global__ void critic_loss_kernel(const float* __restrict__ score, const float*
 
 // generator losses: adv = -mean(score); CE over 4-way logits; dlogits = weight * (softmax - onehot)/B
 // out: [0]=loss_g_adv [1]=loss_g_emo
-__global__ void generator_loss_kernel(const float* __restrict__ score, const float* __restrict__ logits,
+static __global__ void generator_loss_kernel(const float* __restrict__ score, const float* __restrict__ logits,
                                       const long long* __restrict__ labels, int B, int NC, float emo_weight,
                                       float* __restrict__ dlogits, float* __restrict__ out) {
     __shared__ double red[2][32];
@@ -492,42 +492,42 @@ __global__ void generator_loss_kernel(const float* __restrict__ score, const flo
 }
 
 // a[i] *= b[i]
-__global__ void mul_inplace_kernel(float* a, const float* b, long long n) {
+static __global__ void mul_inplace_kernel(float* a, const float* b, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] *= b[i];
 }
 // a[i] += b[i]
-__global__ void axpy_kernel(float* a, const float* b, long long n) {
+static __global__ void axpy_kernel(float* a, const float* b, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] += b[i];
 }
 // a[i] += x[i]; b[i] += y[i]   (accumulate the two BatchNorm affine gradients)
-__global__ void add2_kernel(float* a, const float* x, float* b, const float* y, int n) {
+static __global__ void add2_kernel(float* a, const float* x, float* b, const float* y, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { a[i] += x[i]; b[i] += y[i]; }
 }
 // hf[i] = lrelu'(hf[i]) * q[i]
-__global__ void lrelu_mask_mul_inplace_kernel(float* hf, const float* q, long long n) {
+static __global__ void lrelu_mask_mul_inplace_kernel(float* hf, const float* q, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) hf[i] = (hf[i] > 0.f ? 1.f : 0.2f) * q[i];
 }
 // eval-mode BatchNorm: mean/invstd from the running statistics
-__global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, int C, float* mean, float* invstd) {
+static __global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, int C, float* mean, float* invstd) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) { mean[c] = rm[c]; invstd[c] = 1.0f / sqrtf(rv[c] + eps); }
 }
-__global__ void const_fill_kernel(float* p, int n, float v) {
+static __global__ void const_fill_kernel(float* p, int n, float v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 // demb[b, j] (+)= seed[b] * w[F + j]     (critic conditioning term, models.py:165-168)
-__global__ void critic_demb_kernel(const float* seed, const float* w, int B, int F, int E, float* demb, int accumulate) {
+static __global__ void critic_demb_kernel(const float* seed, const float* w, int B, int F, int E, float* demb, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * E) return;
     const float v = seed[i / E] * w[F + i % E];
     demb[i] = accumulate ? demb[i] + v : v;
 }
-__global__ void critic_seed_kernel(float* seed, int B, float w_real, float w_fake) {
+static __global__ void critic_seed_kernel(float* seed, int B, float w_real, float w_fake) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * B) return;
     seed[i] = i < B ? w_real / (float)B : (i < 2 * B ? w_fake / (float)B : 1.0f);
@@ -535,7 +535,7 @@ __global__ void critic_seed_kernel(float* seed, int B, float w_real, float w_fak
 
 // classifier training loss: mean CE over B, accuracy, and dlogits = (softmax - onehot)/B    (train_ed.py:66-80)
 // out: [0] = loss, [1] = accuracy
-__global__ void ce_loss_acc_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int NC,
+static __global__ void ce_loss_acc_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int NC,
                                    float* __restrict__ dlogits, float* __restrict__ out) {
     __shared__ double red[2][32];
     double ce = 0, hit = 0;
@@ -563,14 +563,14 @@ __global__ void ce_loss_acc_kernel(const float* __restrict__ logits, const long 
     }
 }
 
-__global__ void fill_kernel(float* p, long long n, float v) {
+static __global__ void fill_kernel(float* p, long long n, float v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 
 // eval-mode BatchNorm folded into a per-channel scale/shift around a conv bias:
 //   y = (conv + bias - rm) * g/sqrt(rv+eps) + b  =  conv*scale + shift
-__global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+static __global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ rm,
                                const float* __restrict__ rv, float eps, int C, float* __restrict__ scale,
                                float* __restrict__ shift) {

@@ -226,24 +226,6 @@ int fe_backward(mg_gan* c, const float* demb, cudaStream_t st) {
 // A-2..A-4 Generator
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
-                     const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st) {
-    if (train) {
-        MG_TRY((colreduce<float, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
-                                         1.0f, 0, st)));
-        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows, (float)c->cfg.bn_eps,
-                                                            (float)c->cfg.bn_momentum, mean, invstd, rm, rv, 1);
-    } else {
-        bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rm, rv, (float)c->cfg.bn_eps, C, mean, invstd);
-    }
-    MG_LAUNCH_OK();
-    const long long n4 = rows * C / 4;
-    bn_relu_apply_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(x, y, n4, C, mean, invstd, gamma, beta);
-    MG_LAUNCH_OK();
-    return MG_OK;
-}
-
-template <typename T>
 int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, float* notes_out, float* latent_out,
                 cudaStream_t st) {
     const mg_gan_config& f = c->cfg;
@@ -280,21 +262,6 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
     if (latent_out)
         MG_CUDA_OK(cudaMemcpyAsync(latent_out, c->g_lat, sizeof(float) * B * f.latent_dim, cudaMemcpyDeviceToDevice, st));
     c->fwd_state |= FWD_G;
-    return MG_OK;
-}
-
-template <typename T>
-int bn_backward(mg_gan* c, const float* x, const float* dy, T* dx, long long rows, int C, const float* mean,
-                const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st) {
-    // sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat
-    MG_TRY((colreduce<float, COL_BN_BWD, float>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
-                                     0, st)));
-    add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
-    MG_LAUNCH_OK();
-    const long long n4 = rows * C / 4;
-    bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
-                                                         c->g_bn_sums);
-    MG_LAUNCH_OK();
     return MG_OK;
 }
 

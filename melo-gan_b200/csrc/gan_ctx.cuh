@@ -156,7 +156,7 @@ int conv_s1_dgrad(const TA* dOut, TO* dIn, const float* W, int R, int L, int Cin
 //   out[r, 2m+ph, n] = sum_{t = ph (mod 2)} sum_k in[r, m + 1 - t/2, k] * W(t, n, k)
 // ConvTranspose1d forward: W [Cin][Cout][5] -> (w_nstride, w_kstride) = (5, Cout*5)
 // dgrad of a strided Conv1d: W [Cconv_out][Cconv_in][5], k = conv_out, n = conv_in -> (5, Cconv_in*5)
-template <typename TA, typename TO>
+template <typename TA, typename TO, typename TMSK = TO>
 int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int K, int N,
                   int w_nstride, int w_kstride, int act, const void* mul_src, int mul_mode, int accumulate,
                   cudaStream_t st) {
@@ -173,7 +173,7 @@ int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int 
         a.Out = out; a.o_bstride = (long long)2 * Lin * N; a.o_mstride = 2 * N; a.o_off = ph * N;
         a.B = R; a.Mper = Lin; a.N = N;
         a.bias = bias; a.act = act; a.mul_src = mul_src; a.mul_mode = mul_mode; a.accumulate = accumulate;
-        int rc = launch_tapgemm<TA, TO>(a, st);
+        int rc = launch_tapgemm<TA, TO, TMSK>(a, st);
         if (rc != MG_OK) return rc;
     }
     return MG_OK;
@@ -255,5 +255,42 @@ inline int grid_for(long long n, int threads = 256, int max_per_sm = 8) {
     if (b > cap) b = cap;
     return (int)(b < 1 ? 1 : b);
 }
+
+// ---- BatchNorm1d + ReLU over a float32 pre-activation [rows, C] (train: batch statistics + running update) ----
+template <typename T>
+int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
+                     const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st) {
+    if (train) {
+        MG_TRY((colreduce<float, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
+                                         1.0f, 0, st)));
+        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows, (float)c->cfg.bn_eps,
+                                                            (float)c->cfg.bn_momentum, mean, invstd, rm, rv, 1);
+    } else {
+        bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rm, rv, (float)c->cfg.bn_eps, C, mean, invstd);
+    }
+    MG_LAUNCH_OK();
+    const long long n4 = rows * C / 4;
+    bn_relu_apply_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(x, y, n4, C, mean, invstd, gamma, beta);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+
+// ---- its backward: dy (float32, ReLU mask already applied) -> dx, accumulates d gamma / d beta ----
+template <typename T>
+int bn_backward(mg_gan* c, const float* x, const float* dy, T* dx, long long rows, int C, const float* mean,
+                const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st) {
+    // sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat
+    MG_TRY((colreduce<float, COL_BN_BWD, float>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
+                                     0, st)));
+    add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
+    MG_LAUNCH_OK();
+    const long long n4 = rows * C / 4;
+    bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
+                                                         c->g_bn_sums);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
 
 }  // namespace mg

@@ -60,6 +60,12 @@ _SIGNATURES = {
     "mg_emotion_train_forward": ([_vp, _vp, _vp, _vp, _d, _vp, _vp], _i),
     "mg_emotion_train_backward": ([_vp, _vp, _vp, _vp, _vp], _i),
     "mg_cross_entropy": ([_vp, _vp, _i, _i, _vp, _vp, _vp], _i),
+    "mg_vae_create": ([_i, _i, _i, _i, _vp], _i),
+    "mg_vae_destroy": ([_vp], None),
+    "mg_vae_bind": ([_vp, _vp, _i, _vp, _i], _i),
+    "mg_vae_forward": ([_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_vae_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_vae_loss_step": ([_vp, _vp, _vp, _d, _vp, _vp], _i),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
 }

@@ -288,3 +288,81 @@ _GAN_SIGNATURES = {
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
 }
+
+
+# ------------------------------------------------------------------------------------------------
+# A-12: VAE context (BASELINE config #2)
+# ------------------------------------------------------------------------------------------------
+VAE_PARAM_KEYS = []
+for _c, _b in ((0, 1), (3, 4), (6, 7)):
+    VAE_PARAM_KEYS += [f"encoder.conv.{_c}.weight", f"encoder.conv.{_c}.bias", f"encoder.conv.{_b}.weight",
+                       f"encoder.conv.{_b}.bias"]
+VAE_PARAM_KEYS += ["encoder._linear.1.weight", "encoder._linear.1.bias", "fc_mu.weight", "fc_mu.bias",
+                   "fc_log_var.weight", "fc_log_var.bias", "decoder.pre.0.weight", "decoder.pre.0.bias",
+                   "decoder.pre.2.weight", "decoder.pre.2.bias", "decoder.deconv.0.weight", "decoder.deconv.0.bias",
+                   "decoder.deconv.1.weight", "decoder.deconv.1.bias", "decoder.deconv.3.weight", "decoder.deconv.3.bias",
+                   "decoder.deconv.4.weight", "decoder.deconv.4.bias", "decoder.deconv.6.weight", "decoder.deconv.6.bias"]
+VAE_BUFFER_KEYS = []
+for _m in ("encoder.conv.1", "encoder.conv.4", "encoder.conv.7", "decoder.deconv.1", "decoder.deconv.4"):
+    VAE_BUFFER_KEYS += [_m + ".running_mean", _m + ".running_var"]
+
+
+class VaeEngine:
+    def __init__(self, batch, max_notes=512, latent_dim=8, precision="fp32", device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("melogan_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.B, self.T, self.latent = int(batch), int(max_notes), int(latent_dim)
+        self._h = ctypes.c_void_p()
+        L = _native.lib()
+        with torch.cuda.device(self.device):
+            _native.check(L.mg_vae_create(self.B, self.T, self.latent, {"fp32": 0, "bf16": 1}[precision], ctypes.byref(self._h)))
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _native.lib().mg_vae_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, name, *args):
+        with torch.cuda.device(self.device):
+            _native.check(getattr(_native.lib(), name)(self._h, *args))
+
+    def bind(self, params, grads=None):
+        pt = [_check_f32_cuda(params[k], k) for k in VAE_PARAM_KEYS + VAE_BUFFER_KEYS]
+        gt = [_check_f32_cuda(grads[k], "grad " + k, params[k].shape) for k in VAE_PARAM_KEYS] if grads is not None else None
+        parr = (ctypes.c_void_p * len(pt))(*[t.data_ptr() for t in pt])
+        garr = (ctypes.c_void_p * len(gt))(*[t.data_ptr() for t in gt]) if gt else None
+        self._call("mg_vae_bind", parr, len(pt), garr, len(gt) if gt else 0)
+        self._keep["bind"] = (pt, gt)
+
+    def forward(self, x, eps, train=True):
+        _check_f32_cuda(x, "x", (self.B, self.T, 4))
+        _check_f32_cuda(eps, "eps", (self.B, self.latent))
+        recon = torch.empty_like(x)
+        z, mu, lv = (torch.empty((self.B, self.latent), device=self.device) for _ in range(3))
+        self._keep["fwd"] = (x, eps)
+        self._call("mg_vae_forward", _ptr(x), _ptr(eps), int(train), _ptr(recon), _ptr(z), _ptr(mu), _ptr(lv), self._stream())
+        return recon, z, mu, lv
+
+    def backward(self, drecon, dz=None, dmu=None, dlogvar=None):
+        x = self._keep["fwd"][0]
+        _check_f32_cuda(drecon, "drecon", (self.B, self.T, 4))
+        self._call("mg_vae_backward", _ptr(x), _ptr(drecon), _ptr(dz), _ptr(dmu), _ptr(dlogvar), self._stream())
+
+    def loss_step(self, x, eps, beta, metrics=None):
+        _check_f32_cuda(x, "x", (self.B, self.T, 4))
+        _check_f32_cuda(eps, "eps", (self.B, self.latent))
+        metrics = metrics if metrics is not None else torch.empty(3, device=self.device)
+        self._keep["fwd"] = (x, eps)
+        self._call("mg_vae_loss_step", _ptr(x), _ptr(eps), float(beta), _ptr(metrics), self._stream())
+        return metrics

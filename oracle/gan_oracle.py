@@ -385,3 +385,106 @@ def ed_train_step(PED, batch, opt_state, update=True, cfg=ED_CFG):
             adamw_update({k: v for k, v in PED.items() if not is_buffer(k)}, grads, opt_state, cfg["lr"], cfg["betas"][0],
                          cfg["betas"][1], cfg["weight_decay"])
     return {"loss": loss.detach(), "acc": acc, "logits": logits.detach(), "grads": grads}
+
+
+# ------------------------------------------------------------------------------------------------
+# A-12: VAE forward / loss / training step (BASELINE config #2)
+#       reference src/ae/model.py:4-148, src/ae/train_ae.py:35-51,114-122
+# ------------------------------------------------------------------------------------------------
+AE_CFG = dict(LATENT_DIM=8, MAX_NOTES=512, LR=1e-4, WEIGHT_DECAY=1e-5, BETA=10.0, BATCH_SIZE=32)
+
+
+VAE_NOISE_BIASES = {f"encoder.conv.{c}.bias" for c in (0, 3, 6)} | {f"decoder.deconv.{c}.bias" for c in (0, 3)}
+
+
+def vae_param_shapes(latent=8, T=512):
+    L0 = max(1, T // 8)
+    S = {}
+    for (c, b), (ci, co) in zip(((0, 1), (3, 4), (6, 7)), ((4, 32), (32, 64), (64, 128))):
+        S[f"encoder.conv.{c}.weight"] = (co, ci, 5); S[f"encoder.conv.{c}.bias"] = (co,)
+        for nm in ("weight", "bias", "running_mean", "running_var"):
+            S[f"encoder.conv.{b}.{nm}"] = (co,)
+    S.update({"encoder._linear.1.weight": (512, 128 * L0), "encoder._linear.1.bias": (512,),
+              "fc_mu.weight": (latent, 512), "fc_mu.bias": (latent,), "fc_log_var.weight": (latent, 512),
+              "fc_log_var.bias": (latent,), "decoder.pre.0.weight": (512, latent), "decoder.pre.0.bias": (512,),
+              "decoder.pre.2.weight": (128 * L0, 512), "decoder.pre.2.bias": (128 * L0,)})
+    for (c, b), (ci, co) in zip(((0, 1), (3, 4)), ((128, 64), (64, 32))):
+        S[f"decoder.deconv.{c}.weight"] = (ci, co, 5); S[f"decoder.deconv.{c}.bias"] = (co,)
+        for nm in ("weight", "bias", "running_mean", "running_var"):
+            S[f"decoder.deconv.{b}.{nm}"] = (co,)
+    S["decoder.deconv.6.weight"] = (32, 4, 5); S["decoder.deconv.6.bias"] = (4,)
+    return S
+
+
+def make_vae_params(seed, latent=8, T=512):
+    from melogan import synth
+    P = {}
+    for k, (name, shape) in enumerate(vae_param_shapes(latent, T).items()):
+        s = seed * 1000 + 500 + k
+        if name.endswith("running_var"):
+            v = synth.uniform(s, shape, 0.5, 1.5)
+        elif name.endswith("running_mean"):
+            v = synth.uniform(s, shape, -0.1, 0.1)
+        elif len(shape) == 1 and name.endswith("weight"):
+            v = synth.uniform(s, shape, 0.8, 1.2)
+        elif name.endswith("bias"):
+            v = synth.uniform(s, shape, -0.05, 0.05)
+        else:
+            v = synth.pseudo_normal(s, shape, 1.7 / math.sqrt(3.0 * int(np.prod(shape[1:]))))
+        P[name] = torch.from_numpy(np.ascontiguousarray(v))
+    return P
+
+
+def make_vae_batch(seed, B, latent=8, T=512):
+    from melogan import synth
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return {"x": t(synth.uniform(seed * 100 + 1, (B, T, 4))), "eps": t(synth.pseudo_normal(seed * 100 + 2, (B, latent)))}
+
+
+def vae_forward(P, x, eps, train=True, bn_state=None):
+    st = bn_state if bn_state is not None else P
+    h = x.permute(0, 2, 1)
+    for c, b in ((0, 1), (3, 4), (6, 7)):
+        h = F.conv1d(h, P[f"encoder.conv.{c}.weight"], P[f"encoder.conv.{c}.bias"], stride=2, padding=2)
+        h = F.relu(F.batch_norm(h, st[f"encoder.conv.{b}.running_mean"], st[f"encoder.conv.{b}.running_var"],
+                                P[f"encoder.conv.{b}.weight"], P[f"encoder.conv.{b}.bias"], training=train, momentum=0.1, eps=1e-5))
+    h = F.relu(F.linear(h.reshape(h.size(0), -1), P["encoder._linear.1.weight"], P["encoder._linear.1.bias"]))
+    mu = F.linear(h, P["fc_mu.weight"], P["fc_mu.bias"])
+    lv = F.linear(h, P["fc_log_var.weight"], P["fc_log_var.bias"])
+    z = mu + eps * torch.exp(0.5 * lv)
+    y = F.relu(F.linear(z, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"]))
+    y = F.relu(F.linear(y, P["decoder.pre.2.weight"], P["decoder.pre.2.bias"]))
+    y = y.view(y.size(0), 128, -1)
+    for c, b in ((0, 1), (3, 4)):
+        y = F.conv_transpose1d(y, P[f"decoder.deconv.{c}.weight"], P[f"decoder.deconv.{c}.bias"], stride=2, padding=2,
+                               output_padding=1)
+        y = F.relu(F.batch_norm(y, st[f"decoder.deconv.{b}.running_mean"], st[f"decoder.deconv.{b}.running_var"],
+                                P[f"decoder.deconv.{b}.weight"], P[f"decoder.deconv.{b}.bias"], training=train, momentum=0.1, eps=1e-5))
+    y = torch.tanh(F.conv_transpose1d(y, P["decoder.deconv.6.weight"], P["decoder.deconv.6.bias"], stride=2, padding=2,
+                                      output_padding=1))
+    return y.permute(0, 2, 1), z, mu, lv
+
+
+def vae_loss(recon, target, mu, log_var, beta):
+    recon_loss = F.mse_loss(recon, target)
+    kld = -0.5 * torch.mean(1 + log_var - mu.pow(2) - log_var.exp())
+    return recon_loss + beta * kld, recon_loss, kld
+
+
+def vae_train_step(P, batch, opt_state, beta=10.0, update=True, cfg=AE_CFG):
+    """train_ae.py:114-122: forward, vae_loss, backward, clip_grad_norm_(1.0), AdamW(lr, weight_decay)."""
+    leaves = _leaves(P)
+    bn_state = P if update else {k: v.clone() for k, v in P.items() if is_buffer(k)}
+    recon, z, mu, lv = vae_forward(leaves, batch["x"], batch["eps"], True, bn_state)
+    loss, rl, kl = vae_loss(recon, batch["x"], mu, lv, beta)
+    grads = dict(zip(leaves.keys(), torch.autograd.grad(loss, list(leaves.values()))))
+    out = {"loss": loss.detach(), "recon_loss": rl.detach(), "kld": kl.detach(), "recon": recon.detach(), "mu": mu.detach(),
+           "log_var": lv.detach(), "z": z.detach(), "grads": {k: g.clone() for k, g in grads.items()}}
+    if update:
+        with torch.no_grad():
+            total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+            coef = torch.clamp(1.0 / (total + 1e-6), max=1.0)
+            clipped = {k: g * coef for k, g in grads.items()}
+            adamw_update({k: v for k, v in P.items() if not is_buffer(k)}, clipped, opt_state, cfg["LR"], 0.9, 0.999,
+                         cfg["WEIGHT_DECAY"])
+    return out

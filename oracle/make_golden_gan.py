@@ -236,6 +236,41 @@ def main():
     for k, t in model.state_dict().items():
         if not k.endswith("num_batches_tracked"):
             out[f"ED.final.{k}"] = tstats(t)
+    # ---- A-12: the reference's VAE (src/ae/model.py) and training iteration (train_ae.py:114-122), 2 steps ----
+    ref_ae = _load("ref_ae_model", "src/ae/model.py")
+    vp = O.make_vae_params(6)
+    vae = ref_ae.VAE({"LATENT_DIM": 8, "MAX_NOTES": 512})
+    with torch.no_grad():
+        vae(torch.zeros(2, 512, 4))                       # materialises the lazy encoder._linear (train_ae.py:75-77)
+    missing, unexpected = vae.load_state_dict(vp, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    opt = optim.AdamW(vae.parameters(), lr=1e-4, weight_decay=1e-5)
+    vae.train()
+    real_randn_like = torch.randn_like
+    for i in range(2):
+        vb = O.make_vae_batch(70 + i, 8)
+        torch.randn_like = lambda t, _e=vb["eps"]: _e.clone()
+        try:
+            recon, z, mu, log_var = vae(vb["x"])
+        finally:
+            torch.randn_like = real_randn_like
+        recon_loss = torch.nn.functional.mse_loss(recon, vb["x"])
+        kld_loss = -0.5 * torch.mean(1 + log_var - mu.pow(2) - log_var.exp())
+        loss = recon_loss + 10.0 * kld_loss                 # vae_loss (train_ae.py:35-51), beta = BETA of ae_config.yaml
+        opt.zero_grad()
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in vae.named_parameters()}
+        torch.nn.utils.clip_grad_norm_(vae.parameters(), max_norm=1.0)
+        opt.step()
+        out[f"VAE.s{i}.scalars"] = np.array([loss.item(), recon_loss.item(), kld_loss.item()])
+        out[f"VAE.s{i}.recon0"] = recon[0].detach().numpy().copy()
+        out[f"VAE.s{i}.mu"] = mu.detach().numpy().copy()
+        out[f"VAE.s{i}.log_var"] = log_var.detach().numpy().copy()
+        for k, g in grads.items():
+            out[f"VAE.s{i}.grad.{k}"] = tstats(g)
+    for k, t in vae.state_dict().items():
+        if not k.endswith("num_batches_tracked"):
+            out[f"VAE.final.{k}"] = tstats(t)
     path = os.path.join(ROOT, "tests", "golden", "gan_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

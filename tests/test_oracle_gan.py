@@ -86,3 +86,25 @@ def test_ed_training_steps_match_reference(gold):
             close_stats(tstats(g), gold[f"ED.s{i}.grad.{k}"], 5e-4, ("ED", i, k))
     for k, t in params["ED"].items():
         close_stats(tstats(t), gold[f"ED.final.{k}"], 5e-4, ("ED final", k))
+
+
+def test_vae_training_steps_match_reference(gold):
+    """A-12: two iterations of train_ae.py:114-122 (forward, vae_loss, backward, clip, AdamW) on the reference's VAE."""
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    P = O.make_vae_params(6)
+    st = {}
+    for i in range(2):
+        vb = O.make_vae_batch(70 + i, 8)
+        r = O.vae_train_step(P, vb, st, beta=10.0)
+        np.testing.assert_allclose([r["loss"].item(), r["recon_loss"].item(), r["kld"].item()], gold[f"VAE.s{i}.scalars"],
+                                   rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(r["recon"][0].numpy(), gold[f"VAE.s{i}.recon0"], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(r["mu"].numpy(), gold[f"VAE.s{i}.mu"], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(r["log_var"].numpy(), gold[f"VAE.s{i}.log_var"], rtol=1e-4, atol=2e-6)
+        for k, g in r["grads"].items():
+            if k in O.VAE_NOISE_BIASES:        # bias in front of a train-mode BatchNorm: exact gradient is 0, fp noise only
+                assert tstats(g)[1] < 1e-5
+                continue
+            close_stats(tstats(g), gold[f"VAE.s{i}.grad.{k}"], 5e-4, ("VAE", i, k))
+    for k, t in P.items():
+        close_stats(tstats(t), gold[f"VAE.final.{k}"], 2e-2 if k in O.VAE_NOISE_BIASES else 5e-4, ("VAE final", k))
