@@ -222,6 +222,8 @@ int mg_vae_forward(mg_vae* ctx, const float* x, const float* eps, int train, flo
                    float* mu_out, float* logvar_out, void* stream);
 int mg_vae_backward(mg_vae* ctx, const float* x, const float* drecon, const float* dz, const float* dmu,
                     const float* dlogvar, void* stream);
+/* Debug view of a named workspace buffer of the VAE context (tests compare intermediate activations / gradients). */
+int mg_vae_buffer(mg_vae* ctx, const char* name, void** ptr, long long* nbytes);
 int mg_vae_loss_step(mg_vae* ctx, const float* x, const float* eps, double beta, float* metrics_out, void* stream);
 
 /* A-7 composite: the whole critic step body up to (not including) opt_D.step()

@@ -11,6 +11,7 @@
 
 #include "gan_ctx.cuh"
 
+#include <cstring>
 using namespace mg;
 
 __global__ void relu_mask_inplace_kernel(float* d, const float* h, long long n) {
@@ -324,6 +325,28 @@ extern "C" int mg_vae_bind(mg_vae* v, void* const* params, int nparams, void* co
     v->bound = true;
     v->has_grads = grads != nullptr;
     return MG_OK;
+}
+
+extern "C" int mg_vae_buffer(mg_vae* v, const char* name, void** ptr, long long* nbytes) {
+    MG_REQUIRE(v && name && ptr && nbytes, "vae_buffer: null argument");
+    const size_t B = v->B, T = v->T, L0 = v->L0, lat = v->latent, es = v->bf16 ? 2 : 4;
+    const struct { const char* n; void* p; size_t b; } tab[] = {
+        {"e_x0", v->e_x[0], B * T / 2 * 32 * 4}, {"e_x1", v->e_x[1], B * T / 4 * 64 * 4}, {"e_x2", v->e_x[2], B * L0 * 128 * 4},
+        {"e_a0", v->e_a[0], B * T / 2 * 32 * es}, {"e_a1", v->e_a[1], B * T / 4 * 64 * es}, {"e_a2", v->e_a[2], B * L0 * 128 * es},
+        {"h", v->h, B * 512 * 4}, {"d0", v->d0, B * 512 * 4}, {"d_y0", v->d_y0, B * L0 * 128 * es},
+        {"d_x0", v->d_x[0], B * 2 * L0 * 64 * 4}, {"d_x1", v->d_x[1], B * 4 * L0 * 32 * 4},
+        {"d_y1", v->d_y[0], B * 2 * L0 * 64 * es}, {"d_y2", v->d_y[1], B * 4 * L0 * 32 * es},
+        {"pre_t", v->pre_t, B * T * 4 * 4}, {"recon", v->recon, B * T * 4 * 4}, {"dt", v->dt, B * T * 4 * 4},
+        {"dy_f1", v->dy_f[0], B * 2 * L0 * 64 * 4}, {"dy_f2", v->dy_f[1], B * 4 * L0 * 32 * 4},
+        {"dxd1", v->dxd[0], B * 2 * L0 * 64 * es}, {"dxd2", v->dxd[1], B * 4 * L0 * 32 * es}, {"dy0", v->dy0, B * L0 * 128 * es},
+        {"dd0", v->dd0, B * 512 * 4}, {"dz", v->dz, B * lat * 4}, {"dmu", v->dmu, B * lat * 4}, {"dlv", v->dlv, B * lat * 4},
+        {"dh", v->dh, B * 512 * 4}, {"de_f2", v->de_f[2], B * L0 * 128 * 4}, {"de_f1", v->de_f[1], B * T / 4 * 64 * 4},
+        {"de_f0", v->de_f[0], B * T / 2 * 32 * 4}, {"dxe2", v->dxe[2], B * L0 * 128 * es}, {"dxe1", v->dxe[1], B * T / 4 * 64 * es},
+        {"dxe0", v->dxe[0], B * T / 2 * 32 * es}};
+    for (const auto& e : tab)
+        if (!strcmp(e.n, name)) { *ptr = e.p; *nbytes = (long long)e.b; return MG_OK; }
+    mg::set_error("vae_buffer: unknown buffer '%s'", name);
+    return MG_ERR_INVALID;
 }
 
 extern "C" int mg_vae_forward(mg_vae* v, const float* x, const float* eps, int train, float* recon_out, float* z_out,

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "mg_vae_bind": ([_vp, _vp, _i, _vp, _i], _i),
     "mg_vae_forward": ([_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_vae_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mg_vae_buffer": ([_vp, ctypes.c_char_p, _vp, _vp], _i),
     "mg_vae_loss_step": ([_vp, _vp, _vp, _d, _vp, _vp], _i),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),

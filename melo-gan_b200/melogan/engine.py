@@ -359,6 +359,15 @@ class VaeEngine:
         _check_f32_cuda(drecon, "drecon", (self.B, self.T, 4))
         self._call("mg_vae_backward", _ptr(x), _ptr(drecon), _ptr(dz), _ptr(dmu), _ptr(dlogvar), self._stream())
 
+    def buffer(self, name, dtype=torch.float32):
+        """Debug view of a named workspace buffer (copied out)."""
+        p, n = ctypes.c_void_p(), ctypes.c_longlong()
+        self._call("mg_vae_buffer", name.encode(), ctypes.byref(p), ctypes.byref(n))
+        out = torch.empty(n.value // torch.empty((), dtype=dtype).element_size(), dtype=dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.call("mg_device_copy", out.data_ptr(), p.value, n.value, self._stream())
+        return out
+
     def loss_step(self, x, eps, beta, metrics=None):
         _check_f32_cuda(x, "x", (self.B, self.T, 4))
         _check_f32_cuda(eps, "eps", (self.B, self.latent))

@@ -441,25 +441,40 @@ def make_vae_batch(seed, B, latent=8, T=512):
     return {"x": t(synth.uniform(seed * 100 + 1, (B, T, 4))), "eps": t(synth.pseudo_normal(seed * 100 + 2, (B, latent)))}
 
 
-def vae_forward(P, x, eps, train=True, bn_state=None):
+def vae_forward(P, x, eps, train=True, bn_state=None, masks=None, snap=1e-4, margins=None):
+    """masks (test aid): name -> bool tensor of the ReLU decisions another implementation took.  Where a pre-activation is
+    within `snap` of zero -- where float32 rounding alone decides the branch -- that decision is used instead of this
+    forward's own, so that gradients can be compared on identical branches.  margins: list collecting min |pre-activation|."""
     st = bn_state if bn_state is not None else P
+
+    def relu(name, t):
+        if margins is not None:
+            margins.append(t.detach().abs().min().item())
+        if masks is None:
+            return F.relu(t)
+        fragile = t.detach().abs() < snap
+        keep = torch.where(fragile, masks[name], t.detach() > 0)
+        return t * keep.to(t.dtype)
+
     h = x.permute(0, 2, 1)
-    for c, b in ((0, 1), (3, 4), (6, 7)):
+    for i, (c, b) in enumerate(((0, 1), (3, 4), (6, 7))):
         h = F.conv1d(h, P[f"encoder.conv.{c}.weight"], P[f"encoder.conv.{c}.bias"], stride=2, padding=2)
-        h = F.relu(F.batch_norm(h, st[f"encoder.conv.{b}.running_mean"], st[f"encoder.conv.{b}.running_var"],
-                                P[f"encoder.conv.{b}.weight"], P[f"encoder.conv.{b}.bias"], training=train, momentum=0.1, eps=1e-5))
-    h = F.relu(F.linear(h.reshape(h.size(0), -1), P["encoder._linear.1.weight"], P["encoder._linear.1.bias"]))
+        h = relu(f"e_a{i}", F.batch_norm(h, st[f"encoder.conv.{b}.running_mean"], st[f"encoder.conv.{b}.running_var"],
+                                         P[f"encoder.conv.{b}.weight"], P[f"encoder.conv.{b}.bias"], training=train, momentum=0.1,
+                                         eps=1e-5))
+    h = relu("h", F.linear(h.reshape(h.size(0), -1), P["encoder._linear.1.weight"], P["encoder._linear.1.bias"]))
     mu = F.linear(h, P["fc_mu.weight"], P["fc_mu.bias"])
     lv = F.linear(h, P["fc_log_var.weight"], P["fc_log_var.bias"])
     z = mu + eps * torch.exp(0.5 * lv)
-    y = F.relu(F.linear(z, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"]))
-    y = F.relu(F.linear(y, P["decoder.pre.2.weight"], P["decoder.pre.2.bias"]))
+    y = relu("d0", F.linear(z, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"]))
+    y = relu("d_y0", F.linear(y, P["decoder.pre.2.weight"], P["decoder.pre.2.bias"]))
     y = y.view(y.size(0), 128, -1)
-    for c, b in ((0, 1), (3, 4)):
+    for i, (c, b) in enumerate(((0, 1), (3, 4))):
         y = F.conv_transpose1d(y, P[f"decoder.deconv.{c}.weight"], P[f"decoder.deconv.{c}.bias"], stride=2, padding=2,
                                output_padding=1)
-        y = F.relu(F.batch_norm(y, st[f"decoder.deconv.{b}.running_mean"], st[f"decoder.deconv.{b}.running_var"],
-                                P[f"decoder.deconv.{b}.weight"], P[f"decoder.deconv.{b}.bias"], training=train, momentum=0.1, eps=1e-5))
+        y = relu(f"d_y{i + 1}", F.batch_norm(y, st[f"decoder.deconv.{b}.running_mean"], st[f"decoder.deconv.{b}.running_var"],
+                                             P[f"decoder.deconv.{b}.weight"], P[f"decoder.deconv.{b}.bias"], training=train,
+                                             momentum=0.1, eps=1e-5))
     y = torch.tanh(F.conv_transpose1d(y, P["decoder.deconv.6.weight"], P["decoder.deconv.6.bias"], stride=2, padding=2,
                                       output_padding=1))
     return y.permute(0, 2, 1), z, mu, lv
@@ -471,11 +486,11 @@ def vae_loss(recon, target, mu, log_var, beta):
     return recon_loss + beta * kld, recon_loss, kld
 
 
-def vae_train_step(P, batch, opt_state, beta=10.0, update=True, cfg=AE_CFG):
+def vae_train_step(P, batch, opt_state, beta=10.0, update=True, cfg=AE_CFG, masks=None, margins=None):
     """train_ae.py:114-122: forward, vae_loss, backward, clip_grad_norm_(1.0), AdamW(lr, weight_decay)."""
     leaves = _leaves(P)
     bn_state = P if update else {k: v.clone() for k, v in P.items() if is_buffer(k)}
-    recon, z, mu, lv = vae_forward(leaves, batch["x"], batch["eps"], True, bn_state)
+    recon, z, mu, lv = vae_forward(leaves, batch["x"], batch["eps"], True, bn_state, masks=masks, margins=margins)
     loss, rl, kl = vae_loss(recon, batch["x"], mu, lv, beta)
     grads = dict(zip(leaves.keys(), torch.autograd.grad(loss, list(leaves.values()))))
     out = {"loss": loss.detach(), "recon_loss": rl.detach(), "kld": kl.detach(), "recon": recon.detach(), "mu": mu.detach(),
