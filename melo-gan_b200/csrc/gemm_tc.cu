@@ -53,6 +53,10 @@ bool ws_enabled() {
     }
     return v == 1;
 }
+bool reuse_enabled() {
+    static const bool on = getenv("MELOGAN_DISABLE_TAP_REUSE") == nullptr;
+    return on;
+}
 int set_enabled(int on) {
     const int prev = enabled() ? 1 : 0;
     g_enabled = on ? 1 : 0;

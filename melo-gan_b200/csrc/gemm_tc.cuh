@@ -114,6 +114,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32 consecutive fp32 columns, asynchronous: call tmem_wait_ld() before using the registers
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -137,6 +150,12 @@ struct TcTapArgs {
     int ntaps, kblocks;                 // kblocks = K / 64 per tap
     int a_p[kTcMaxTaps], a_dm[kTcMaxTaps];  // per tap: plane (dim 1) and row shift (dim 2) of the A map
     int b_row[kTcMaxTaps];                  // per tap: first row of that tap's [N][K] block in the packed weight
+    // tap groups (weight-stationary kernel): the taps of a group read the same plane at row shifts within `halo` rows of
+    // g_dmin, so ONE activation tile of 128 + halo rows per k-block serves all of them -- each tap's MMA operand is the
+    // same shared-memory tile entered `a_dm - g_dmin` rows further down (a SWIZZLE_128B K-major descriptor may start at any
+    // 128-byte row: the swizzle is a function of the absolute shared-memory address, scripts/probes/desc_rowoff_probe.cu).
+    int ngroups, halo;
+    int g_p[kTcMaxTaps], g_dmin[kTcMaxTaps], g_first[kTcMaxTaps], g_count[kTcMaxTaps], g_tap[kTcMaxTaps];
     int mpt, bpt;                       // tile = bpt samples x mpt rows, mpt * bpt = 128
     int Mper, B, N;
     int n_perm_q, n_perm_p;             // bias index permutation (the packed weight is already permuted)
@@ -145,6 +164,17 @@ struct TcTapArgs {
     const void* mul_src; int mul_mode; void* aux;
     float alpha; int accumulate;
 };
+
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {      // one 16-byte store
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b),
+                                              *reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
+}
 
 // Drain one 128 x BN accumulator tile: TMEM -> registers -> bias/scale/activation/mask -> global.
 // `wait_bar`/`wait_parity`: the MMA->epilogue barrier of this accumulator.  The mask row is prefetched BEFORE the wait.
@@ -170,59 +200,64 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
         }
         mbar_wait(wait_bar, wait_parity);
         tc_fence_after();
+        static_assert(NC % 32 == 0, "column range must be whole groups of 32");
+        const float4* __restrict__ sc4 = reinterpret_cast<const float4*>(s_scale);
+        const float4* __restrict__ bi4 = reinterpret_cast<const float4*>(s_bias);
 #pragma unroll 1
-        for (int c0 = c_begin; c0 < c_begin + NC; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        for (int c0 = c_begin; c0 < c_begin + NC; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32_async(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+            tmem_wait_ld();
             if (!row_ok) continue;
-            float ms[16];
-            if (P.mul_mode != MUL_NONE) {
-                if (kPrefetchMask) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint4 mv = mreg[((c0 - c_begin) >> 3) + h];
+            for (int g8 = 0; g8 < 32; g8 += 8) {          // 8 columns: one 16-byte (bf16) or two 16-byte (float) stores
+                float ms[8], old[8], x[8], gd[8];
+                if (P.mul_mode != MUL_NONE) {
+                    if (kPrefetchMask) {
+                        const uint4 mv = mreg[(c0 - c_begin + g8) >> 3];
                         const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            ms[h * 8 + 2 * e] = __uint_as_float(w[e] << 16);
-                            ms[h * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                            ms[2 * e] = __uint_as_float(w[e] << 16);
+                            ms[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 8; h += 4) {
+                            float t4[4];
+                            ld4(Mb + o + c0 + g8 + h, t4);
+                            ms[h] = t4[0]; ms[h + 1] = t4[1]; ms[h + 2] = t4[2]; ms[h + 3] = t4[3];
                         }
                     }
-                } else {
+                }
+                if (P.accumulate) {
 #pragma unroll
-                    for (int g4 = 0; g4 < 16; g4 += 4) {
+                    for (int h = 0; h < 8; h += 4) {
                         float t4[4];
-                        ld4(Mb + o + c0 + g4, t4);
-                        ms[g4] = t4[0]; ms[g4 + 1] = t4[1]; ms[g4 + 2] = t4[2]; ms[g4 + 3] = t4[3];
+                        ld4(Ob + o + c0 + g8 + h, t4);
+                        old[h] = t4[0]; old[h + 1] = t4[1]; old[h + 2] = t4[2]; old[h + 3] = t4[3];
                     }
                 }
-            }
-            float old[16];
-            if (P.accumulate) {
 #pragma unroll
-                for (int g4 = 0; g4 < 16; g4 += 4) {
-                    float t4[4];
-                    ld4(Ob + o + c0 + g4, t4);
-                    old[g4] = t4[0]; old[g4 + 1] = t4[1]; old[g4 + 2] = t4[2]; old[g4 + 3] = t4[3];
+                for (int h = 0; h < 8; h += 4) {
+                    const float4 sc = sc4[(c0 + g8 + h) >> 2], bi = bi4[(c0 + g8 + h) >> 2];
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float y = fmaf(__uint_as_float(raw[g8 + h + j]), scv[j], biv[j]);
+                        gd[h + j] = 0.0f;
+                        if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
+                        else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
+                        else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[h + j]); y = yy; }
+                        if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.2f);
+                        else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.0f);
+                        else if (P.mul_mode == MUL_VALUE) y *= ms[h + j];
+                        if (P.accumulate) y += old[h + j];
+                        x[h + j] = y;
+                    }
                 }
-            }
-#pragma unroll
-            for (int g4 = 0; g4 < 16; g4 += 4) {
-                float x[4], gd[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float y = fmaf(v[g4 + j], s_scale[c0 + g4 + j], s_bias[c0 + g4 + j]);
-                    if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
-                    else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
-                    else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[j]); y = yy; }
-                    if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.2f);
-                    else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[g4 + j] > 0.0f ? 1.0f : 0.0f);
-                    else if (P.mul_mode == MUL_VALUE) y *= ms[g4 + j];
-                    if (P.accumulate) y += old[g4 + j];
-                    x[j] = y;
-                }
-                st4(Ob + o + c0 + g4, x);
-                if (P.aux) st4(Xb + o + c0 + g4, gd);
+                st8(Ob + o + c0 + g8, x);
+                if (P.aux) st8(Xb + o + c0 + g8, gd);
             }
         }
 }
@@ -233,14 +268,14 @@ struct TapSmem {
     __nv_bfloat16 b[kStages][BN * kTileK];
     uint64_t full[kStages], empty[kStages], tmem_full;
     uint32_t tmem_base;
-    float bias[BN], scale[BN];          // this tile's bias (permuted) and alpha * folded-BN scale
+    alignas(16) float bias[BN], scale[BN];          // this tile's bias (permuted) and alpha * folded-BN scale
 };
 
 template <int BN, typename TO, typename TMSK>
 __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__ CUtensorMap a_map,
                                                          const __grid_constant__ CUtensorMap b_map, const TcTapArgs P) {
     extern __shared__ unsigned char smem_raw[];
-    TapSmem<BN>& S = *reinterpret_cast<TapSmem<BN>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    TapSmem<BN>& S = *reinterpret_cast<TapSmem<BN>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
     constexpr uint32_t kStageBytes = (kTileM + BN) * kTileK * 2;
@@ -338,7 +373,7 @@ template <int BN>
 struct WsHeader {
     uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
-    float bias[BN], scale[BN];
+    alignas(16) float bias[BN], scale[BN];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -350,14 +385,16 @@ __global__ void __launch_bounds__(kWsThreads) tc_tapgemm_ws_kernel(const __grid_
                                                             const __grid_constant__ CUtensorMap b_map, const TcTapArgs P,
                                                             int mtiles, int nstages) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     WsHeader<BN>& H = *reinterpret_cast<WsHeader<BN>*>(base);
     const int nkb = P.ntaps * P.kblocks;
     __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(base + 2048);                       // [nkb][BN][64]
-    __nv_bfloat16* asm_ = wsm + (size_t)nkb * BN * kTileK;                                    // [nstages][128][64]
+    unsigned char* asm_ = reinterpret_cast<unsigned char*>(wsm + (size_t)nkb * BN * kTileK);  // [nstages][128 + halo][64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
-    constexpr uint32_t kABytes = kTileM * kTileK * 2, kWBytes = BN * kTileK * 2;
+    constexpr uint32_t kWBytes = BN * kTileK * 2;
+    const uint32_t a_tx = (uint32_t)(kTileM + P.halo) * kTileK * 2;                           // bytes one A box delivers
+    const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
     const int n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
@@ -390,14 +427,13 @@ __global__ void __launch_bounds__(kWsThreads) tc_tapgemm_ws_kernel(const __grid_
             for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
                 int b0, m0;
                 tile_coords(tile, b0, m0);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % nstages, ph = (it / nstages) & 1;
-                    mbar_wait(&H.empty[s], ph ^ 1);
-                    const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
-                    mbar_expect_tx(&H.full[s], kABytes);
-                    tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * kTileM * kTileK, kc * kTileK, P.a_p[t],
-                                m0 + P.a_dm[t], b0);
-                }
+                for (int g = 0; g < P.ngroups; ++g)
+                    for (int kc = 0; kc < P.kblocks; ++kc, ++it) {
+                        const int s = it % nstages, ph = (it / nstages) & 1;
+                        mbar_wait(&H.empty[s], ph ^ 1);
+                        mbar_expect_tx(&H.full[s], a_tx);
+                        tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, kc * kTileK, P.g_p[g], m0 + P.g_dmin[g], b0);
+                    }
             }
         }
     } else if (warp == 1) {
@@ -409,22 +445,30 @@ __global__ void __launch_bounds__(kWsThreads) tc_tapgemm_ws_kernel(const __grid_
             mbar_wait(&H.tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem0 + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % nstages, ph = (it / nstages) & 1;
-                mbar_wait(&H.full[s], ph);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(asm_ + (size_t)s * kTileM * kTileK);
-                    const uint32_t b_addr = smem_u32(wsm + (size_t)kb * BN * kTileK);
+            uint32_t started = 0;
+            for (int g = 0; g < P.ngroups; ++g)
+                for (int kc = 0; kc < P.kblocks; ++kc, ++it) {
+                    const int s = it % nstages, ph = (it / nstages) & 1;
+                    mbar_wait(&H.full[s], ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t stage_addr = smem_u32(asm_ + (size_t)s * a_stage);
+                        for (int j = 0; j < P.g_count[g]; ++j) {
+                            const int t = P.g_tap[P.g_first[g] + j];
+                            const uint32_t a_addr = stage_addr + (uint32_t)(P.a_dm[t] - P.g_dmin[g]) * 128u;
+                            const uint32_t b_addr = smem_u32(wsm + (size_t)(t * P.kblocks + kc) * BN * kTileK);
 #pragma unroll
-                    for (int k = 0; k < kTileK / 16; ++k)
-                        umma_f16(tacc, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
-                                 idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&H.empty[s]);
-                    if (kb == nkb - 1) umma_commit(&H.tmem_full[acc]);
+                            for (int k = 0; k < kTileK / 16; ++k) {
+                                umma_f16(tacc, make_smem_desc(a_addr + k * 32, 16, 1024),
+                                         make_smem_desc(b_addr + k * 32, 16, 1024), idesc, started);
+                                started = 1;
+                            }
+                        }
+                        umma_commit(&H.empty[s]);
+                        if (g == P.ngroups - 1 && kc == P.kblocks - 1) umma_commit(&H.tmem_full[acc]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
         }
     } else {
         const int et = threadIdx.x - 64;                 // 0..255
@@ -480,7 +524,7 @@ template <int BNK>
 __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap g_map,
                                                        const __grid_constant__ CUtensorMap a_map, const TcWgradArgs P) {
     extern __shared__ unsigned char smem_raw[];
-    WgradSmem<BNK>& S = *reinterpret_cast<WgradSmem<BNK>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    WgradSmem<BNK>& S = *reinterpret_cast<WgradSmem<BNK>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = BNK < 32 ? 32 : BNK;
     constexpr uint32_t kStageBytes = (2 + BNK / 64) * 64 * 64 * 2;
@@ -662,10 +706,41 @@ int launch_tc_wgrad(const CUtensorMap& gm, const CUtensorMap& am, const TcWgradA
 
 static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+// Tap groups for the weight-stationary kernel.  halo_max = 0: every tap is its own group (one 128-row tile per tap).
+// Otherwise taps of the same plane whose row shifts lie within halo_max rows share one tile with a halo.
+inline void build_tap_groups(TcTapArgs& a, int halo_max) {
+    int order[kTcMaxTaps];
+    for (int t = 0; t < a.ntaps; ++t) order[t] = t;
+    if (halo_max > 0)
+        for (int i = 1; i < a.ntaps; ++i)          // insertion sort by (plane, row shift)
+            for (int j = i; j > 0; --j) {
+                const int x = order[j - 1], y = order[j];
+                if (a.a_p[x] < a.a_p[y] || (a.a_p[x] == a.a_p[y] && a.a_dm[x] <= a.a_dm[y])) break;
+                order[j - 1] = y; order[j] = x;
+            }
+    a.ngroups = 0; a.halo = 0;
+    for (int i = 0; i < a.ntaps; ++i) {
+        const int t = order[i];
+        a.g_tap[i] = t;
+        const int g = a.ngroups - 1;
+        if (g >= 0 && halo_max > 0 && a.g_p[g] == a.a_p[t] && a.a_dm[t] - a.g_dmin[g] <= halo_max) {
+            a.g_count[g]++;
+            if (a.a_dm[t] - a.g_dmin[g] > a.halo) a.halo = a.a_dm[t] - a.g_dmin[g];
+        } else {
+            a.g_p[a.ngroups] = a.a_p[t]; a.g_dmin[a.ngroups] = a.a_dm[t]; a.g_first[a.ngroups] = i; a.g_count[a.ngroups] = 1;
+            a.ngroups++;
+        }
+    }
+}
+
+bool reuse_enabled();        // MELOGAN_DISABLE_TAP_REUSE=1: one activation tile per tap (A/B profiling)
+
 // Launch a tap-GEMM whose tensor maps and TcTapArgs are ready: weight-stationary persistent form when the slab's
-// weights fit in shared memory next to >= 4 activation stages and every CTA gets >= 4 tiles, else one tile per CTA.
+// weights fit in shared memory next to >= 3 activation stages and every CTA gets >= 4 tiles, else one tile per CTA.
+// am_halo (optional): the same activation view with boxes of 128 + a.halo rows, a.ngroups/g_* describing the tap groups.
 template <typename TO, typename TMSK>
-int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a, int BN, int K, cudaStream_t st) {
+int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN, int K, cudaStream_t st,
+               const CUtensorMap* am_halo = nullptr) {
     const long long rows = (long long)a.B * a.Mper;
     const int mtiles = (int)((rows + 127) / 128);
     ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * a.N * a.ntaps * K, (double)rows * (K * 2.0 + a.N * sizeof(TO)), st);
@@ -675,12 +750,15 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a,
     int ctas_x = num_sms() / nslabs;
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
-    if (ws_enabled() && wbytes + 4 * 16384 <= avail && mtiles >= 4 * ctas_x) {
-        int nstages = (int)((avail - wbytes) / 16384);
+    if (!am_halo) build_tap_groups(a, 0);
+    const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
+    if (ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x) {
+        int nstages = (int)((avail - wbytes) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
-        const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * 16384;
-        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st)
-                           : launch_tc_tap_ws<64, TO, TMSK>(am, bm, a, mtiles, nstages, ctas_x, smem, st);
+        const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * a_stage;
+        const CUtensorMap& amap = am_halo ? *am_halo : am;
+        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, a, mtiles, nstages, ctas_x, smem, st)
+                           : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, a, mtiles, nstages, ctas_x, smem, st);
     }
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
 }
@@ -746,7 +824,17 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     if (rc != MG_OK) return rc;
     rc = make_weight_map(&bm, wp, P.K, (long long)P.ntaps * P.N, BN);
     if (rc != MG_OK) return rc;
-    rc = run_tc_tap<TO, TMSK>(am, bm, a, BN, P.K, st);
+    CUtensorMap amh;
+    const CUtensorMap* halo_map = nullptr;
+    if (reuse_enabled() && a.mpt == 128 && P.ntaps > 1) {
+        build_tap_groups(a, 8);
+        if (a.ngroups < a.ntaps) {
+            rc = make_act_map(&amh, P.A, P.K, LA, P.B, stride, 128 + a.halo, 1);
+            if (rc != MG_OK) return rc;
+            halo_map = &amh;
+        }
+    }
+    rc = run_tc_tap<TO, TMSK>(am, bm, a, BN, P.K, st, halo_map);
     return rc == MG_OK ? 1 : rc;
 }
 
