@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
 // TMA-loaded into shared memory once (<= 192 KB), the CTA then walks M tiles (grid-strided), streaming only activation
 // tiles through a small ring, with two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 constexpr int kWsMaxStages = 8;
-constexpr int kWsThreads = 320;      // TMA warp, MMA warp, 2 x 4 epilogue warps (each warpgroup drains half the columns)
+// TMA warp, MMA warp, then BN / 32 epilogue warpgroups of 4 warps; each warpgroup drains 32 accumulator columns.  The
+// drain is a chain of dependent latencies (tcgen05.ld -> math -> store), so it is hidden by warps, not by ILP.
+template <int BN> struct WsCfg { static constexpr int kGroups = BN / 32, kEpiThreads = kGroups * 128, kThreads = 64 + kEpiThreads; };
 template <int BN>
 struct WsHeader {
     uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2];
@@ -381,7 +383,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int BN, typename TO, typename TMSK>
-__global__ void __launch_bounds__(kWsThreads) tc_tapgemm_ws_kernel(const __grid_constant__ CUtensorMap a_map,
+__global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(const __grid_constant__ CUtensorMap a_map,
                                                             const __grid_constant__ CUtensorMap b_map, const TcTapArgs P,
                                                             int mtiles, int nstages) {
     extern __shared__ unsigned char smem_raw[];
@@ -472,21 +474,22 @@ __global__ void __launch_bounds__(kWsThreads) tc_tapgemm_ws_kernel(const __grid_
         }
     } else {
         const int et = threadIdx.x - 64;                 // 0..255
-        const int half = et >> 7;                        // which half of the BN columns this warpgroup drains
-        for (int i = et; i < BN; i += 256) {
+        constexpr int kEpi = WsCfg<BN>::kEpiThreads;
+        const int grp = et >> 7;                         // which 32 columns of the slab this warpgroup drains
+        for (int i = et; i < BN; i += kEpi) {
             H.bias[i] = P.bias ? __ldg(P.bias + perm_index(n0 + i, P.n_perm_q, P.n_perm_p)) : 0.0f;
             H.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
         int tcount = 0;
         for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
             const int acc = tcount & 1;
             int b0, m0;
             tile_coords(tile, b0, m0);
-            drain_tile<BN, BN / 2, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
-                                             &H.tmem_full[acc], (tcount >> 1) & 1, half * (BN / 2));
+            drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
+                                         &H.tmem_full[acc], (tcount >> 1) & 1, grp * 32);
             tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");       // every epilogue thread has read its TMEM lanes
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");   // every epilogue thread has read its TMEM lanes
             if (et == 0) mbar_arrive(&H.tmem_empty[acc]);
         }
     }
@@ -685,7 +688,7 @@ int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const TcTapAr
         attr_smem = 227 * 1024;
     }
     dim3 grid(ctas_x, a.N / BN);
-    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, kWsThreads, smem, st>>>(am, bm, a, mtiles, nstages);
+    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, a, mtiles, nstages);
     MG_LAUNCH_OK();
     return MG_OK;
 }
