@@ -128,23 +128,77 @@ static __global__ void __launch_bounds__(256) colreduce_vec4_kernel(const ColRed
     }
 }
 
+// Narrow matrices (C <= 1024, C/4 a power of two): the 256 threads of a CTA tile (row lane) x (4-column group) so that
+// every lane loads, whatever C is; one CTA per row chunk, rows unrolled 8 deep to keep ~16 KB per CTA in flight.
+template <typename T, typename TY, int OP>
+static __global__ void __launch_bounds__(256) colreduce_flat_kernel(const ColReduceArgs P) {
+    constexpr int NOUT = (OP == COL_SUM_SQ || OP == COL_BN_BWD) ? 2 : 1;
+    __shared__ float red[NOUT][4][256];
+    const int cgs = P.C >> 2, lanes = 256 / cgs;
+    const int cg = threadIdx.x % cgs, rl = threadIdx.x / cgs, c = cg * 4;
+    const long long rb = P.r0 + (long long)blockIdx.y * P.rows_per_chunk;
+    long long re = rb + P.rows_per_chunk;
+    if (re > P.r1) re = P.r1;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* x = static_cast<const T*>(P.x);
+    const TY* y = static_cast<const TY*>(P.y);
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {0.f, 0.f, 0.f, 0.f};
+    if (OP == COL_BN_BWD) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { mu[e] = P.mean[c + e]; is[e] = P.invstd[c + e]; }
+    }
+#pragma unroll 8
+    for (long long r = rb + rl; r < re; r += lanes) {
+        float xv[4];
+        ld4(x + r * P.ldx + c, xv);
+        if (OP == COL_SUM) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a0[e] += xv[e];
+        } else if (OP == COL_SUM_SQ) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { a0[e] += xv[e]; a1[e] = fmaf(xv[e], xv[e], a1[e]); }
+        } else if (OP == COL_BN_BWD) {
+            float dy[4];
+            ld4(y + r * P.ldy + c, dy);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { a0[e] += dy[e]; a1[e] = fmaf(dy[e], (xv[e] - mu[e]) * is[e], a1[e]); }
+        } else {
+            const float w = P.roww[r / P.roww_div];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a0[e] = fmaf(w, xv[e], a0[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        red[0][e][threadIdx.x] = a0[e];
+        if (NOUT == 2) red[1][e][threadIdx.x] = a1[e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NOUT * P.C; i += 256) {
+        const int k = i / P.C, cc = i - k * P.C, g = cc >> 2, e = cc & 3;
+        float sum = 0.f;
+        for (int j = 0; j < lanes; ++j) sum += red[k][e][j * cgs + g];
+        P.partial[((long long)blockIdx.y * NOUT + k) * P.C + cc] = sum;
+    }
+}
+
 // out[k*out_kstride + perm(c)] (+)= alpha * sum_chunks partial[chunk][k][c]   (float64 accumulation)
-// 32 outputs per CTA, 8 chunk lanes each, combined in a fixed order (deterministic)
+// 8 outputs per CTA, 32 chunk lanes each, combined in a fixed order (deterministic)
 static __global__ void __launch_bounds__(256) colreduce_finish_kernel(const float* __restrict__ partial, int nchunk, int nout,
                                                                int C, float* out, int out_kstride, int perm_q,
                                                                int perm_p, float alpha, int accumulate) {
-    __shared__ double red[8][33];
-    const int cx = threadIdx.x & 31, jl = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + cx;
+    __shared__ double red[32][9];
+    const int cx = threadIdx.x & 7, jl = threadIdx.x >> 3;
+    const int i = blockIdx.x * 8 + cx;
     double s = 0.0;
     if (i < nout * C)
-        for (int j = jl; j < nchunk; j += 8) s += (double)partial[(long long)j * nout * C + i];
+        for (int j = jl; j < nchunk; j += 32) s += (double)partial[(long long)j * nout * C + i];
     red[jl][cx] = s;
     __syncthreads();
     if (jl == 0 && i < nout * C) {
         double t = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t += red[j][cx];
+        for (int j = 0; j < 32; ++j) t += red[j][cx];
         const int k = i / C, c = i - k * C;
         float* o = out + (long long)k * out_kstride + perm_index(c, perm_q, perm_p);
         const float v = (float)(t * (double)alpha);

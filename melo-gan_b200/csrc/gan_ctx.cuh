@@ -217,7 +217,13 @@ int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const floa
     const long long rows = r1 - r0;
     if (rows <= 0 || C <= 0) return MG_OK;
     long long maxchunks = (long long)(c->partial_floats / ((size_t)NOUT * C));
-    {   // enough CTAs to fill the machine: (column groups) x (row chunks) ~ 4 per SM
+    const bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x) % (4 * sizeof(T)) == 0) &&
+                      (OP != COL_BN_BWD || ((ldy % 4 == 0) && (((uintptr_t)y) % (4 * sizeof(TY)) == 0)));
+    const bool flat = vec4 && C <= 1024 && ((C / 4) & (C / 4 - 1)) == 0;
+    if (flat) {
+        const long long want = (long long)num_sms() * 8;
+        if (maxchunks > want) maxchunks = want;
+    } else {   // enough CTAs to fill the machine: (column groups) x (row chunks) ~ 4 per SM
         long long want = (long long)num_sms() * 4 / ((C / 4 + 31) / 32 > 0 ? (C / 4 + 31) / 32 : 1);
         if (want < 16) want = 16;
         if (want > 256) want = 256;
@@ -232,9 +238,9 @@ int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const floa
     a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.mean = mean; a.invstd = invstd; a.roww = roww;
     a.roww_div = roww_div > 0 ? roww_div : 1; a.r0 = r0; a.r1 = r1; a.C = C; a.partial = c->partial;
     a.rows_per_chunk = (int)rpc;
-    const bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x) % (4 * sizeof(T)) == 0) &&
-                      (OP != COL_BN_BWD || ((ldy % 4 == 0) && (((uintptr_t)y) % (4 * sizeof(TY)) == 0)));
-    if (vec4) {
+    if (flat) {
+        colreduce_flat_kernel<T, TY, OP><<<dim3(1, nchunk), 256, 0, st>>>(a);
+    } else if (vec4) {
         dim3 grid((C / 4 + 31) / 32, nchunk);
         colreduce_vec4_kernel<T, TY, OP><<<grid, 256, 0, st>>>(a);
     } else {
@@ -243,7 +249,7 @@ int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const floa
     }
     MG_LAUNCH_OK();
     const int n = NOUT * C;
-    colreduce_finish_kernel<<<(n + 31) / 32, 256, 0, st>>>(c->partial, nchunk, NOUT, C, out, out_kstride, perm_q,
+    colreduce_finish_kernel<<<(n + 7) / 8, 256, 0, st>>>(c->partial, nchunk, NOUT, C, out, out_kstride, perm_q,
                                                              perm_p, alpha, accumulate);
     MG_LAUNCH_OK();
     return MG_OK;
