@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <stdlib.h>
+#include <cstdio>
 
 #include <type_traits>
 
@@ -176,6 +177,78 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {    
                                               *reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
 }
 
+// Column loop of the drain for one thread's row.  ACT/MUL/AFF/AUX are compile-time unless GEN (then read from P).
+template <int NC, int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool kPrefetchMask, int KMV, typename TO, typename TMSK>
+__device__ __forceinline__ void drain_cols(const TcTapArgs& P, uint32_t taddr, int c_begin, bool row_ok, TO* __restrict__ orow,
+                                           const TMSK* __restrict__ mrow, TO* __restrict__ xrow, const uint4 (&mreg)[KMV],
+                                           const float4* sc4, const float4* bi4) {
+    static_assert(NC % 32 == 0, "column range must be whole groups of 32");
+    const int act = GEN ? P.act : ACT, mul = GEN ? P.mul_mode : MUL;
+    const bool aff = GEN ? true : AFF, aux = GEN ? (P.aux != nullptr) : AUX, acc = GEN ? (P.accumulate != 0) : false;
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_begin + NC; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32_async(taddr + (uint32_t)c0, raw);
+        tmem_wait_ld();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g8 = 0; g8 < 32; g8 += 8) {          // 8 columns: one 16-byte (bf16) or two 16-byte (float) stores
+            float ms[8], old[8], x[8], gd[8];
+            if (mul != MUL_NONE) {
+                if (kPrefetchMask) {
+                    const uint4 mv = mreg[((c0 - c_begin + g8) >> 3) < KMV ? ((c0 - c_begin + g8) >> 3) : 0];
+                    const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        ms[2 * e] = __uint_as_float(w[e] << 16);
+                        ms[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 8; h += 4) {
+                        float t4[4];
+                        ld4(mrow + c0 + g8 + h, t4);
+                        ms[h] = t4[0]; ms[h + 1] = t4[1]; ms[h + 2] = t4[2]; ms[h + 3] = t4[3];
+                    }
+                }
+            }
+            if (acc) {
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                    float t4[4];
+                    ld4(orow + c0 + g8 + h, t4);
+                    old[h] = t4[0]; old[h + 1] = t4[1]; old[h + 2] = t4[2]; old[h + 3] = t4[3];
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+                float scv[4] = {1.f, 1.f, 1.f, 1.f}, biv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (aff) {
+                    const float4 sc = sc4[(c0 + g8 + h) >> 2], bi = bi4[(c0 + g8 + h) >> 2];
+                    scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+                    biv[0] = bi.x; biv[1] = bi.y; biv[2] = bi.z; biv[3] = bi.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y = __uint_as_float(raw[g8 + h + j]);
+                    if (aff) y = fmaf(y, scv[j], biv[j]);
+                    gd[h + j] = 0.0f;
+                    if (act == ACT_RELU) y = fmaxf(y, 0.0f);
+                    else if (act == ACT_LRELU) y = fmaxf(y, 0.2f * y);
+                    else if (act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[h + j]); y = yy; }
+                    if (mul == MUL_LRELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.2f);
+                    else if (mul == MUL_RELU_SIGN) y = ms[h + j] > 0.0f ? y : 0.0f;
+                    else if (mul == MUL_VALUE) y *= ms[h + j];
+                    if (acc) y += old[h + j];
+                    x[h + j] = y;
+                }
+            }
+            st8(orow + c0 + g8, x);
+            if (aux) st8(xrow + c0 + g8, gd);
+        }
+    }
+}
+
 // Drain one 128 x BN accumulator tile: TMEM -> registers -> bias/scale/activation/mask -> global.
 // `wait_bar`/`wait_parity`: the MMA->epilogue barrier of this accumulator.  The mask row is prefetched BEFORE the wait.
 // NC = number of accumulator columns this warp drains, starting at column c_begin (two epilogue warpgroups split a tile).
@@ -200,66 +273,32 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
         }
         mbar_wait(wait_bar, wait_parity);
         tc_fence_after();
-        static_assert(NC % 32 == 0, "column range must be whole groups of 32");
-        const float4* __restrict__ sc4 = reinterpret_cast<const float4*>(s_scale);
-        const float4* __restrict__ bi4 = reinterpret_cast<const float4*>(s_bias);
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_begin + NC; c0 += 32) {
-            uint32_t raw[32];
-            tmem_ld32_async(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-            tmem_wait_ld();
-            if (!row_ok) continue;
-#pragma unroll
-            for (int g8 = 0; g8 < 32; g8 += 8) {          // 8 columns: one 16-byte (bf16) or two 16-byte (float) stores
-                float ms[8], old[8], x[8], gd[8];
-                if (P.mul_mode != MUL_NONE) {
-                    if (kPrefetchMask) {
-                        const uint4 mv = mreg[(c0 - c_begin + g8) >> 3];
-                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            ms[2 * e] = __uint_as_float(w[e] << 16);
-                            ms[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-                        }
-                    } else {
-#pragma unroll
-                        for (int h = 0; h < 8; h += 4) {
-                            float t4[4];
-                            ld4(Mb + o + c0 + g8 + h, t4);
-                            ms[h] = t4[0]; ms[h + 1] = t4[1]; ms[h + 2] = t4[2]; ms[h + 3] = t4[3];
-                        }
-                    }
-                }
-                if (P.accumulate) {
-#pragma unroll
-                    for (int h = 0; h < 8; h += 4) {
-                        float t4[4];
-                        ld4(Ob + o + c0 + g8 + h, t4);
-                        old[h] = t4[0]; old[h + 1] = t4[1]; old[h + 2] = t4[2]; old[h + 3] = t4[3];
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                    const float4 sc = sc4[(c0 + g8 + h) >> 2], bi = bi4[(c0 + g8 + h) >> 2];
-                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float y = fmaf(__uint_as_float(raw[g8 + h + j]), scv[j], biv[j]);
-                        gd[h + j] = 0.0f;
-                        if (P.act == ACT_RELU) y = fmaxf(y, 0.0f);
-                        else if (P.act == ACT_LRELU) y = y > 0.0f ? y : 0.2f * y;
-                        else if (P.act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[h + j]); y = yy; }
-                        if (P.mul_mode == MUL_LRELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.2f);
-                        else if (P.mul_mode == MUL_RELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.0f);
-                        else if (P.mul_mode == MUL_VALUE) y *= ms[h + j];
-                        if (P.accumulate) y += old[h + j];
-                        x[h + j] = y;
-                    }
-                }
-                st8(Ob + o + c0 + g8, x);
-                if (P.aux) st8(Xb + o + c0 + g8, gd);
-            }
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+        const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+        // The drain is bound by instruction issue (a 128x128 tile is 16 K elements against as few as 4 MMAs), and a
+        // predicated-off instruction still costs its issue slot: pick a loop compiled for exactly this epilogue.
+        const bool affine = P.bias != nullptr || P.col_scale != nullptr || P.alpha != 1.0f;
+        int variant = 0;                                  // generic
+        if (!P.accumulate) {
+            if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = 1 + P.act;              // 1,2,3
+            else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
+            else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;  // 5,6,7
         }
+#define MG_DRAIN(ACT_, MUL_, AFF_, AUX_, GEN_)                                                                        \
+    drain_cols<NC, ACT_, MUL_, AFF_, AUX_, GEN_, kPrefetchMask, kMaskVecs, TO, TMSK>(P, taddr, c_begin, row_ok, Ob + o, \
+                                                                                    Mb + o, Xb + o, mreg, sc4, bi4)
+        switch (variant) {
+            case 1: MG_DRAIN(ACT_NONE, MUL_NONE, true, false, false); break;
+            case 2: MG_DRAIN(ACT_RELU, MUL_NONE, true, false, false); break;
+            case 3: MG_DRAIN(ACT_LRELU, MUL_NONE, true, false, false); break;
+            case 4: MG_DRAIN(ACT_GELU, MUL_NONE, true, true, false); break;
+            case 5: MG_DRAIN(ACT_NONE, MUL_LRELU_SIGN, false, false, false); break;
+            case 6: MG_DRAIN(ACT_NONE, MUL_RELU_SIGN, false, false, false); break;
+            case 7: MG_DRAIN(ACT_NONE, MUL_VALUE, false, false, false); break;
+            default: MG_DRAIN(ACT_NONE, MUL_NONE, true, true, true); break;
+        }
+#undef MG_DRAIN
 }
 
 template <int BN>
@@ -755,7 +794,13 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ctas_x > mtiles) ctas_x = mtiles;
     if (!am_halo) build_tap_groups(a, 0);
     const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
-    if (ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x) {
+    static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
+    const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x;
+    if (trace)
+        fprintf(stderr, "[tc_tap] rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%zu ws=%d stages=%d act=%d mul=%d aux=%d\n",
+                rows, a.N, K, a.ntaps, a.ngroups, a.halo, BN, sizeof(TO), (int)ws, ws ? (int)((avail - wbytes) / a_stage) : 3, a.act,
+                a.mul_mode, a.aux != nullptr);
+    if (ws) {
         int nstages = (int)((avail - wbytes) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * a_stage;
