@@ -61,6 +61,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && spins > (1u << 26)) asm volatile("trap;");   // a protocol bug must not hang the GPU
     }
 }
+// exactly one lane of a converged warp gets true; unlike `lane == 0` the compiler keeps the surrounding values in the
+// uniform datapath, which tcgen05.mma / tcgen05.commit operands need (otherwise every issue is wrapped in a vote loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -407,6 +418,8 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
 // TMA-loaded into shared memory once (<= 192 KB), the CTA then walks M tiles (grid-strided), streaming only activation
 // tiles through a small ring, with two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 constexpr int kWsMaxStages = 8;
+constexpr int kWsMaxLoads = 80;      // taps x k-blocks per tile
+constexpr int kWsHeaderBytes = 4096;
 // TMA warp, MMA warp, then BN / 32 epilogue warpgroups of 4 warps; each warpgroup drains 32 accumulator columns.  The
 // drain is a chain of dependent latencies (tcgen05.ld -> math -> store), so it is hidden by warps, not by ILP.
 template <int BN> struct WsCfg { static constexpr int kGroups = BN / 32, kEpiThreads = kGroups * 128, kThreads = 64 + kEpiThreads; };
@@ -415,6 +428,11 @@ struct WsHeader {
     uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     alignas(16) float bias[BN], scale[BN];
+    // per-tile schedules, built once per CTA so that the single-thread producer / MMA loops carry no index arithmetic:
+    // ldtab[j]  = (k coordinate, plane, row shift, -) of activation load j;  mmatab[i] = (byte offset of the tap's first row
+    // inside the stage, byte offset of its weight block, 1 if last MMA block of its stage, -)
+    alignas(16) int4 ldtab[kWsMaxLoads];
+    alignas(16) int4 mmatab[kWsMaxLoads];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -429,7 +447,8 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     WsHeader<BN>& H = *reinterpret_cast<WsHeader<BN>*>(base);
     const int nkb = P.ntaps * P.kblocks;
-    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(base + 2048);                       // [nkb][BN][64]
+    static_assert(sizeof(WsHeader<BN>) <= kWsHeaderBytes, "header does not fit its reservation");
+    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(base + kWsHeaderBytes);             // [nkb][BN][64]
     unsigned char* asm_ = reinterpret_cast<unsigned char*>(wsm + (size_t)nkb * BN * kTileK);  // [nstages][128 + halo][64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -447,6 +466,19 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     }
     if (warp == 1) tmem_alloc(&H.tmem_base, kTmemCols);
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&a_map); tma_prefetch_desc(&b_map); }
+    const int npt = P.ngroups * P.kblocks;            // activation loads (= stages consumed) per tile
+    if (threadIdx.x == 64) {
+        int i = 0;
+        for (int g = 0; g < P.ngroups; ++g)
+            for (int kc = 0; kc < P.kblocks; ++kc) {
+                H.ldtab[g * P.kblocks + kc] = make_int4(kc * kTileK, P.g_p[g], P.g_dmin[g], 0);
+                for (int j = 0; j < P.g_count[g]; ++j, ++i) {
+                    const int t = P.g_tap[P.g_first[g] + j];
+                    H.mmatab[i] = make_int4((P.a_dm[t] - P.g_dmin[g]) * 128, (t * P.kblocks + kc) * (int)kWBytes,
+                                            j == P.g_count[g] - 1, 0);
+                }
+            }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -464,52 +496,57 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                 const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
                 tma_load_2d(&b_map, &H.wfull, wsm + (size_t)kb * BN * kTileK, kc * kTileK, P.b_row[t] + n0);
             }
-            int it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
                 int b0, m0;
                 tile_coords(tile, b0, m0);
-                for (int g = 0; g < P.ngroups; ++g)
-                    for (int kc = 0; kc < P.kblocks; ++kc, ++it) {
-                        const int s = it % nstages, ph = (it / nstages) & 1;
-                        mbar_wait(&H.empty[s], ph ^ 1);
-                        mbar_expect_tx(&H.full[s], a_tx);
-                        tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, kc * kTileK, P.g_p[g], m0 + P.g_dmin[g], b0);
-                    }
+                for (int j = 0; j < npt; ++j) {
+                    mbar_wait(&H.empty[s], ph ^ 1);
+                    const int4 L = H.ldtab[j];
+                    mbar_expect_tx(&H.full[s], a_tx);
+                    tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, L.x, L.y, m0 + L.z, b0);
+                    if (++s == nstages) { s = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(BN, 0, 0);
         mbar_wait(&H.wfull, 0);
-        int it = 0, tcount = 0;
+        int s = 0, tcount = 0;
+        uint32_t ph = 0;
+        const uint64_t dbase = make_smem_desc(0, 16, 1024);
+        const uint32_t a_base = smem_u32(asm_), w_base = smem_u32(wsm);
         for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
             const int acc = tcount & 1;
             mbar_wait(&H.tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem0 + (uint32_t)(acc * BN);
             uint32_t started = 0;
-            for (int g = 0; g < P.ngroups; ++g)
-                for (int kc = 0; kc < P.kblocks; ++kc, ++it) {
-                    const int s = it % nstages, ph = (it / nstages) & 1;
-                    mbar_wait(&H.full[s], ph);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t stage_addr = smem_u32(asm_ + (size_t)s * a_stage);
-                        for (int j = 0; j < P.g_count[g]; ++j) {
-                            const int t = P.g_tap[P.g_first[g] + j];
-                            const uint32_t a_addr = stage_addr + (uint32_t)(P.a_dm[t] - P.g_dmin[g]) * 128u;
-                            const uint32_t b_addr = smem_u32(wsm + (size_t)(t * P.kblocks + kc) * BN * kTileK);
+            int i = 0;
+            for (int j = 0; j < npt; ++j) {
+                mbar_wait(&H.full[s], ph);
+                tc_fence_after();
+                const uint32_t stage_addr = a_base + (uint32_t)s * a_stage;
+                int last;
+                do {                                           // warp-uniform: every lane walks the schedule
+                    const int4 M = H.mmatab[i++];
+                    const uint64_t ad = dbase | (uint64_t)(((stage_addr + (uint32_t)M.x) >> 4) & 0x3FFF);
+                    const uint64_t bd = dbase | (uint64_t)(((w_base + (uint32_t)M.y) >> 4) & 0x3FFF);
+                    if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < kTileK / 16; ++k) {
-                                umma_f16(tacc, make_smem_desc(a_addr + k * 32, 16, 1024),
-                                         make_smem_desc(b_addr + k * 32, 16, 1024), idesc, started);
-                                started = 1;
-                            }
-                        }
-                        umma_commit(&H.empty[s]);
-                        if (g == P.ngroups - 1 && kc == P.kblocks - 1) umma_commit(&H.tmem_full[acc]);
+                        for (int k = 0; k < kTileK / 16; ++k) umma_f16(tacc, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : started);
                     }
-                    __syncwarp();
+                    started = 1;
+                    last = M.z;
+                } while (!last);
+                if (elect_one()) {
+                    umma_commit(&H.empty[s]);
+                    if (j == npt - 1) umma_commit(&H.tmem_full[acc]);
                 }
+                __syncwarp();
+                if (++s == nstages) { s = 0; ph ^= 1; }
+            }
         }
     } else {
         const int et = threadIdx.x - 64;                 // 0..255
@@ -788,14 +825,14 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * a.N * a.ntaps * K, (double)rows * (K * 2.0 + a.N * sizeof(TO)), st);
     const int nslabs = a.N / BN;
     const size_t wbytes = (size_t)a.ntaps * (K / 64) * BN * 128;
-    const size_t avail = (size_t)227 * 1024 - 1024 - 2048;
+    const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes;
     int ctas_x = num_sms() / nslabs;
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
     if (!am_halo) build_tap_groups(a, 0);
     const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
-    const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x;
+    const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x && a.ntaps * (K / 64) <= kWsMaxLoads;
     if (trace)
         fprintf(stderr, "[tc_tap] rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%zu ws=%d stages=%d act=%d mul=%d aux=%d\n",
                 rows, a.N, K, a.ntaps, a.ngroups, a.halo, BN, sizeof(TO), (int)ws, ws ? (int)((avail - wbytes) / a_stage) : 3, a.act,
@@ -803,7 +840,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ws) {
         int nstages = (int)((avail - wbytes) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
-        const size_t smem = 1024 + 2048 + wbytes + (size_t)nstages * a_stage;
+        const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, a, mtiles, nstages, ctas_x, smem, st)
                            : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, a, mtiles, nstages, ctas_x, smem, st);
@@ -862,7 +899,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     CUtensorMap am, bm;
     int BN = (P.N % 128 == 0) ? 128 : 64;
     if (BN == 128) {   // a 128-wide slab whose taps do not fit in shared memory: take 64-wide slabs if THOSE can stay resident
-        const size_t avail = (size_t)227 * 1024 - 1024 - 2048 - 4 * 16384;
+        const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes - 4 * 16384;
         const size_t w128 = (size_t)P.ntaps * (P.K / 64) * 128 * 128;
         const long long mt = ((long long)P.B * P.Mper + 127) / 128;
         static const bool narrow = getenv("MELOGAN_WS_NARROW") != nullptr;   // measured slower on B200 (A re-read 4x): off
