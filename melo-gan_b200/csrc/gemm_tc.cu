@@ -53,6 +53,26 @@ bool ws_enabled() {
     }
     return v == 1;
 }
+bool tma_store_enabled() {
+    static const bool on = getenv("MELOGAN_DISABLE_TMA_STORE") == nullptr;
+    return on;
+}
+int make_out_map(CUtensorMap* map, const void* base, int elem_bytes, long long cols, long long rows, long long row_stride) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)row_stride * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(out cols=%lld rows=%lld stride=%lld) failed: %d", cols, rows, row_stride, (int)r);
+        return MG_ERR_CUDA;
+    }
+    return MG_OK;
+}
 bool reuse_enabled() {
     static const bool on = getenv("MELOGAN_DISABLE_TAP_REUSE") == nullptr;
     return on;

@@ -47,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok = 0;
@@ -90,6 +93,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -175,6 +186,8 @@ struct TcTapArgs {
     const float* bias; const float* col_scale; int act;
     const void* mul_src; int mul_mode; void* aux;
     float alpha; int accumulate;
+    int tma_store;                      // weight-stationary kernel: tiles leave through shared memory + TMA bulk stores
+    int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
 
 __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
@@ -270,7 +283,7 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;             // tile row
         const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
-        const bool row_ok = bb < P.B;
+        const bool row_ok = bb < P.B && !(P.dbg & 1);
         TO* __restrict__ Ob = static_cast<TO*>(P.Out);
         const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
         TO* __restrict__ Xb = static_cast<TO*>(P.aux);
@@ -310,6 +323,164 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
             default: MG_DRAIN(ACT_NONE, MUL_NONE, true, true, true); break;
         }
 #undef MG_DRAIN
+}
+
+// ---- drain through shared memory + TMA store (weight-stationary kernel) ----
+// Row-per-thread global stores hand L2 thirty-two half-sector writes per instruction; measured on the whole training
+// cycle they cost 11 of 37 ms.  Here every epilogue thread writes its 32 columns into a 128B-swizzled staging tile
+// (conflict-free: 8 consecutive rows hit 8 different 16-byte pieces) and ONE thread issues cp.async.bulk.tensor stores:
+// full 128-byte lines, no LSU work, asynchronous to the next tile's drain.
+template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TMSK>
+__device__ __forceinline__ void epi_math32(const TcTapArgs& P, const uint32_t (&raw)[32], const uint4 (&mreg)[4],
+                                           const TMSK* __restrict__ mrow, bool row_ok, const float4* sc4, const float4* bi4,
+                                           int c0, float (&x)[32], uint4 (&gpk)[4]) {
+    const int act = GEN ? P.act : ACT, mul = GEN ? P.mul_mode : MUL;
+    const bool aff = GEN ? true : AFF, aux = GEN ? (P.aux != nullptr) : AUX;
+#pragma unroll
+    for (int g8 = 0; g8 < 32; g8 += 8) {
+        float ms[8], gd[8];
+        if (mul != MUL_NONE) {
+            if (sizeof(TMSK) == 2) {
+                const uint4 mv = mreg[g8 >> 3];
+                const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ms[2 * e] = __uint_as_float(w[e] << 16);
+                    ms[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                    float t4[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (row_ok) ld4(mrow + c0 + g8 + h, t4);
+                    ms[h] = t4[0]; ms[h + 1] = t4[1]; ms[h + 2] = t4[2]; ms[h + 3] = t4[3];
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+            float scv[4] = {1.f, 1.f, 1.f, 1.f}, biv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (aff) {
+                const float4 sc = sc4[(c0 + g8 + h) >> 2], bi = bi4[(c0 + g8 + h) >> 2];
+                scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+                biv[0] = bi.x; biv[1] = bi.y; biv[2] = bi.z; biv[3] = bi.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y = __uint_as_float(raw[g8 + h + j]);
+                if (aff) y = fmaf(y, scv[j], biv[j]);
+                gd[h + j] = 0.0f;
+                if (act == ACT_RELU) y = fmaxf(y, 0.0f);
+                else if (act == ACT_LRELU) y = fmaxf(y, 0.2f * y);
+                else if (act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[h + j]); y = yy; }
+                if (mul == MUL_LRELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.2f);
+                else if (mul == MUL_RELU_SIGN) y = ms[h + j] > 0.0f ? y : 0.0f;
+                else if (mul == MUL_VALUE) y *= ms[h + j];
+                x[g8 + h + j] = y;
+            }
+        }
+        if (aux) {      // derivative tile, kept packed as bf16 until the staging buffer is free again (bf16 outputs only)
+            __nv_bfloat162 a = __floats2bfloat162_rn(gd[0], gd[1]), b = __floats2bfloat162_rn(gd[2], gd[3]);
+            __nv_bfloat162 c = __floats2bfloat162_rn(gd[4], gd[5]), d = __floats2bfloat162_rn(gd[6], gd[7]);
+            gpk[g8 >> 3] = make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b),
+                                      *reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
+        }
+    }
+}
+
+// staging tile: boxes of [128 rows][128 bytes], piece p of row r at (p ^ (r & 7)) * 16
+__device__ __forceinline__ void stage_row32(unsigned char* staging, int r, int col, const float (&x)[32], __nv_bfloat16) {
+#pragma unroll
+    for (int g8 = 0; g8 < 32; g8 += 8) {
+        const int cc = col + g8, box = cc >> 6, pidx = (cc & 63) >> 3;
+        __nv_bfloat162 a = __floats2bfloat162_rn(x[g8], x[g8 + 1]), b = __floats2bfloat162_rn(x[g8 + 2], x[g8 + 3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(x[g8 + 4], x[g8 + 5]), d = __floats2bfloat162_rn(x[g8 + 6], x[g8 + 7]);
+        *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) =
+            make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b), *reinterpret_cast<unsigned*>(&c),
+                       *reinterpret_cast<unsigned*>(&d));
+    }
+}
+__device__ __forceinline__ void stage_row32(unsigned char* staging, int r, int col, const float (&x)[32], float) {
+#pragma unroll
+    for (int g4 = 0; g4 < 32; g4 += 4) {
+        const int cc = col + g4, box = cc >> 5, pidx = (cc & 31) >> 2;
+        *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) =
+            make_uint4(__float_as_uint(x[g4]), __float_as_uint(x[g4 + 1]), __float_as_uint(x[g4 + 2]), __float_as_uint(x[g4 + 3]));
+    }
+}
+
+template <int BN, int kEpi, typename TO, typename TMSK>
+__device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
+                                               const float* s_bias, const float* s_scale, uint32_t tmem_acc, int b0, int m0,
+                                               int n0, int warp, int lane, int et, uint64_t* full_bar, uint32_t parity,
+                                               uint64_t* empty_bar, int c_begin, unsigned char* staging) {
+    constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
+    const int q = warp & 3, r = q * 32 + lane;
+    const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
+    const bool row_ok = bb < P.B;
+    const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
+    const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
+    uint4 mreg[4] = {};
+    if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o + c_begin) + i);
+    }
+    mbar_wait(full_bar, parity);
+    tc_fence_after();
+    uint32_t raw[32];
+    tmem_ld32_async(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin, raw);
+    tmem_wait_ld();
+    tc_fence_before();
+    if (et == 0) bulk_wait_read0();                              // the previous tile's stores have left the staging tile
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");      // every thread holds its accumulator row: TMEM is free
+    if (et == 0) mbar_arrive(empty_bar);
+    const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+    const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
+    const bool affine = P.bias != nullptr || P.col_scale != nullptr || P.alpha != 1.0f;
+    int variant = 0;
+    if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = 1 + P.act;
+    else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
+    else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
+    float x[32];
+    uint4 gpk[4] = {};
+#define MG_MATH(ACT_, MUL_, AFF_, AUX_, GEN_) \
+    epi_math32<ACT_, MUL_, AFF_, AUX_, GEN_, TMSK>(P, raw, mreg, Mb + o, row_ok, sc4, bi4, c_begin, x, gpk)
+    switch (variant) {
+        case 1: MG_MATH(ACT_NONE, MUL_NONE, true, false, false); break;
+        case 2: MG_MATH(ACT_RELU, MUL_NONE, true, false, false); break;
+        case 3: MG_MATH(ACT_LRELU, MUL_NONE, true, false, false); break;
+        case 4: MG_MATH(ACT_GELU, MUL_NONE, true, true, false); break;
+        case 5: MG_MATH(ACT_NONE, MUL_LRELU_SIGN, false, false, false); break;
+        case 6: MG_MATH(ACT_NONE, MUL_RELU_SIGN, false, false, false); break;
+        case 7: MG_MATH(ACT_NONE, MUL_VALUE, false, false, false); break;
+        default: MG_MATH(ACT_NONE, MUL_NONE, true, true, true); break;
+    }
+#undef MG_MATH
+    stage_row32(staging, r, c_begin, x, TO());
+    fence_proxy_async();
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+    const int row0 = b0 * P.Mper + m0;
+    if (et == 0 && !(P.dbg & 1)) {
+#pragma unroll
+        for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, staging + bx * 16384, n0 + bx * EPB, row0);
+        bulk_commit();
+    }
+    if (P.aux) {                                                 // second tile (activation derivative), bf16 only
+        if (et == 0) bulk_wait_read0();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+#pragma unroll
+        for (int g8 = 0; g8 < 32; g8 += 8) {
+            const int cc = c_begin + g8, box = cc >> 6, pidx = (cc & 63) >> 3;
+            *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) = gpk[g8 >> 3];
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+        if (et == 0) {
+#pragma unroll
+            for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, staging + bx * 16384, n0 + bx * EPB, row0);
+            bulk_commit();
+        }
+    }
 }
 
 template <int BN>
@@ -435,13 +606,11 @@ struct WsHeader {
     alignas(16) int4 mmatab[kWsMaxLoads];
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int BN, typename TO, typename TMSK>
 __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(const __grid_constant__ CUtensorMap a_map,
-                                                            const __grid_constant__ CUtensorMap b_map, const TcTapArgs P,
+                                                            const __grid_constant__ CUtensorMap b_map,
+                                                            const __grid_constant__ CUtensorMap o_map,
+                                                            const __grid_constant__ CUtensorMap x_map, const TcTapArgs P,
                                                             int mtiles, int nstages) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
@@ -455,6 +624,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     constexpr uint32_t kWBytes = BN * kTileK * 2;
     const uint32_t a_tx = (uint32_t)(kTileM + P.halo) * kTileK * 2;                           // bytes one A box delivers
     const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
+    unsigned char* staging = asm_ + (size_t)nstages * a_stage;                                 // [BN*sizeof(TO)/128][128][128 B]
     const int n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
@@ -504,8 +674,11 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                 for (int j = 0; j < npt; ++j) {
                     mbar_wait(&H.empty[s], ph ^ 1);
                     const int4 L = H.ldtab[j];
-                    mbar_expect_tx(&H.full[s], a_tx);
-                    tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, L.x, L.y, m0 + L.z, b0);
+                    if (P.dbg & 4) { mbar_expect_tx(&H.full[s], 0); }
+                    else {
+                        mbar_expect_tx(&H.full[s], a_tx);
+                        tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, L.x, L.y, m0 + L.z, b0);
+                    }
                     if (++s == nstages) { s = 0; ph ^= 1; }
                 }
             }
@@ -533,7 +706,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                     const int4 M = H.mmatab[i++];
                     const uint64_t ad = dbase | (uint64_t)(((stage_addr + (uint32_t)M.x) >> 4) & 0x3FFF);
                     const uint64_t bd = dbase | (uint64_t)(((w_base + (uint32_t)M.y) >> 4) & 0x3FFF);
-                    if (elect_one()) {
+                    if (!(P.dbg & 2) && elect_one()) {
 #pragma unroll
                         for (int k = 0; k < kTileK / 16; ++k) umma_f16(tacc, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : started);
                     }
@@ -562,12 +735,19 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             const int acc = tcount & 1;
             int b0, m0;
             tile_coords(tile, b0, m0);
+            if (P.tma_store) {
+                drain_tile_tma<BN, kEpi, TO, TMSK>(P, &o_map, &x_map, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0,
+                                                   warp, lane, et, &H.tmem_full[acc], (tcount >> 1) & 1, &H.tmem_empty[acc],
+                                                   grp * 32, staging);
+                continue;
+            }
             drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
                                          &H.tmem_full[acc], (tcount >> 1) & 1, grp * 32);
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");   // every epilogue thread has read its TMEM lanes
             if (et == 0) mbar_arrive(&H.tmem_empty[acc]);
         }
+        if (P.tma_store && et == 0) bulk_wait0();             // all bulk stores complete before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -737,6 +917,9 @@ int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, 
 int make_view_map(CUtensorMap* map, const void* base, long long inner, long long planes, long long plane_stride,
                   long long rows, long long row_stride, long long samples, long long sample_stride, int box_rows,
                   int box_samples);
+// 2-D view (column, flat row) of an output tensor whose rows are row_stride elements apart; boxes of 128 bytes x 128 rows
+int make_out_map(CUtensorMap* map, const void* base, int elem_bytes, long long cols, long long rows, long long row_stride);
+bool tma_store_enabled();    // MELOGAN_DISABLE_TMA_STORE=1 keeps the row-per-thread epilogue stores (A/B profiling)
 // 2-D view (k, rows) of a packed weight [rows][K]
 int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows);
 
@@ -755,8 +938,8 @@ int launch_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs&
 }
 
 template <int BN, typename TO, typename TMSK>
-int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a, int mtiles, int nstages,
-                     int ctas_x, size_t smem, cudaStream_t st) {
+int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const CUtensorMap& om, const CUtensorMap& xm,
+                     const TcTapArgs& a, int mtiles, int nstages, int ctas_x, size_t smem, cudaStream_t st) {
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_ws_kernel<BN, TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -764,7 +947,7 @@ int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const TcTapAr
         attr_smem = 227 * 1024;
     }
     dim3 grid(ctas_x, a.N / BN);
-    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, a, mtiles, nstages);
+    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, om, xm, a, mtiles, nstages);
     MG_LAUNCH_OK();
     return MG_OK;
 }
@@ -830,6 +1013,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
     if (!am_halo) build_tap_groups(a, 0);
+    { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = dbg; }
     const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
     const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x && a.ntaps * (K / 64) <= kWsMaxLoads;
@@ -838,12 +1022,29 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
                 rows, a.N, K, a.ntaps, a.ngroups, a.halo, BN, sizeof(TO), (int)ws, ws ? (int)((avail - wbytes) / a_stage) : 3, a.act,
                 a.mul_mode, a.aux != nullptr);
     if (ws) {
-        int nstages = (int)((avail - wbytes) / a_stage);
+        // tiles leave through a staging tile + TMA bulk stores when the output rows are uniformly strided and the staging
+        // tile fits next to >= 3 activation stages
+        const size_t staging = (size_t)128 * BN * sizeof(TO);
+        CUtensorMap om = am, xm = am;
+        a.tma_store = 0;
+        if (tma_store_enabled() && !a.accumulate && a.o_bstride == (long long)a.Mper * a.o_mstride &&
+            wbytes + 3 * a_stage + staging <= avail && (a.o_mstride * sizeof(TO)) % 16 == 0 &&
+            ((uintptr_t)((TO*)a.Out + a.o_off)) % 16 == 0 && (!a.aux || sizeof(TO) == 2)) {
+            int rc = make_out_map(&om, (TO*)a.Out + a.o_off, (int)sizeof(TO), a.N, rows, a.o_mstride);
+            if (rc != MG_OK) return rc;
+            if (a.aux) {
+                rc = make_out_map(&xm, (TO*)a.aux + a.o_off, (int)sizeof(TO), a.N, rows, a.o_mstride);
+                if (rc != MG_OK) return rc;
+            }
+            a.tma_store = 1;
+        }
+        const size_t extra = a.tma_store ? staging : 0;
+        int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
-        const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage;
+        const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage + extra;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
-        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, a, mtiles, nstages, ctas_x, smem, st)
-                           : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, a, mtiles, nstages, ctas_x, smem, st);
+        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, om, xm, a, mtiles, nstages, ctas_x, smem, st)
+                           : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, om, xm, a, mtiles, nstages, ctas_x, smem, st);
     }
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
 }
