@@ -236,7 +236,26 @@ static __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __r
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((stride * 4) % C == 0) {      // this thread's 4 channels never change: fold the statistics once
+        const int c = (int)((i0 * 4) % C);
+        float sc[4], sh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sc[e] = invstd[c + e] * gamma[c + e];
+            sh[e] = fmaf(-mean[c + e], sc[e], beta[c + e]);
+        }
+#pragma unroll 4
+        for (long long i = i0; i < n4; i += stride) {
+            float v[4];
+            ld4(x + i * 4, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.0f);
+            st4(y + i * 4, v);
+        }
+        return;
+    }
+    for (long long i = i0; i < n4; i += stride) {
         const int c = (int)((i * 4) % C);
         float v[4];
         ld4(x + i * 4, v);
@@ -343,6 +362,25 @@ static __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __
     const T* r0 = ref + (long long)s * L * C;
     TOUT* o0 = out + (long long)s * L * C;
     const TS* sp = src + (long long)s * C;
+    if ((gridDim.x * 1024) % C == 0) {      // this thread's 4 channels never change: fold the row factor once
+        const int c = ((blockIdx.x * 256 + threadIdx.x) * 4) % C;
+        float f[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = ld_as_float(sp + c + e) * (scale * (colscale ? colscale[c + e] : 1.0f));
+#pragma unroll 4
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+            float r[4], o[4];
+            ld4(r0 + i * 4, r);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = (mode == MUL_LRELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.2f)
+                                : (mode == MUL_RELU_SIGN) ? (r[e] > 0.f ? 1.f : 0.f) : r[e];
+                o[e] = f[e] * d;
+            }
+            st4(o0 + i * 4, o);
+        }
+        return;
+    }
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
         const int c = (i * 4) % C;
         float r[4], o[4];

@@ -1103,7 +1103,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
         const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes - 4 * 16384;
         const size_t w128 = (size_t)P.ntaps * (P.K / 64) * 128 * 128;
         const long long mt = ((long long)P.B * P.Mper + 127) / 128;
-        static const bool narrow = getenv("MELOGAN_WS_NARROW") != nullptr;   // measured slower on B200 (A re-read 4x): off
+        static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;   // A is re-read 4x but no weight traffic: -0.6 ms/cycle
         if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64))) BN = 64;
     }
     int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt);
