@@ -291,7 +291,7 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
         constexpr bool kPrefetchMask = sizeof(TMSK) == 2;
         constexpr int kMaskVecs = kPrefetchMask ? NC / 8 : 1;
         uint4 mreg[kMaskVecs];
-        if (kPrefetchMask && P.mul_mode != MUL_NONE && row_ok) {
+        if (kPrefetchMask && P.mul_mode != MUL_NONE && row_ok && !(P.dbg & 8)) {
 #pragma unroll
             for (int i = 0; i < kMaskVecs; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o + c_begin) + i);
         }
@@ -421,7 +421,7 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
     const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
     const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
     uint4 mreg[4] = {};
-    if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok) {
+    if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok && !(P.dbg & 8)) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o + c_begin) + i);
     }
@@ -1099,11 +1099,12 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
 
     CUtensorMap am, bm;
     int BN = (P.N % 128 == 0) ? 128 : 64;
-    if (BN == 128) {   // a 128-wide slab whose taps do not fit in shared memory: take 64-wide slabs if THOSE can stay resident
-        const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes - 4 * 16384;
+    if (BN == 128) {   // a 128-wide slab whose taps cannot stay resident next to 3 activation stages: take 64-wide slabs if
+                       // THOSE can (the activation is then read once per slab, but no weight tile is ever re-fetched)
+        const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes - 3 * 17408;
         const size_t w128 = (size_t)P.ntaps * (P.K / 64) * 128 * 128;
         const long long mt = ((long long)P.B * P.Mper + 127) / 128;
-        static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;   // A is re-read 4x but no weight traffic: -0.6 ms/cycle
+        static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;
         if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64))) BN = 64;
     }
     int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt);
