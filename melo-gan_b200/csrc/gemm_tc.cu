@@ -53,6 +53,10 @@ bool ws_enabled() {
     }
     return v == 1;
 }
+bool mask_tma_enabled() {
+    static const bool on = getenv("MELOGAN_DISABLE_TMA_MASK") == nullptr;
+    return on;
+}
 bool tma_store_enabled() {
     static const bool on = getenv("MELOGAN_DISABLE_TMA_STORE") == nullptr;
     return on;

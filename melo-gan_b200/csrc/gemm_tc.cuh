@@ -186,6 +186,7 @@ struct TcTapArgs {
     const float* bias; const float* col_scale; int act;
     const void* mul_src; int mul_mode; void* aux;
     float alpha; int accumulate;
+    int tma_mask;                       // ... and the mask tile (f' of the saved activation) arrives by TMA as well
     int tma_store;                      // weight-stationary kernel: tiles leave through shared memory + TMA bulk stores
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
@@ -411,9 +412,11 @@ __device__ __forceinline__ void stage_row32(unsigned char* staging, int r, int c
 
 template <int BN, int kEpi, typename TO, typename TMSK>
 __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
-                                               const float* s_bias, const float* s_scale, uint32_t tmem_acc, int b0, int m0,
-                                               int n0, int warp, int lane, int et, uint64_t* full_bar, uint32_t parity,
-                                               uint64_t* empty_bar, int c_begin, unsigned char* staging) {
+                                               const CUtensorMap* m_map, const float* s_bias, const float* s_scale,
+                                               uint32_t tmem_acc, int b0, int m0, int n0, int warp, int lane, int et,
+                                               uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int c_begin,
+                                               unsigned char* staging, unsigned char* maskbuf, uint64_t* mask_bar,
+                                               uint32_t mask_parity, int next_row0) {
     constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
     const int q = warp & 3, r = q * 32 + lane;
     const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
@@ -421,7 +424,7 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
     const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
     const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
     uint4 mreg[4] = {};
-    if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok && !(P.dbg & 8)) {
+    if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok && !(P.dbg & 8) && !P.tma_mask) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o + c_begin) + i);
     }
@@ -434,6 +437,13 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
     if (et == 0) bulk_wait_read0();                              // the previous tile's stores have left the staging tile
     asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");      // every thread holds its accumulator row: TMEM is free
     if (et == 0) mbar_arrive(empty_bar);
+    if (P.tma_mask) {                                            // this thread's 64 mask bytes from the TMA-loaded tile
+        mbar_wait(mask_bar, mask_parity);
+        const int box = c_begin >> 6, p0 = (c_begin & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            mreg[i] = *reinterpret_cast<const uint4*>(maskbuf + box * 16384 + r * 128 + (((p0 + i) ^ (r & 7)) << 4));
+    }
     const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
     const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
     const bool affine = P.bias != nullptr || P.col_scale != nullptr || P.alpha != 1.0f;
@@ -464,6 +474,11 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
 #pragma unroll
         for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, staging + bx * 16384, n0 + bx * EPB, row0);
         bulk_commit();
+    }
+    if (P.tma_mask && et == 0 && next_row0 >= 0) {               // every thread has read this tile's mask: fetch the next
+        mbar_expect_tx(mask_bar, (uint32_t)(BN / 64) * 16384u);
+#pragma unroll
+        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, mask_bar, maskbuf + bx * 16384, n0 + bx * 64, next_row0);
     }
     if (P.aux) {                                                 // second tile (activation derivative), bf16 only
         if (et == 0) bulk_wait_read0();
@@ -596,7 +611,7 @@ constexpr int kWsHeaderBytes = 4096;
 template <int BN> struct WsCfg { static constexpr int kGroups = BN / 32, kEpiThreads = kGroups * 128, kThreads = 64 + kEpiThreads; };
 template <int BN>
 struct WsHeader {
-    uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2];
+    uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2], mask_full;
     uint32_t tmem_base;
     alignas(16) float bias[BN], scale[BN];
     // per-tile schedules, built once per CTA so that the single-thread producer / MMA loops carry no index arithmetic:
@@ -610,7 +625,8 @@ template <int BN, typename TO, typename TMSK>
 __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(const __grid_constant__ CUtensorMap a_map,
                                                             const __grid_constant__ CUtensorMap b_map,
                                                             const __grid_constant__ CUtensorMap o_map,
-                                                            const __grid_constant__ CUtensorMap x_map, const TcTapArgs P,
+                                                            const __grid_constant__ CUtensorMap x_map,
+                                                            const __grid_constant__ CUtensorMap m_map, const TcTapArgs P,
                                                             int mtiles, int nstages) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
@@ -625,12 +641,14 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     const uint32_t a_tx = (uint32_t)(kTileM + P.halo) * kTileK * 2;                           // bytes one A box delivers
     const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
     unsigned char* staging = asm_ + (size_t)nstages * a_stage;                                 // [BN*sizeof(TO)/128][128][128 B]
+    unsigned char* maskbuf = staging + (size_t)128 * BN * sizeof(TO);                          // [BN/64][128][128 B] (bf16 masks)
     const int n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstages; ++s) { mbar_init(&H.full[s], 1); mbar_init(&H.empty[s], 1); }
         mbar_init(&H.wfull, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(&H.tmem_full[a], 1); mbar_init(&H.tmem_empty[a], 1); }
+        mbar_init(&H.mask_full, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -736,9 +754,22 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             int b0, m0;
             tile_coords(tile, b0, m0);
             if (P.tma_store) {
-                drain_tile_tma<BN, kEpi, TO, TMSK>(P, &o_map, &x_map, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0,
-                                                   warp, lane, et, &H.tmem_full[acc], (tcount >> 1) & 1, &H.tmem_empty[acc],
-                                                   grp * 32, staging);
+                int next_row0 = -1;
+                if (tile + (int)gridDim.x < mtiles) {
+                    int nb0, nm0;
+                    tile_coords(tile + (int)gridDim.x, nb0, nm0);
+                    next_row0 = nb0 * P.Mper + nm0;
+                }
+                if (P.tma_mask && tcount == 0 && et == 0) {
+                    mbar_expect_tx(&H.mask_full, (uint32_t)(BN / 64) * 16384u);
+#pragma unroll
+                    for (int bx = 0; bx < BN / 64; ++bx)
+                        tma_load_2d(&m_map, &H.mask_full, maskbuf + bx * 16384, n0 + bx * 64, b0 * P.Mper + m0);
+                }
+                drain_tile_tma<BN, kEpi, TO, TMSK>(P, &o_map, &x_map, &m_map, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0,
+                                                   m0, n0, warp, lane, et, &H.tmem_full[acc], (tcount >> 1) & 1,
+                                                   &H.tmem_empty[acc], grp * 32, staging, maskbuf, &H.mask_full, tcount & 1,
+                                                   next_row0);
                 continue;
             }
             drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
@@ -919,6 +950,7 @@ int make_view_map(CUtensorMap* map, const void* base, long long inner, long long
                   int box_samples);
 // 2-D view (column, flat row) of an output tensor whose rows are row_stride elements apart; boxes of 128 bytes x 128 rows
 int make_out_map(CUtensorMap* map, const void* base, int elem_bytes, long long cols, long long rows, long long row_stride);
+bool mask_tma_enabled();     // MELOGAN_DISABLE_TMA_MASK=1 keeps per-thread mask loads (A/B profiling)
 bool tma_store_enabled();    // MELOGAN_DISABLE_TMA_STORE=1 keeps the row-per-thread epilogue stores (A/B profiling)
 // 2-D view (k, rows) of a packed weight [rows][K]
 int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows);
@@ -939,7 +971,7 @@ int launch_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs&
 
 template <int BN, typename TO, typename TMSK>
 int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const CUtensorMap& om, const CUtensorMap& xm,
-                     const TcTapArgs& a, int mtiles, int nstages, int ctas_x, size_t smem, cudaStream_t st) {
+                     const CUtensorMap& mm, const TcTapArgs& a, int mtiles, int nstages, int ctas_x, size_t smem, cudaStream_t st) {
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_ws_kernel<BN, TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -947,7 +979,7 @@ int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const CUtenso
         attr_smem = 227 * 1024;
     }
     dim3 grid(ctas_x, a.N / BN);
-    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, om, xm, a, mtiles, nstages);
+    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, om, xm, mm, a, mtiles, nstages);
     MG_LAUNCH_OK();
     return MG_OK;
 }
@@ -1038,13 +1070,23 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
             }
             a.tma_store = 1;
         }
-        const size_t extra = a.tma_store ? staging : 0;
+        // the mask tile (same layout as the output) by TMA too when it is bf16 and its buffer still leaves 3 stages
+        CUtensorMap mm = am;
+        const size_t maskbytes = (size_t)128 * BN * 2;
+        a.tma_mask = 0;
+        if (a.tma_store && a.mul_mode != MUL_NONE && sizeof(TMSK) == 2 && mask_tma_enabled() &&
+            wbytes + 3 * a_stage + staging + maskbytes <= avail && ((uintptr_t)((const TMSK*)a.mul_src + a.o_off)) % 16 == 0) {
+            const int rc = make_out_map(&mm, (const TMSK*)a.mul_src + a.o_off, 2, a.N, rows, a.o_mstride);
+            if (rc != MG_OK) return rc;
+            a.tma_mask = 1;
+        }
+        const size_t extra = (a.tma_store ? staging : 0) + (a.tma_mask ? maskbytes : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage + extra;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
-        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, om, xm, a, mtiles, nstages, ctas_x, smem, st)
-                           : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, om, xm, a, mtiles, nstages, ctas_x, smem, st);
+        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
+                           : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
 }
