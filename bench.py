@@ -253,7 +253,7 @@ def main():
     import ctypes
     pr = (ctypes.c_double * 4)()
     L.mg_probe_end(pr)
-    probe_launches, probe_ms, probe_flops = pr[0], pr[1], pr[2]
+    probe_launches, probe_ms, probe_flops, probe_bytes = pr[0], pr[1], pr[2], pr[3]
     if family == 3 and probe_launches == 0:      # bf16 mode without tensor-core kernels yet
         family = 1
     peaks = {}
@@ -265,6 +265,15 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json, bf16 sustained)" if peaks else "fallback (B200_PROFILING.md, 1.4 PF sustained)"
     achieved_tf = (probe_flops / (probe_ms * 1e-3) / 1e12) if probe_ms > 0 else 0.0
+    # the same launches against the HBM roofline: algorithmic bytes (activation once + output + mask/derivative tiles)
+    peak_gbs = float(peaks.get("hbm_gbs", 6546.6))
+    achieved_gbs = (probe_bytes / (probe_ms * 1e-3) / 1e9) if probe_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_tc_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch_avg")
+    except Exception:
+        pass
 
     rolls_per_step = K * B * world
     value = rolls_per_step / (ms_dev / args.steps * 1e-3)
@@ -288,9 +297,14 @@ def main():
         "roofline": {"bound": "tensor", "kernel": {1: "tapgemm_kernel (CUDA-core fp32 implicit GEMM)",
                                                    3: "tc_gemm_kernel (tcgen05 bf16 implicit GEMM)"}[family],
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_note": "dram read+write bytes per launch, mean over the ncu --set full capture in profiles/ "
+                                     "(r01_tc_traffic.json); algorithmic bytes per launch = "
+                                     f"{probe_bytes / max(probe_launches, 1):.3e}",
                      "launches_per_step": probe_launches, "kernel_ms_per_step": probe_ms,
-                     "share_of_step": probe_ms / (ms_dev / args.steps) if ms_dev > 0 else None},
+                     "share_of_step": probe_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
+                     "hbm_view": {"achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s",
+                                  "frac": achieved_gbs / peak_gbs if peak_gbs else None}},
         "whole_step_model_tflops": value * MFLOP_PER_ROLL * 1e6 / 1e12 / max(world, 1),
     }
     if rank == 0:

@@ -1037,7 +1037,10 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
                const CUtensorMap* am_halo = nullptr) {
     const long long rows = (long long)a.B * a.Mper;
     const int mtiles = (int)((rows + 127) / 128);
-    ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * a.N * a.ntaps * K, (double)rows * (K * 2.0 + a.N * sizeof(TO)), st);
+    // algorithmic traffic: the activation once, the output (and derivative tile), the mask tile
+    ProbeScope probe(PROBE_TC_GEMM, 2.0 * (double)rows * a.N * a.ntaps * K,
+                     (double)rows * (K * 2.0 + a.N * sizeof(TO) * (a.aux ? 2.0 : 1.0) +
+                                     (a.mul_mode != MUL_NONE ? a.N * (double)sizeof(TMSK) : 0.0)), st);
     const int nslabs = a.N / BN;
     const size_t wbytes = (size_t)a.ntaps * (K / 64) * BN * 128;
     const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes;
