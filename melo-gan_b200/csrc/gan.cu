@@ -757,7 +757,9 @@ int generator_step(mg_gan* c, const float* numeric, const float* noise, const lo
     do {                                                                              \
         if (!(c)->has_grads[m]) { mg::set_error(what ": module %d has no gradient buffers bound", m); return MG_ERR_STATE; } \
     } while (0)
-#define MG_DISPATCH(c, fn, ...) ((c)->bf16 ? fn<__nv_bfloat16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+// TF32 tensor cores for the fp32 Linears are a bf16-mode choice; fp32 parity mode never takes them
+#define MG_DISPATCH(c, fn, ...) \
+    (mg::tc::set_tf32((c)->bf16), (c)->bf16 ? fn<__nv_bfloat16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
     MG_REQUIRE(cfg && out, "gan_create: null argument");
@@ -961,6 +963,7 @@ extern "C" int mg_gradient_penalty(mg_gan* c, const float* real, const float* fa
     MG_NEED_GRADS(c, 2, "gradient_penalty");
     MG_REQUIRE(real && fake && alpha, "gradient_penalty: null pointer");
     // GP alone: zero seeds for the real/fake rows, unit weight on the penalty
+    mg::tc::set_tf32(c->bf16);
     return c->bf16 ? critic_loss_backward<__nv_bfloat16>(c, real, fake, emb, alpha, metrics_out, as_stream(stream), 0.f, 0.f, 1.f)
                    : critic_loss_backward<float>(c, real, fake, emb, alpha, metrics_out, as_stream(stream), 0.f, 0.f, 1.f);
 }
@@ -988,6 +991,7 @@ extern "C" int mg_emotion_train_forward(mg_gan* c, const float* notes, const flo
     MG_REQUIRE(dropout_p >= 0.0 && dropout_p < 1.0, "emotion_train_forward: dropout must be in [0, 1)");
     MG_REQUIRE(dropout_p == 0.0 || (mask1 && mask2), "emotion_train_forward: dropout masks required");
     if (dropout_p == 0.0) { mask1 = mask2 = nullptr; }
+    mg::tc::set_tf32(c->bf16);
     return c->bf16 ? ed_train_forward<__nv_bfloat16>(c, notes, mask1, mask2, (float)dropout_p, logits_out, as_stream(stream))
                    : ed_train_forward<float>(c, notes, mask1, mask2, (float)dropout_p, logits_out, as_stream(stream));
 }

@@ -87,11 +87,18 @@ int set_enabled(int on) {
     return prev;
 }
 
+static bool g_tf32 = false;
+bool tf32_enabled() {
+    static const bool off = getenv("MELOGAN_DISABLE_TF32") != nullptr;
+    return g_tf32 && !off;
+}
+void set_tf32(bool on) { g_tf32 = on; }
+
 int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
-                 int box_samples) {
+                 int box_samples, int elem_bytes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
-    const cuuint64_t row_bytes = (cuuint64_t)C * 2;
+    const cuuint64_t row_bytes = (cuuint64_t)C * (cuuint64_t)elem_bytes;
     cuuint64_t gdim[4], gstr[3];
     if (stride == 1) {
         gdim[0] = (cuuint64_t)C; gdim[1] = 1; gdim[2] = (cuuint64_t)L; gdim[3] = (cuuint64_t)B;
@@ -100,9 +107,9 @@ int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, 
         gdim[0] = (cuuint64_t)C; gdim[1] = 2; gdim[2] = (cuuint64_t)(L / 2); gdim[3] = (cuuint64_t)B;
         gstr[0] = row_bytes; gstr[1] = 2 * row_bytes; gstr[2] = row_bytes * (cuuint64_t)L;
     }
-    const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, (cuuint32_t)box_samples};
+    const cuuint32_t box[4] = {(cuuint32_t)(128 / elem_bytes), 1, (cuuint32_t)box_rows, (cuuint32_t)box_samples};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -133,14 +140,14 @@ int make_view_map(CUtensorMap* map, const void* base, long long inner, long long
     return MG_OK;
 }
 
-int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows) {
+int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows, int elem_bytes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)K * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

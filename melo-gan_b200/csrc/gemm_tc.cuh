@@ -121,6 +121,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// fp32 operands in shared memory, read as TF32 (10-bit mantissa), fp32 accumulate: K = 8 per instruction = 32 bytes
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (TF32) umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
+    else umma_f16(d_tmem, a_desc, b_desc, idesc, acc);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -161,8 +175,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// operand format: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+__host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major, uint32_t fmt = 1) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
@@ -170,7 +185,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_m
 // tap-GEMM
 // ---------------------------------------------------------------------------------------------
 struct TcTapArgs {
-    int ntaps, kblocks;                 // kblocks = K / 64 per tap
+    int ntaps, kblocks;                 // kblocks = K / ktile per tap
+    int ktile;                          // elements per 128-byte k-block: 64 (bf16) or 32 (fp32 read as TF32)
     int a_p[kTcMaxTaps], a_dm[kTcMaxTaps];  // per tap: plane (dim 1) and row shift (dim 2) of the A map
     int b_row[kTcMaxTaps];                  // per tap: first row of that tap's [N][K] block in the packed weight
     // tap groups (weight-stationary kernel): the taps of a group read the same plane at row shifts within `halo` rows of
@@ -507,7 +523,7 @@ struct TapSmem {
     alignas(16) float bias[BN], scale[BN];          // this tile's bias (permuted) and alpha * folded-BN scale
 };
 
-template <int BN, typename TO, typename TMSK>
+template <int BN, typename TO, typename TMSK, bool TF32 = false>
 __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__ CUtensorMap a_map,
                                                          const __grid_constant__ CUtensorMap b_map, const TcTapArgs P) {
     extern __shared__ unsigned char smem_raw[];
@@ -550,13 +566,13 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
                 mbar_wait(&S.empty[s], (it & 1) ^ 1);
                 const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
                 mbar_expect_tx(&S.full[s], kStageBytes);
-                tma_load_4d(&a_map, &S.full[s], S.a[s], kc * kTileK, P.a_p[t], m0 + P.a_dm[t], b0);
-                tma_load_2d(&b_map, &S.full[s], S.b[s], kc * kTileK, P.b_row[t] + n0);
+                tma_load_4d(&a_map, &S.full[s], S.a[s], kc * P.ktile, P.a_p[t], m0 + P.a_dm[t], b0);
+                tma_load_2d(&b_map, &S.full[s], S.b[s], kc * P.ktile, P.b_row[t] + n0);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0, TF32 ? 2u : 1u);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % kStages, it = kb / kStages;
             mbar_wait(&S.full[s], it & 1);
@@ -567,7 +583,7 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
                 for (int k = 0; k < kTileK / 16; ++k) {
                     const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
                     const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_f16(tmem_acc, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    umma<TF32>(tmem_acc, ad, bd, idesc, (kb | k) ? 1u : 0u);
                 }
                 umma_commit(&S.empty[s]);                       // frees the smem stage when these MMAs retire
                 if (kb == nkb - 1) umma_commit(&S.tmem_full);   // accumulator complete
@@ -621,7 +637,7 @@ struct WsHeader {
     alignas(16) int4 mmatab[kWsMaxLoads];
 };
 
-template <int BN, typename TO, typename TMSK>
+template <int BN, typename TO, typename TMSK, bool TF32 = false>
 __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(const __grid_constant__ CUtensorMap a_map,
                                                             const __grid_constant__ CUtensorMap b_map,
                                                             const __grid_constant__ CUtensorMap o_map,
@@ -659,7 +675,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
         int i = 0;
         for (int g = 0; g < P.ngroups; ++g)
             for (int kc = 0; kc < P.kblocks; ++kc) {
-                H.ldtab[g * P.kblocks + kc] = make_int4(kc * kTileK, P.g_p[g], P.g_dmin[g], 0);
+                H.ldtab[g * P.kblocks + kc] = make_int4(kc * P.ktile, P.g_p[g], P.g_dmin[g], 0);
                 for (int j = 0; j < P.g_count[g]; ++j, ++i) {
                     const int t = P.g_tap[P.g_first[g] + j];
                     H.mmatab[i] = make_int4((P.a_dm[t] - P.g_dmin[g]) * 128, (t * P.kblocks + kc) * (int)kWBytes,
@@ -682,7 +698,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             mbar_expect_tx(&H.wfull, (uint32_t)nkb * kWBytes);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
-                tma_load_2d(&b_map, &H.wfull, wsm + (size_t)kb * BN * kTileK, kc * kTileK, P.b_row[t] + n0);
+                tma_load_2d(&b_map, &H.wfull, wsm + (size_t)kb * BN * kTileK, kc * P.ktile, P.b_row[t] + n0);
             }
             int s = 0;
             uint32_t ph = 0;
@@ -702,7 +718,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0, TF32 ? 2u : 1u);
         mbar_wait(&H.wfull, 0);
         int s = 0, tcount = 0;
         uint32_t ph = 0;
@@ -726,7 +742,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                     const uint64_t bd = dbase | (uint64_t)(((w_base + (uint32_t)M.y) >> 4) & 0x3FFF);
                     if (!(P.dbg & 2) && elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kTileK / 16; ++k) umma_f16(tacc, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : started);
+                        for (int k = 0; k < kTileK / 16; ++k) umma<TF32>(tacc, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : started);
                     }
                     started = 1;
                     last = M.z;
@@ -911,7 +927,7 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
 struct PackArgs {
     const float* W; int w_toff[kMaxTaps]; int w_nstride, w_kstride, n_perm_q, n_perm_p, k_perm_q, k_perm_p;
     int ntaps, N, K;
-    __nv_bfloat16* out;
+    void* out; int f32;          // packed [tap][n][k] as bf16, or as fp32 for the TF32 path
 };
 static __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs P) {
     const long long total = (long long)P.ntaps * P.N * P.K;
@@ -922,7 +938,8 @@ static __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs 
         const int n = (int)(tn % P.N), t = (int)(tn / P.N);
         const float w = __ldg(P.W + P.w_toff[t] + (long long)perm_index(n, P.n_perm_q, P.n_perm_p) * P.w_nstride +
                               (long long)perm_index(k, P.k_perm_q, P.k_perm_p) * P.w_kstride);
-        P.out[i] = __float2bfloat16_rn(w);
+        if (P.f32) static_cast<float*>(P.out)[i] = w;
+        else static_cast<__nv_bfloat16*>(P.out)[i] = __float2bfloat16_rn(w);
     }
 }
 
@@ -942,7 +959,7 @@ bool ws_enabled();           // MELOGAN_DISABLE_WS=1 keeps the non-persistent te
 // 4-D view (k, parity, row, sample) of a channels-last activation [B][L][C] (bf16):
 //   stride 1: dims (C, 1, L, B);  stride 2: dims (C, 2, L/2, B)
 int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
-                 int box_samples);
+                 int box_samples, int elem_bytes = 2);
 // general 4-D bf16 view: dims (64-wide inner box over `inner` elements, planes, rows, samples) with explicit
 // element strides; used for the overlapping note windows and the row-mod-P planes of the banded layers
 int make_view_map(CUtensorMap* map, const void* base, long long inner, long long planes, long long plane_stride,
@@ -953,33 +970,35 @@ int make_out_map(CUtensorMap* map, const void* base, int elem_bytes, long long c
 bool mask_tma_enabled();     // MELOGAN_DISABLE_TMA_MASK=1 keeps per-thread mask loads (A/B profiling)
 bool tma_store_enabled();    // MELOGAN_DISABLE_TMA_STORE=1 keeps the row-per-thread epilogue stores (A/B profiling)
 // 2-D view (k, rows) of a packed weight [rows][K]
-int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows);
+int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows, int elem_bytes = 2);
+bool tf32_enabled();         // set per API call from the context's precision (fp32 parity mode never uses TF32)
+void set_tf32(bool on);
 
-template <int BN, typename TO, typename TMSK>
+template <int BN, typename TO, typename TMSK, bool TF32 = false>
 int launch_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, const TcTapArgs& a, int mtiles, cudaStream_t st) {
     static bool attr_done = false;
     const size_t smem = sizeof(TapSmem<BN>) + 1024;
     if (!attr_done) {
-        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_kernel<BN, TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_kernel<BN, TO, TMSK, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     dim3 grid(mtiles, a.N / BN);
-    tc_tapgemm_kernel<BN, TO, TMSK><<<grid, 192, smem, st>>>(am, bm, a);
+    tc_tapgemm_kernel<BN, TO, TMSK, TF32><<<grid, 192, smem, st>>>(am, bm, a);
     MG_LAUNCH_OK();
     return MG_OK;
 }
 
-template <int BN, typename TO, typename TMSK>
+template <int BN, typename TO, typename TMSK, bool TF32 = false>
 int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const CUtensorMap& om, const CUtensorMap& xm,
                      const CUtensorMap& mm, const TcTapArgs& a, int mtiles, int nstages, int ctas_x, size_t smem, cudaStream_t st) {
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_ws_kernel<BN, TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_ws_kernel<BN, TO, TMSK, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(227 * 1024)));
         attr_smem = 227 * 1024;
     }
     dim3 grid(ctas_x, a.N / BN);
-    tc_tapgemm_ws_kernel<BN, TO, TMSK><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, om, xm, mm, a, mtiles, nstages);
+    tc_tapgemm_ws_kernel<BN, TO, TMSK, TF32><<<grid, WsCfg<BN>::kThreads, smem, st>>>(am, bm, om, xm, mm, a, mtiles, nstages);
     MG_LAUNCH_OK();
     return MG_OK;
 }
@@ -1032,9 +1051,10 @@ bool reuse_enabled();        // MELOGAN_DISABLE_TAP_REUSE=1: one activation tile
 // Launch a tap-GEMM whose tensor maps and TcTapArgs are ready: weight-stationary persistent form when the slab's
 // weights fit in shared memory next to >= 3 activation stages and every CTA gets >= 4 tiles, else one tile per CTA.
 // am_halo (optional): the same activation view with boxes of 128 + a.halo rows, a.ngroups/g_* describing the tap groups.
-template <typename TO, typename TMSK>
+template <typename TO, typename TMSK, bool TF32 = false>
 int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN, int K, cudaStream_t st,
                const CUtensorMap* am_halo = nullptr) {
+    a.ktile = TF32 ? 32 : 64;
     const long long rows = (long long)a.B * a.Mper;
     const int mtiles = (int)((rows + 127) / 128);
     // algorithmic traffic: the activation once, the output (and derivative tile), the mask tile
@@ -1042,7 +1062,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
                      (double)rows * (K * 2.0 + a.N * sizeof(TO) * (a.aux ? 2.0 : 1.0) +
                                      (a.mul_mode != MUL_NONE ? a.N * (double)sizeof(TMSK) : 0.0)), st);
     const int nslabs = a.N / BN;
-    const size_t wbytes = (size_t)a.ntaps * (K / 64) * BN * 128;
+    const size_t wbytes = (size_t)a.ntaps * (K / a.ktile) * BN * 128;
     const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes;
     int ctas_x = num_sms() / nslabs;
     if (ctas_x < 1) ctas_x = 1;
@@ -1051,7 +1071,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = dbg; }
     const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
-    const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x && a.ntaps * (K / 64) <= kWsMaxLoads;
+    const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x && a.ntaps * (K / a.ktile) <= kWsMaxLoads;
     if (trace)
         fprintf(stderr, "[tc_tap] rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%zu ws=%d stages=%d act=%d mul=%d aux=%d\n",
                 rows, a.N, K, a.ntaps, a.ngroups, a.halo, BN, sizeof(TO), (int)ws, ws ? (int)((avail - wbytes) / a_stage) : 3, a.act,
@@ -1088,18 +1108,22 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage + extra;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
-        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
-                           : launch_tc_tap_ws<64, TO, TMSK>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
+        return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
+                           : launch_tc_tap_ws<64, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
-    return (BN == 128) ? launch_tc_tap<128, TO, TMSK>(am, bm, a, mtiles, st) : launch_tc_tap<64, TO, TMSK>(am, bm, a, mtiles, st);
+    return (BN == 128) ? launch_tc_tap<128, TO, TMSK, TF32>(am, bm, a, mtiles, st)
+                       : launch_tc_tap<64, TO, TMSK, TF32>(am, bm, a, mtiles, st);
 }
 
 // Try to run a tap-GEMM described in SIMT terms on the tensor cores.  Returns 1 if launched, 0 if the shape
 // does not qualify (caller falls back to the CUDA-core kernel), or a negative mg_status on error.
 template <typename TA, typename TO, typename TMSK>
 int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
-    if (!std::is_same<TA, __nv_bfloat16>::value || !enabled()) return 0;
-    if (P.K % 64 || P.N % 64 || P.row_scale || P.ntaps < 1 || P.ntaps > kMaxTaps) return 0;
+    constexpr bool TF32 = std::is_same<TA, float>::value;
+    constexpr int EB = TF32 ? 4 : 2, KT = TF32 ? 32 : 64;          // operand element bytes, elements per 128-byte k-block
+    if (!enabled()) return 0;
+    if (TF32 && !(tf32_enabled() && P.Mper == 1 && P.ntaps == 1 && P.B >= 128)) return 0;   // the fp32 Linears of bf16 mode
+    if (P.K % KT || P.N % 64 || P.row_scale || P.ntaps < 1 || P.ntaps > kMaxTaps) return 0;
     if (!is_pow2(P.Mper) || (P.Mper > 128 && P.Mper % 128)) return 0;
     int stride;
     if (P.Mper == 1) stride = 1;
@@ -1112,7 +1136,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     if (((uintptr_t)P.A) % 16 || ((uintptr_t)P.Out) % 16) return 0;
     if (P.o_off % 8 || P.o_mstride % 8 || P.o_bstride % 8) return 0;
     TcTapArgs a{};
-    a.ntaps = P.ntaps; a.kblocks = P.K / 64;
+    a.ntaps = P.ntaps; a.kblocks = P.K / KT; a.ktile = KT;
     for (int t = 0; t < P.ntaps; ++t) {
         if (P.a_toff[t] % P.K) return 0;
         const int r = P.a_toff[t] / P.K;                    // row shift in A rows
@@ -1130,12 +1154,12 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     // pack the weight taps [ntaps][N][K] bf16 into the next scratch slot
     Scratch& sc = scratch();
     const size_t need = (size_t)P.ntaps * P.N * P.K;
-    if (need > sc.slot_elems) return 0;
+    if (need * EB > sc.slot_elems * 2) return 0;
     __nv_bfloat16* wp = sc.slot[sc.next];
     sc.next = (sc.next + 1) & 3;
     PackArgs pk{};
     pk.W = P.W; pk.w_nstride = P.w_nstride; pk.w_kstride = P.w_kstride; pk.n_perm_q = P.n_perm_q; pk.n_perm_p = P.n_perm_p;
-    pk.k_perm_q = P.k_perm_q; pk.k_perm_p = P.k_perm_p; pk.ntaps = P.ntaps; pk.N = P.N; pk.K = P.K; pk.out = wp;
+    pk.k_perm_q = P.k_perm_q; pk.k_perm_p = P.k_perm_p; pk.ntaps = P.ntaps; pk.N = P.N; pk.K = P.K; pk.out = wp; pk.f32 = TF32 ? 1 : 0;
     for (int t = 0; t < P.ntaps; ++t) pk.w_toff[t] = P.w_toff[t];
     long long blocks = ((long long)need + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
@@ -1147,26 +1171,26 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     if (BN == 128) {   // a 128-wide slab whose taps cannot stay resident next to 3 activation stages: take 64-wide slabs if
                        // THOSE can (the activation is then read once per slab, but no weight tile is ever re-fetched)
         const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes - 3 * 17408;
-        const size_t w128 = (size_t)P.ntaps * (P.K / 64) * 128 * 128;
+        const size_t w128 = (size_t)P.ntaps * (P.K / KT) * 128 * 128;
         const long long mt = ((long long)P.B * P.Mper + 127) / 128;
         static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;
         if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64))) BN = 64;
     }
-    int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt);
+    int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt, EB);
     if (rc != MG_OK) return rc;
-    rc = make_weight_map(&bm, wp, P.K, (long long)P.ntaps * P.N, BN);
+    rc = make_weight_map(&bm, wp, P.K, (long long)P.ntaps * P.N, BN, EB);
     if (rc != MG_OK) return rc;
     CUtensorMap amh;
     const CUtensorMap* halo_map = nullptr;
     if (reuse_enabled() && a.mpt == 128 && P.ntaps > 1) {
         build_tap_groups(a, 8);
         if (a.ngroups < a.ntaps) {
-            rc = make_act_map(&amh, P.A, P.K, LA, P.B, stride, 128 + a.halo, 1);
+            rc = make_act_map(&amh, P.A, P.K, LA, P.B, stride, 128 + a.halo, 1, EB);
             if (rc != MG_OK) return rc;
             halo_map = &amh;
         }
     }
-    rc = run_tc_tap<TO, TMSK>(am, bm, a, BN, P.K, st, halo_map);
+    rc = run_tc_tap<TO, TMSK, TF32>(am, bm, a, BN, P.K, st, halo_map);
     return rc == MG_OK ? 1 : rc;
 }
 

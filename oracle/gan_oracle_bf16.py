@@ -17,11 +17,36 @@ def q(t):
     return t + (t.to(torch.bfloat16).to(torch.float32) - t).detach()
 
 
+def t32(t):
+    """What tcgen05 kind::tf32 reads of a float32 operand: the low 13 mantissa bits are ignored.  Identity for autograd."""
+    tt = (t.detach().contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return t + (tt - t).detach()
+
+
+def lin(x, w, b):
+    """The float32 Linears of bf16 mode run on the tensor cores as TF32 when they are tile-shaped (gemm_tc.cuh
+    try_tc_tapgemm: batch >= 128, K % 32 == 0, N % 64 == 0); otherwise on the CUDA cores in full float32."""
+    if x.shape[0] >= 128 and w.shape[1] % 32 == 0 and w.shape[0] % 64 == 0:
+        return F.linear(t32(x), t32(w), b)
+    return F.linear(x, w, b)
+
+
+def fe_forward(P, x, mask1=None, mask2=None, train=True, p_drop=0.2):
+    h = F.layer_norm(x, (x.shape[1],), P["net.0.weight"], P["net.0.bias"], 1e-5)
+    h = F.gelu(lin(h, P["net.1.weight"], P["net.1.bias"]))
+    if train:
+        h = h * (mask1 * (1.0 / (1.0 - p_drop)))
+    h = F.gelu(lin(h, P["net.4.weight"], P["net.4.bias"]))
+    if train:
+        h = h * (mask2 * (1.0 / (1.0 - p_drop)))
+    return lin(h, P["net.7.weight"], P["net.7.bias"])
+
+
 def gen_forward(P, noise, emb, bn_state):
     x = torch.cat([noise, emb], 1)
-    h = F.relu(F.linear(x, P["noise_to_latent.net.0.weight"], P["noise_to_latent.net.0.bias"]))
-    latent = F.linear(h, P["noise_to_latent.net.2.weight"], P["noise_to_latent.net.2.bias"])
-    y = q(F.relu(F.linear(latent, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"])))
+    h = F.relu(lin(x, P["noise_to_latent.net.0.weight"], P["noise_to_latent.net.0.bias"]))
+    latent = lin(h, P["noise_to_latent.net.2.weight"], P["noise_to_latent.net.2.bias"])
+    y = q(F.relu(lin(latent, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"])))
     y = q(F.relu(F.linear(y, q(P["decoder.pre.2.weight"]), P["decoder.pre.2.bias"])))
     y = y.view(y.shape[0], 256, -1)
     for conv, bn in (("decoder.deconv.0", "decoder.deconv.1"), ("decoder.deconv.3", "decoder.deconv.4")):
@@ -39,7 +64,7 @@ def disc_forward(P, notes, emb):
     for i, name in enumerate(("conv.0", "conv.2", "conv.4")):
         h = q(F.leaky_relu(F.conv1d(h, q(P[name + ".weight"]), P[name + ".bias"], stride=2, padding=2), 0.2))
     h = F.adaptive_avg_pool1d(h, 1)
-    feat = F.leaky_relu(F.linear(h.view(h.size(0), -1), P["fc.1.weight"], P["fc.1.bias"]), 0.2)
+    feat = F.leaky_relu(lin(h.view(h.size(0), -1), P["fc.1.weight"], P["fc.1.bias"]), 0.2)
     feat = torch.cat([feat, emb], 1)
     return F.linear(feat, P["real_fake.weight"], P["real_fake.bias"]).squeeze(1)
 
@@ -53,9 +78,9 @@ def ed_forward(P, notes):
                          training=False, eps=1e-5)
         x = q(F.gelu(x))
     x = F.adaptive_avg_pool1d(x, 1).squeeze(-1)
-    x = F.linear(x, P["encoder.project.weight"], P["encoder.project.bias"])
-    x = F.gelu(F.linear(x, P["classifier.net.0.weight"], P["classifier.net.0.bias"]))
-    x = F.gelu(F.linear(x, P["classifier.net.3.weight"], P["classifier.net.3.bias"]))
+    x = lin(x, P["encoder.project.weight"], P["encoder.project.bias"])
+    x = F.gelu(lin(x, P["classifier.net.0.weight"], P["classifier.net.0.bias"]))
+    x = F.gelu(lin(x, P["classifier.net.3.weight"], P["classifier.net.3.bias"]))
     return F.linear(x, P["classifier.head.weight"], P["classifier.head.bias"])
 
 
@@ -63,7 +88,7 @@ def generator_step(params, batch, cfg=O.CFG):
     PE, PG, PD, PED = params["E"], params["G"], params["D"], params["ED"]
     El, Gl = O._leaves(PE), O._leaves(PG)
     bn_state = {k: v.clone() for k, v in PG.items() if O.is_buffer(k)}
-    emb = O.fe_forward(El, batch["numeric"], batch["mask1_g"], batch["mask2_g"], train=True, p_drop=cfg["ENC_DROPOUT"])
+    emb = fe_forward(El, batch["numeric"], batch["mask1_g"], batch["mask2_g"], train=True, p_drop=cfg["ENC_DROPOUT"])
     notes, latent = gen_forward(Gl, batch["noise_g"], emb, bn_state)
     loss_adv = -disc_forward(PD, notes, emb).mean()
     logits = ed_forward(PED, notes)
@@ -76,7 +101,7 @@ def generator_step(params, batch, cfg=O.CFG):
 def critic_step(params, batch, cfg=O.CFG):
     PE, PG, PD = params["E"], params["G"], params["D"]
     with torch.no_grad():
-        emb = O.fe_forward(PE, batch["numeric"], batch["mask1_d"], batch["mask2_d"], train=True, p_drop=cfg["ENC_DROPOUT"])
+        emb = fe_forward(PE, batch["numeric"], batch["mask1_d"], batch["mask2_d"], train=True, p_drop=cfg["ENC_DROPOUT"])
         fake, _ = gen_forward(PG, batch["noise_d"], emb, {k: v.clone() for k, v in PG.items() if O.is_buffer(k)})
         fake = fake.contiguous()
     Dl = O._leaves(PD)

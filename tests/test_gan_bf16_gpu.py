@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 from oracle import gan_oracle_bf16 as OB
 
 TOL = 1e-2          # losses: relative; activation tensors: relative L2 (and 2x that in max-norm)
-EMU_TOL = 4e-2      # gradients against the bf16-STORAGE-EMULATING oracle (same rounding points, CPU float32 math):
+EMU_TOL = 4e-2      # (x2 from 128 samples on: the TF32 dgrad Linears are only approximately emulated) gradients against the bf16-STORAGE-EMULATING oracle (same rounding points, CPU float32 math):
                     # what is left is the bf16 rounding of activation gradients and summation order
 # Gradients (relative L2): a bf16 forward moves ~0.3% of the near-zero pre-activations across zero relative to the
 # fp32 oracle; each such LeakyReLU/ReLU mask flip changes one activation-gradient element by O(1), i.e. about
@@ -39,7 +39,7 @@ def test_bf16_critic_step(B, fan, pseed):
         if k.endswith("bias"):
             continue      # sums of +1/B and -1/B weighted terms: cancellation-dominated (see fp32 tests)
         assert_close_l2(grads["D"][k], g, GRAD_TOL, "D grad " + k)
-        assert_close_l2(grads["D"][k], emu["grads"][k], EMU_TOL, "D grad vs bf16-emulating oracle " + k)
+        assert_close_l2(grads["D"][k], emu["grads"][k], EMU_TOL * (2 if B >= 128 else 1), "D grad vs bf16-emulating oracle " + k)
 
 
 @pytest.mark.parametrize("B,fan,pseed", [(8, True, 4), (32, False, 2), (160, True, 7)])
@@ -56,12 +56,14 @@ def test_bf16_generator_step(B, fan, pseed):
     assert_close(eng.buffer("g.notes").view(B, 512, 4), ref["notes"], 2 * TOL, "notes (max-norm)")
     assert_close(eng.buffer("ed.logits")[:B * 4].view(B, 4), ref["logits"], TOL, "logits")
     emu = OB.generator_step(O.clone_params(params), batch)
-    assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), emu["notes"], 2e-3, "notes vs bf16-emulating oracle")
+    # from 128 samples on the float32 Linears run as TF32 (emulated in the oracle by mantissa truncation)
+    assert_close_l2(eng.buffer("g.notes").view(B, 512, 4), emu["notes"], 4e-3 if B >= 128 else 2e-3,
+                    "notes vs bf16-emulating oracle")
     for k, g in ref["grads_G"].items():
         if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias"):
             continue
         assert_close_l2(grads["G"][k], g, GRAD_TOL, "G grad " + k)
-        assert_close_l2(grads["G"][k], emu["grads_G"][k], EMU_TOL, "G grad vs bf16-emulating oracle " + k)
+        assert_close_l2(grads["G"][k], emu["grads_G"][k], EMU_TOL * (2 if B >= 128 else 1), "G grad vs bf16-emulating oracle " + k)
     for k, g in ref["grads_E"].items():
         assert_close_l2(grads["E"][k], g, GRAD_TOL, "E grad " + k)
-        assert_close_l2(grads["E"][k], emu["grads_E"][k], EMU_TOL, "E grad vs bf16-emulating oracle " + k)
+        assert_close_l2(grads["E"][k], emu["grads_E"][k], EMU_TOL * (2 if B >= 128 else 1), "E grad vs bf16-emulating oracle " + k)

@@ -49,9 +49,10 @@ def test_tensor_core_path_equals_cuda_core_path(B, which):
     for name in b0:
         # forward activations: bf16 storage rounding of slightly different fp32 sums.  Backward buffers additionally
         # see a few LeakyReLU/ReLU mask flips where a near-zero activation changed sign between the two paths.
-        assert_close_l2(b1[name], b0[name], 8e-3 if name in fwd else 8e-2, f"{which}:{name}")   # the banded conv.0 also rounds the notes to bf16
+        # the banded conv.0 also rounds the notes to bf16; from 128 samples on the float32 Linears run as TF32
+        assert_close_l2(b1[name], b0[name], 1e-2 if name in fwd else (1.5e-1 if B >= 128 else 8e-2), f"{which}:{name}")
     assert torch.allclose(m1, m0, rtol=2e-3, atol=1e-5), (m1, m0)
     for k in g0:
         if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias") or k.startswith("real_fake"):
             continue
-        assert_close_l2(g1[k], g0[k], 8e-2, f"{which}: grad {k}")
+        assert_close_l2(g1[k], g0[k], 1e-1 if B >= 128 else 8e-2, f"{which}: grad {k}")
