@@ -158,7 +158,9 @@ def main():
     W = max(3, args.warmup)
     cfg, ed_cfg = load_cfgs()
     B, K = args.batch, int(cfg.get("CRITIC_ITERS", 5))
-    tr = GanTrainer(cfg, ed_cfg, batch=B, precision=args.precision, device=dev, process_group=pg, seed_offset=rank)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):     # the drop-in modules print like the reference's; stdout is ONE JSON line
+        tr = GanTrainer(cfg, ed_cfg, batch=B, precision=args.precision, device=dev, process_group=pg, seed_offset=rank)
 
     # synthetic inputs: several resident cycles so consecutive steps read different data
     NSETS = 3
