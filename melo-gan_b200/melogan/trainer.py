@@ -261,4 +261,20 @@ class GanTrainer:
     def state_dict(self):
         """Checkpoint layout of train_gan.py:269-276."""
         return {'G': self.G.state_dict(), 'D': self.D.state_dict(), 'E_num': self.E_num.state_dict(),
-                'opt_G': self.opt_G.state_dict(), 'opt_D': self.opt_D.state_dict()}
+                'opt_G': self.opt_G.state_dict(), 'opt_D': self.opt_D.state_dict(),
+                'rng_counter': self.rng_counter.clone()}
+
+    def load_state_dict(self, ck):
+        """Resume from a checkpoint of train_gan.py:269-276 (this trainer's or the reference's: same keys and optimizer
+        state layout).  Parameters are copied INTO the flat groups, so the native bindings stay valid; `rng_counter`
+        (ours only) restores the device noise stream, a reference checkpoint just starts a fresh one."""
+        self.G.load_state_dict(ck['G'])
+        self.D.load_state_dict(ck['D'])
+        self.E_num.load_state_dict(ck['E_num'])
+        if 'opt_G' in ck:
+            self.opt_G.load_state_dict(ck['opt_G'])
+        if 'opt_D' in ck:
+            self.opt_D.load_state_dict(ck['opt_D'])
+        if 'rng_counter' in ck:
+            self.rng_counter.copy_(ck['rng_counter'].to(self.rng_counter.device))
+        self.rebind()

@@ -48,6 +48,7 @@ def main(argv=None):
     ap.add_argument("--config", type=str, default="config/gan_config.yaml", help="Path to the main GAN config")
     ap.add_argument("--ed_config", type=str, default="config/ed_config.yaml", help="Path to the ED config")
     ap.add_argument("--ed_ckpt", type=str, default="data/models/ed/ed_best.pth")
+    ap.add_argument("--resume", type=str, default=None, help="gan_epochNNNN.pth to continue from (SURVEY 8f-4)")
     args = ap.parse_args(argv)
     cfg, ed_cfg = load_config(args.config), load_config(args.ed_config)
     if not torch.cuda.is_available():
@@ -78,6 +79,12 @@ def main(argv=None):
     tr = GanTrainer(cfg, ed_cfg, batch=B // world, precision=os.environ.get("MELOGAN_PRECISION", "fp32"), device=device,
                     ed_state_dict=ed_state, process_group=pg, seed_offset=rank)
     d_notes, d_numeric, d_labels = (torch.from_numpy(a).to(device) for a in (notes, numeric, labels))   # 7 MB: resident
+    start_epoch = 1
+    if args.resume:
+        ck = torch.load(args.resume, map_location=device)
+        tr.load_state_dict(ck)
+        start_epoch = int(ck.get('epoch', 0)) + 1
+        print(f"[INFO] Resumed from {args.resume} (epoch {start_epoch - 1})")
 
     writer = None
     if rank == 0:
@@ -94,6 +101,8 @@ def main(argv=None):
     steps = len(notes) // B                       # drop_last=True
     for epoch in range(1, cfg['EPOCHS'] + 1):
         perm = torch.randperm(len(notes), generator=gen).to(device)          # shuffle=True, same order on every rank
+        if epoch < start_epoch:
+            continue                                                          # replay the shuffle stream up to the resume point
         for batch_idx in range(steps):
             idx = perm[batch_idx * B:(batch_idx + 1) * B].view(world, -1)[rank]
             real, num, lab = d_notes[idx].contiguous(), d_numeric[idx].contiguous(), d_labels[idx].contiguous()

@@ -195,3 +195,38 @@ def test_generation_and_midi_writer_roundtrip(tmp_path):
     # overlapping notes of one pitch make the on/off pairing ambiguous in any SMF: compare the event multisets
     assert sorted((v_, p_, on) for v_, p_, on, _ in got) == sorted((v_, p_, on) for v_, p_, on, _ in want)
     assert sorted((p_, off) for _, p_, _, off in got) == sorted((p_, off) for _, p_, _, off in want)
+
+
+def test_trainer_resume_continues_the_run():
+    """a checkpoint in the layout of train_gan.py:269-276 restores parameters, optimizer moments, step
+    counters and the device noise stream: the next cycle equals the uninterrupted one (up to the summation order of the
+    float32 atomics in the weight-gradient kernels; the two bias vectors in front of BatchNorm carry pure rounding noise
+    that Adam turns into +-lr)."""
+    import copy
+    import os
+    import yaml
+    from melogan.trainer import GanTrainer
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "melo-gan_b200", "config")
+    cfg = yaml.safe_load(open(os.path.join(root, "gan_config.yaml")))
+    ed_cfg = yaml.safe_load(open(os.path.join(root, "ed_config.yaml")))
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(3)
+    reals = torch.rand((5, B, 512, 4), generator=g, device="cuda") * 2 - 1
+    nums = torch.randn((5, B, 6), generator=g, device="cuda")
+    labels = (torch.arange(B, device="cuda") % 4).to(torch.int64)
+    a = GanTrainer(cfg, ed_cfg, batch=B, precision="fp32")
+    a.train_cycle(reals, nums, labels)
+    ck = copy.deepcopy(a.state_dict())
+    ed_state = copy.deepcopy(a.ED.state_dict())
+    a.train_cycle(reals, nums, labels)
+    b = GanTrainer(cfg, ed_cfg, batch=B, precision="fp32", ed_state_dict=ed_state)
+    b.load_state_dict(ck)
+    b.train_cycle(reals, nums, labels)
+    for name in ("G", "D", "E_num"):
+        sa, sb = a.state_dict()[name], b.state_dict()[name]
+        for k in sa:
+            if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias") or not sa[k].is_floating_point():
+                continue
+            assert torch.allclose(sa[k], sb[k], rtol=0, atol=2e-5), (name, k, (sa[k] - sb[k]).abs().max().item())
+    # and it is not trivially equal to the checkpoint itself
+    assert not torch.equal(a.state_dict()["D"]["conv.2.weight"], ck["D"]["conv.2.weight"])

@@ -155,3 +155,19 @@ def test_train_ae_iteration_on_the_dropin_module_matches_reference_golden():
             continue
         want = gold[f"VAE.final.{k}"]
         assert abs(sd[k].double().norm().item() - want[1]) <= 1e-3 * max(want[1], 1e-12), (k, sd[k].double().norm().item(), want[1])
+
+
+def test_encode_path_returns_eval_mode_mu():
+    """src/ae/encode.py -- posterior means of an eval-mode VAE, ragged tail batch included."""
+    from src.ae.encode import encode
+    from src.ae.model import VAE
+    P0 = O.make_vae_params(6)
+    model = VAE({"LATENT_DIM": 8, "MAX_NOTES": 512}).cuda()
+    with torch.no_grad():
+        model.encoder(torch.zeros(1, 512, 4, device="cuda"))
+    model.load_state_dict(P0, strict=False)
+    notes = O.make_vae_batch(74, 11)["x"].numpy()
+    got = encode(model, notes, batch_size=8)
+    assert got.shape == (11, 8)
+    _, _, mu, _ = O.vae_forward(P0, torch.from_numpy(notes), torch.zeros(11, 8), train=False)
+    assert_close(torch.from_numpy(got), mu, 1e-5, "encode(): mu in eval mode")
