@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MELOGAN_BENCH_BATCH", "4096")),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MELOGAN_BENCH_BATCH", "8192")),
                     help="per-GPU batch B of every critic/generator step")
     ap.add_argument("--precision", default=os.environ.get("MELOGAN_PRECISION", "bf16"), choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core mode (north_star tolerance 1e-2); fp32 = CUDA-core parity mode (1e-5)")
