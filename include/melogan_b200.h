@@ -124,6 +124,8 @@ typedef struct mg_gan_config {
     double lambda_emotion; /* LAMBDA_EMOTION                                                 */
     double bn_momentum; /* 0.1                                                               */
     double bn_eps;      /* 1e-5                                                              */
+    int cond_dim;       /* INTEGRATION_MODE 'conditioning': width of the AE latent appended to G's input
+                           (models.py:99-100,121-123); 0 = 'warm_start'                       */
 } mg_gan_config;
 
 enum { MG_MOD_ENCODER = 0, MG_MOD_GENERATOR = 1, MG_MOD_CRITIC = 2, MG_MOD_EMOTION = 3 };
@@ -159,6 +161,10 @@ int mg_feature_encoder_backward(mg_gan* ctx, const float* demb, void* stream);
  * backward: dnotes (B, max_notes, 4) [+ dlatent] -> G parameter gradients (added) and demb_out (B, embed_dim). */
 int mg_generator_forward(mg_gan* ctx, const float* noise, const float* emb, int train, float* notes_out,
                          float* latent_out, void* stream);
+/* 'conditioning' mode (cond_dim > 0): encoder_latent (B, cond_dim) is the third block of G's input row
+ * [noise | numeric embedding | encoder latent] (models.py:112-126).  The pointer is remembered and read by every later
+ * generator forward / fused step of this context; it carries no gradient (the reference feeds detached AE latents). */
+int mg_generator_set_condition(mg_gan* ctx, const float* encoder_latent);
 int mg_generator_backward(mg_gan* ctx, const float* dnotes, const float* dlatent, float* demb_out, void* stream);
 
 /* A-5  Discriminator.forward (WGAN critic)         src/gan/models.py:158-169

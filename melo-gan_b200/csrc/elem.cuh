@@ -446,6 +446,14 @@ static __global__ void concat2_kernel(const float* __restrict__ a, int Da, const
     out[i] = j < Da ? a[b * Da + j] : c[b * Dc + (j - Da)];
 }
 
+// out[b, off + j] = src[b, j]  for j < D   (block of a wider row)
+static __global__ void copy_cols_kernel(const float* __restrict__ src, int D, float* __restrict__ out, int ldo, int off, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int b = i / D, j = i - b * D;
+    out[(long long)b * ldo + off + j] = src[i];
+}
+
 // out[b, j] (+)= src[b, off + j]  for j < D   (slice of a wider row)
 static __global__ void slice_add_kernel(const float* __restrict__ src, int lds, int off, float* __restrict__ out, int D,
                                  int B, int accumulate) {

@@ -230,7 +230,16 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
                 cudaStream_t st) {
     const mg_gan_config& f = c->cfg;
     const int B = c->B, L0 = c->L0;
-    {
+    if (f.cond_dim > 0) {       // [noise | numeric embedding | encoder latent]   (models.py:112-126, 'conditioning')
+        MG_REQUIRE(c->g_cond, "generator_forward: conditioning mode needs mg_generator_set_condition first");
+        const int nb[3] = {f.noise_dim, f.embed_dim, f.cond_dim};
+        const float* src[3] = {noise, emb, c->g_cond};
+        for (int i = 0, off = 0; i < 3; off += nb[i], ++i) {
+            const int n = B * nb[i];
+            copy_cols_kernel<<<(n + 255) / 256, 256, 0, st>>>(src[i], nb[i], c->g_xcat, c->zin, off, B);
+            MG_LAUNCH_OK();
+        }
+    } else {
         const int n = B * c->zin;
         concat2_kernel<<<(n + 255) / 256, 256, 0, st>>>(noise, f.noise_dim, emb, f.embed_dim, c->g_xcat, B);
         MG_LAUNCH_OK();
@@ -772,6 +781,7 @@ extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
                    cfg->numeric_dim <= 32 && cfg->enc_hidden1 > 0 && cfg->enc_hidden2 > 0 && cfg->embed_dim > 0,
                "gan_create: bad layer widths");
     MG_REQUIRE(cfg->n_classes >= 2 && cfg->n_classes <= 8, "gan_create: n_classes must be in [2, 8]");
+    MG_REQUIRE(cfg->cond_dim >= 0 && cfg->cond_dim <= 4096, "gan_create: cond_dim must be in [0, 4096]");
     MG_REQUIRE(cfg->enc_dropout >= 0.0 && cfg->enc_dropout < 1.0, "gan_create: dropout must be in [0, 1)");
     int dev = 0, major = 0;
     MG_CUDA_OK(cudaGetDevice(&dev));
@@ -779,7 +789,7 @@ extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
     MG_REQUIRE(major == 10, "gan_create: this library is built for sm_100a only (device has compute capability %d.x)", major);
     mg_gan* c = new mg_gan();
     c->cfg = *cfg;
-    c->B = cfg->batch; c->T = cfg->max_notes; c->L0 = cfg->max_notes / 8; c->zin = cfg->noise_dim + cfg->embed_dim;
+    c->B = cfg->batch; c->T = cfg->max_notes; c->L0 = cfg->max_notes / 8; c->zin = cfg->noise_dim + cfg->embed_dim + cfg->cond_dim;
     c->bf16 = cfg->precision == 1;
     layout(c, nullptr);
     cudaError_t e = cudaMalloc(&c->arena, c->arena_bytes);
@@ -887,6 +897,14 @@ extern "C" int mg_generator_forward(mg_gan* c, const float* noise, const float* 
     MG_NEED_BOUND(c, 1, "generator_forward");
     MG_REQUIRE(noise && emb, "generator_forward: null pointer");
     return MG_DISPATCH(c, gen_forward, c, noise, emb, train, notes_out, latent_out, as_stream(stream));
+}
+
+extern "C" int mg_generator_set_condition(mg_gan* c, const float* encoder_latent) {
+    MG_CTX_CHECK(c);
+    MG_REQUIRE(c->cfg.cond_dim > 0, "generator_set_condition: the context was created with cond_dim = 0 (warm_start mode)");
+    MG_REQUIRE(encoder_latent, "generator_set_condition: null pointer");
+    c->g_cond = encoder_latent;
+    return MG_OK;
 }
 
 extern "C" int mg_generator_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* demb_out, void* stream) {

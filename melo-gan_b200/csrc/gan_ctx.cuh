@@ -72,6 +72,7 @@ struct mg_gan {
     float edt_drop_scale = 1.0f;
     // misc
     float *partial, *metrics, *seed_g;
+    const float* g_cond = nullptr;     // 'conditioning' mode: encoder latent (B, cond_dim), caller-owned
     size_t partial_floats = 0;
     int fwd_state = 0;   // bit flags of completed forwards, for MG_ERR_STATE checks
 };

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mg_feature_encoder_forward": ([_vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "mg_feature_encoder_backward": ([_vp, _vp, _vp], _i),
     "mg_generator_forward": ([_vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "mg_generator_set_condition": ([_vp, _vp], _i),
     "mg_generator_backward": ([_vp, _vp, _vp, _vp, _vp], _i),
     "mg_discriminator_forward": ([_vp, _vp, _vp, _i, _vp, _vp], _i),
     "mg_discriminator_backward": ([_vp, _vp, _i, _vp, _vp, _vp], _i),

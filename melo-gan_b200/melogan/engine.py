@@ -43,7 +43,7 @@ class _Config(ctypes.Structure):
                 ("gen_hidden", ctypes.c_int), ("numeric_dim", ctypes.c_int), ("enc_hidden1", ctypes.c_int),
                 ("enc_hidden2", ctypes.c_int), ("embed_dim", ctypes.c_int), ("n_classes", ctypes.c_int),
                 ("enc_dropout", ctypes.c_double), ("lambda_gp", ctypes.c_double), ("lambda_emotion", ctypes.c_double),
-                ("bn_momentum", ctypes.c_double), ("bn_eps", ctypes.c_double)]
+                ("bn_momentum", ctypes.c_double), ("bn_eps", ctypes.c_double), ("cond_dim", ctypes.c_int)]
 
 
 def _ptr(t):
@@ -63,7 +63,7 @@ class GanEngine:
 
     def __init__(self, batch, precision="fp32", max_notes=512, note_dim=4, noise_dim=128, latent_dim=64,
                  gen_hidden=512, numeric_dim=6, enc_hidden=(256, 128), embed_dim=128, n_classes=4, enc_dropout=0.2,
-                 lambda_gp=10.0, lambda_emotion=5.0, bn_momentum=0.1, bn_eps=1e-5, device=None):
+                 lambda_gp=10.0, lambda_emotion=5.0, bn_momentum=0.1, bn_eps=1e-5, device=None, cond_dim=0):
         if not torch.cuda.is_available():
             raise RuntimeError("melogan_b200 needs a CUDA (sm_100a) device; there is no CPU path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -71,10 +71,11 @@ class GanEngine:
         self.noise_dim, self.latent_dim, self.embed_dim = int(noise_dim), int(latent_dim), int(embed_dim)
         self.numeric_dim, self.enc_hidden, self.n_classes = int(numeric_dim), tuple(enc_hidden), int(n_classes)
         self.precision = precision
+        self.cond_dim = int(cond_dim)
         cfg = _Config(self.B, {"fp32": 0, "bf16": 1}[precision], self.T, self.note_dim, self.noise_dim, self.latent_dim,
                       int(gen_hidden), self.numeric_dim, int(enc_hidden[0]), int(enc_hidden[1]), self.embed_dim,
                       self.n_classes, float(enc_dropout), float(lambda_gp), float(lambda_emotion), float(bn_momentum),
-                      float(bn_eps))
+                      float(bn_eps), self.cond_dim)
         self._h = ctypes.c_void_p()
         L = _native.lib()
         for name, (argtypes, restype) in _GAN_SIGNATURES.items():
@@ -142,6 +143,12 @@ class GanEngine:
         self._call("mg_feature_encoder_backward", _ptr(demb), self._stream())
 
     # ---- A-2..A-4 ----
+    def set_condition(self, encoder_latent):
+        """'conditioning' mode: the AE latent block of G's input row, read by every later generator forward / fused step."""
+        _check_f32_cuda(encoder_latent, "encoder_latent", (self.B, self.cond_dim))
+        self._keep["cond"] = encoder_latent
+        self._call("mg_generator_set_condition", _ptr(encoder_latent))
+
     def generator_forward(self, noise, emb, train=True):
         _check_f32_cuda(noise, "noise", (self.B, self.noise_dim))
         _check_f32_cuda(emb, "numeric_embedding", (self.B, self.embed_dim))
@@ -275,6 +282,7 @@ _GAN_SIGNATURES = {
     "mg_feature_encoder_forward": ([_vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "mg_feature_encoder_backward": ([_vp, _vp, _vp], _i),
     "mg_generator_forward": ([_vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "mg_generator_set_condition": ([_vp, _vp], _i),
     "mg_generator_backward": ([_vp, _vp, _vp, _vp, _vp], _i),
     "mg_discriminator_forward": ([_vp, _vp, _vp, _i, _vp, _vp], _i),
     "mg_discriminator_backward": ([_vp, _vp, _i, _vp, _vp, _vp], _i),

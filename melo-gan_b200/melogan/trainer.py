@@ -76,8 +76,7 @@ class GanTrainer:
                 ED.load_state_dict(ed_state_dict, strict=False)
         else:
             E_num, G, D, ED = modules
-        if G.mode != "warm_start":
-            raise NotImplementedError("GanTrainer implements INTEGRATION_MODE 'warm_start' (config/gan_config.yaml)")
+        self.cond_dim = int(G.latent_dim) if G.mode == "conditioning" else 0
         self.E_num, self.G, self.D, self.ED = (m.to(self.device) for m in (E_num, G, D, ED))
         for p in self.ED.parameters():
             p.requires_grad = False
@@ -98,7 +97,11 @@ class GanTrainer:
                                   numeric_dim=cfg.get('NUMERIC_INPUT_DIM', 6), enc_hidden=h, embed_dim=emb_dim,
                                   n_classes=ed_cfg.get('n_classes', 4), enc_dropout=self.E_num.dropout,
                                   lambda_gp=cfg.get('LAMBDA_GP', 10.0), lambda_emotion=cfg.get('LAMBDA_EMOTION', 1.0),
-                                  device=self.device)
+                                  device=self.device, cond_dim=self.cond_dim)
+        # 'conditioning' mode: the AE latents of the batch (encoder_feats.npy rows) live in one persistent buffer
+        self.cond = torch.zeros((self.B, self.cond_dim), device=self.device) if self.cond_dim else None
+        if self.cond is not None:
+            self.engine.set_condition(self.cond)
         self.rebind()
 
         dev, B = self.device, self.B
@@ -151,8 +154,15 @@ class GanTrainer:
             D_.allreduce_sum_(flat.grad, self.pg)      # the 1/world factor is folded into Adam's grad_scale
 
     # ---- the two step bodies ----
-    def critic_step(self, real, numeric, noise=None, alpha=None, mask1=None, mask2=None):
+    def _set_cond(self, cond):
+        if self.cond_dim:
+            if cond is None:
+                raise ValueError("INTEGRATION_MODE 'conditioning' needs the AE latents of the batch (encoder_feats.npy)")
+            self.cond.copy_(cond)
+
+    def critic_step(self, real, numeric, noise=None, alpha=None, mask1=None, mask2=None, cond=None):
         """train_gan.py:183-205.  Returns the device tensor [loss_d, gp, mean D(real), mean D(fake)]."""
+        self._set_cond(cond)
         if noise is None:
             self._draw(critic=True)
             noise, alpha, mask1, mask2 = self.noise, self.alpha, self.mask1, self.mask2
@@ -166,8 +176,9 @@ class GanTrainer:
         self.loss_acc[6] += 1
         return self.m_d
 
-    def generator_step(self, numeric, labels, noise=None, mask1=None, mask2=None):
+    def generator_step(self, numeric, labels, noise=None, mask1=None, mask2=None, cond=None):
         """train_gan.py:212-251.  Returns the device tensor [loss_g_adv, loss_g_emo]."""
+        self._set_cond(cond)
         if noise is None:
             self._draw(critic=False)
             noise, mask1, mask2 = self.noise, self.mask1, self.mask2
@@ -181,13 +192,13 @@ class GanTrainer:
         self.loss_acc[7] += 1
         return self.m_g
 
-    def train_cycle(self, reals, numerics, labels):
+    def train_cycle(self, reals, numerics, labels, conds=None):
         """CRITIC_ITERS critic steps on reals[i], numerics[i], then one generator step on the last batch.
-        reals (K, B, T, 4), numerics (K, B, F), labels (B,) are CUDA tensors."""
+        reals (K, B, T, 4), numerics (K, B, F), labels (B,), conds (K, B, latent; 'conditioning' mode) are CUDA tensors."""
         K = self.critic_iters
         for i in range(K):
-            self.critic_step(reals[i], numerics[i])
-        self.generator_step(numerics[K - 1], labels)
+            self.critic_step(reals[i], numerics[i], cond=None if conds is None else conds[i])
+        self.generator_step(numerics[K - 1], labels, cond=None if conds is None else conds[K - 1])
 
     # ---- whole-cycle CUDA graph ----
     def capture_cycle(self):

@@ -49,23 +49,27 @@ class GeneratorDecoder(nn.Module):
 
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, noise, emb, *params):
+    def forward(ctx, module, noise, emb, cond, *params):
         eng = module._engine(noise)
         P = R.params_of(module, E.G_PARAM_KEYS + E.G_BUFFER_KEYS)
         eng.bind(E.MOD_G, P, None)
+        if cond is not None:
+            eng.set_condition(R.as_f32c(cond))
         notes, latent = eng.generator_forward(R.as_f32c(noise), R.as_f32c(emb), train=module.training)
         if module.training:
             for bn in (module.decoder.deconv[1], module.decoder.deconv[4]):
                 bn.num_batches_tracked += 1
-        ctx.module, ctx.train = module, module.training
-        ctx.save_for_backward(noise, emb)
+        ctx.module, ctx.train, ctx.has_cond = module, module.training, cond is not None
+        ctx.save_for_backward(*((noise, emb) if cond is None else (noise, emb, cond)))
         return notes, latent
 
     @staticmethod
     def backward(ctx, dnotes, dlatent):
         module = ctx.module
-        noise, emb = ctx.saved_tensors
+        noise, emb = ctx.saved_tensors[:2]
         eng = module._engine(noise)
+        if ctx.has_cond:
+            eng.set_condition(R.as_f32c(ctx.saved_tensors[2]))
         P = R.params_of(module, E.G_PARAM_KEYS + E.G_BUFFER_KEYS)
         G = R.fresh_grads(P, E.G_PARAM_KEYS)
         if ctx.train:      # recompute with batch statistics but WITHOUT advancing the running stats twice
@@ -79,7 +83,7 @@ class _GeneratorFn(torch.autograd.Function):
         demb = eng.generator_backward(dn, R.as_f32c(dlatent) if dlatent is not None else None)
         named = dict(module.named_parameters())
         grads = tuple(G[k] if named[k].requires_grad else None for k in E.G_PARAM_KEYS)
-        return (None, None, demb) + grads
+        return (None, None, demb, None) + grads       # the AE latent is data: no gradient (reference feeds it detached)
 
 
 class Generator(nn.Module):
@@ -102,7 +106,7 @@ class Generator(nn.Module):
     def _engine(self, noise):
         return R.engine_for(noise.device, noise.shape[0], max_notes=self.max_notes, note_dim=self.note_dim,
                             noise_dim=self.noise_dim, latent_dim=self.latent_dim, gen_hidden=self.hidden,
-                            embed_dim=self.numeric_embed_dim)
+                            embed_dim=self.numeric_embed_dim, cond_dim=self.latent_dim if self.mode == "conditioning" else 0)
 
     def forward(self, noise, encoder_latent=None, numeric_embedding=None):
         """noise (B, noise_dim); encoder_latent (B, latent_dim) only in 'conditioning' mode;
@@ -111,8 +115,6 @@ class Generator(nn.Module):
             assert numeric_embedding is not None, "numeric_embedding is required"
         if self.mode == "conditioning":
             assert encoder_latent is not None, "conditioning mode requires encoder latent input"
-            raise NotImplementedError("INTEGRATION_MODE 'conditioning' is a SURVEY.md 8(f) 'next' row; "
-                                      "config/gan_config.yaml trains in 'warm_start'")
         if self.numeric_embed_dim <= 0:
             raise NotImplementedError("the native generator expects the numeric embedding of gan_config.yaml "
                                       "(numeric_embed_dim > 0)")
@@ -120,7 +122,8 @@ class Generator(nn.Module):
             raise NotImplementedError("native generator: max_notes must be a multiple of 8 and note_dim 4")
         names = E.G_PARAM_KEYS
         named = dict(self.named_parameters())
-        return _GeneratorFn.apply(self, noise, numeric_embedding, *[named[k] for k in names])
+        cond = encoder_latent.detach() if self.mode == "conditioning" else None
+        return _GeneratorFn.apply(self, noise, numeric_embedding, cond, *[named[k] for k in names])
 
 
 class _CriticFn(torch.autograd.Function):

@@ -79,6 +79,12 @@ def main(argv=None):
     tr = GanTrainer(cfg, ed_cfg, batch=B // world, precision=os.environ.get("MELOGAN_PRECISION", "fp32"), device=device,
                     ed_state_dict=ed_state, process_group=pg, seed_offset=rank)
     d_notes, d_numeric, d_labels = (torch.from_numpy(a).to(device) for a in (notes, numeric, labels))   # 7 MB: resident
+    d_cond = None
+    if tr.cond_dim:                             # INTEGRATION_MODE 'conditioning': AE latents from src/ae/encode.py
+        feats = os.path.join(cfg.get('SPLITS_DIR', 'data/splits'), Path(cfg['TRAIN_SPLIT']).stem, "encoder_feats.npy")
+        d_cond = torch.from_numpy(np.load(feats).astype(np.float32)).to(device)
+        if d_cond.shape != (len(notes), tr.cond_dim):
+            raise ValueError(f"{feats}: expected shape {(len(notes), tr.cond_dim)}, got {tuple(d_cond.shape)}")
     start_epoch = 1
     if args.resume:
         ck = torch.load(args.resume, map_location=device)
@@ -106,9 +112,10 @@ def main(argv=None):
         for batch_idx in range(steps):
             idx = perm[batch_idx * B:(batch_idx + 1) * B].view(world, -1)[rank]
             real, num, lab = d_notes[idx].contiguous(), d_numeric[idx].contiguous(), d_labels[idx].contiguous()
-            tr.critic_step(real, num)
+            cond = d_cond[idx].contiguous() if d_cond is not None else None
+            tr.critic_step(real, num, cond=cond)
             if (batch_idx + 1) % critic_iters == 0:
-                tr.generator_step(num, lab)
+                tr.generator_step(num, lab, cond=cond)
         d_loss, g_adv, g_emo = tr.epoch_means()
         if rank == 0:
             print(f"Epoch {epoch}/{cfg['EPOCHS']} | D_loss: {d_loss:.4f} | G_adv: {g_adv:.4f} | G_emo: {g_emo:.4f}")

@@ -153,10 +153,10 @@ def fe_forward(P, x, mask1=None, mask2=None, train=True, p_drop=0.2):
     return F.linear(h, P["net.7.weight"], P["net.7.bias"])
 
 
-def gen_forward(P, noise, emb, train=True, bn_state=None, momentum=0.1, keep=None):
-    """Generator in warm_start mode (models.py:108-130): cat[noise, emb] -> NoiseToLatent -> decoder.
+def gen_forward(P, noise, emb, train=True, bn_state=None, momentum=0.1, keep=None, cond=None):
+    """Generator (models.py:108-130): cat[noise, emb (, encoder latent in 'conditioning' mode)] -> NoiseToLatent -> decoder.
     bn_state (dict of running_mean/var tensors) is updated in place in train mode like nn.BatchNorm1d."""
-    x = torch.cat([noise, emb], dim=1)
+    x = torch.cat([noise, emb] + ([cond] if cond is not None else []), dim=1)
     h = F.relu(F.linear(x, P["noise_to_latent.net.0.weight"], P["noise_to_latent.net.0.bias"]))
     latent = F.linear(h, P["noise_to_latent.net.2.weight"], P["noise_to_latent.net.2.bias"])
     y = F.relu(F.linear(latent, P["decoder.pre.0.weight"], P["decoder.pre.0.bias"]))
@@ -503,3 +503,39 @@ def vae_train_step(P, batch, opt_state, beta=10.0, update=True, cfg=AE_CFG, mask
             adamw_update({k: v for k, v in P.items() if not is_buffer(k)}, clipped, opt_state, cfg["LR"], 0.9, 0.999,
                          cfg["WEIGHT_DECAY"])
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-2: Generator in 'conditioning' mode (models.py:99-100,112-126): the AE latent is a third input block
+# ------------------------------------------------------------------------------------------------
+def make_cond_params(seed, cfg=CFG):
+    """Generator parameters with the wider first Linear (noise + embedding + AE latent columns)."""
+    from melogan import synth
+    P = make_params(seed, cfg, fan_in_scale=True)["G"]
+    zin = cfg["NOISE_DIM"] + cfg.get("ENCODER_OUT_DIM", 128) + cfg["LATENT_DIM"]
+    shape = (P["noise_to_latent.net.0.weight"].shape[0], zin)
+    P["noise_to_latent.net.0.weight"] = torch.from_numpy(np.ascontiguousarray(
+        synth.pseudo_normal(seed * 1000 + 901, shape, 1.7 / math.sqrt(3.0 * zin))))
+    return P
+
+
+def make_cond_batch(seed, B, cfg=CFG):
+    from melogan import synth
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return {"noise": t(synth.pseudo_normal(seed * 100 + 1, (B, cfg["NOISE_DIM"]))),
+            "emb": t(synth.pseudo_normal(seed * 100 + 2, (B, cfg.get("ENCODER_OUT_DIM", 128)), 0.5)),
+            "cond": t(synth.pseudo_normal(seed * 100 + 3, (B, cfg["LATENT_DIM"]))),
+            "w_notes": t(synth.pseudo_normal(seed * 100 + 4, (B, cfg["MAX_NOTES"], cfg["NOTE_DIM"]), 1.0 / B)),
+            "w_latent": t(synth.pseudo_normal(seed * 100 + 5, (B, cfg["LATENT_DIM"]), 1.0 / B))}
+
+
+def cond_generator_grads(P, batch):
+    """Forward in train mode and the gradients of sum(notes * w_notes) + sum(latent * w_latent)."""
+    leaves = _leaves(P)
+    emb = batch["emb"].clone().requires_grad_(True)
+    bn_state = {k: v.clone() for k, v in P.items() if is_buffer(k)}
+    notes, latent = gen_forward(leaves, batch["noise"], emb, True, bn_state, cond=batch["cond"])
+    loss = (notes * batch["w_notes"]).sum() + (latent * batch["w_latent"]).sum()
+    g = torch.autograd.grad(loss, list(leaves.values()) + [emb])
+    return {"notes": notes.detach(), "latent": latent.detach(), "demb": g[-1],
+            "grads": dict(zip(leaves.keys(), g[:-1]))}

@@ -236,6 +236,24 @@ def main():
     for k, t in model.state_dict().items():
         if not k.endswith("num_batches_tracked"):
             out[f"ED.final.{k}"] = tstats(t)
+    # ---- 8f-2: the reference's Generator in 'conditioning' mode (models.py:99-100,121-123): forward + all gradients ----
+    Gc = ref_models.Generator(noise_dim=128, latent_dim=64, mode="conditioning", max_notes=512, note_dim=4,
+                              numeric_embed_dim=128)
+    pc = O.make_cond_params(8)
+    missing, unexpected = Gc.load_state_dict(pc, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    Gc.train()
+    cb = O.make_cond_batch(80, 8)
+    emb_c = cb["emb"].clone().requires_grad_(True)
+    notes_c, latent_c = Gc(cb["noise"], cb["cond"], emb_c)
+    loss_c = (notes_c * cb["w_notes"]).sum() + (latent_c * cb["w_latent"]).sum()
+    loss_c.backward()
+    out["COND.notes0"] = notes_c[0].detach().numpy().copy()
+    out["COND.latent"] = latent_c.detach().numpy().copy()
+    out["COND.demb"] = tstats(emb_c.grad)
+    for k, p_ in Gc.named_parameters():
+        out[f"COND.grad.{k}"] = tstats(p_.grad)
+
     # ---- A-12: the reference's VAE (src/ae/model.py) and training iteration (train_ae.py:114-122), 2 steps ----
     ref_ae = _load("ref_ae_model", "src/ae/model.py")
     vp = O.make_vae_params(6)

@@ -230,3 +230,32 @@ def test_trainer_resume_continues_the_run():
             assert torch.allclose(sa[k], sb[k], rtol=0, atol=2e-5), (name, k, (sa[k] - sb[k]).abs().max().item())
     # and it is not trivially equal to the checkpoint itself
     assert not torch.equal(a.state_dict()["D"]["conv.2.weight"], ck["D"]["conv.2.weight"])
+
+
+def test_trainer_conditioning_mode_cycle():
+    """8f-2: INTEGRATION_MODE 'conditioning' through the fused step path: the AE latents of the batch are a third input
+    block of G; a cycle runs, needs the latents, and depends on them."""
+    import os
+    import yaml
+    from melogan.trainer import GanTrainer
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "melo-gan_b200", "config")
+    cfg = yaml.safe_load(open(os.path.join(root, "gan_config.yaml")))
+    ed_cfg = yaml.safe_load(open(os.path.join(root, "ed_config.yaml")))
+    cfg["INTEGRATION_MODE"] = "conditioning"
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    reals = torch.rand((5, B, 512, 4), generator=g, device="cuda") * 2 - 1
+    nums = torch.randn((5, B, 6), generator=g, device="cuda")
+    conds = torch.randn((5, B, cfg["LATENT_DIM"]), generator=g, device="cuda")
+    labels = (torch.arange(B, device="cuda") % 4).to(torch.int64)
+    outs = []
+    for scale in (1.0, 0.0):
+        tr = GanTrainer(cfg, ed_cfg, batch=B, precision="fp32")
+        assert tr.G.input_dim == cfg["NOISE_DIM"] + 128 + cfg["LATENT_DIM"]
+        tr.train_cycle(reals, nums, labels, conds * scale)
+        d_loss, g_adv, g_emo = tr.epoch_means()
+        assert all(map(lambda v: v == v and abs(v) < 1e6, (d_loss, g_adv, g_emo)))
+        outs.append((d_loss, g_adv, g_emo))
+    assert outs[0] != outs[1]
+    with pytest.raises(ValueError):
+        tr.critic_step(reals[0], nums[0])

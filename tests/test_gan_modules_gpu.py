@@ -160,3 +160,44 @@ def test_emotion_forward_and_input_gradient(setup):
     assert_close(dx, dx_ref, GRAD_TOL, "d notes (ED)")
     dx2 = eng.emotion_backward_input(dl.cuda().contiguous(), out=(0.5 * dx).contiguous(), accumulate=True)
     assert_close(dx2, 1.5 * dx_ref, GRAD_TOL, "accumulate")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_generator_conditioning_mode(precision):
+    """8f-2: INTEGRATION_MODE 'conditioning' (models.py:99-100,112-126): G's input row is
+    [noise | numeric embedding | AE latent]; drop-in module forward + backward against the oracle."""
+    import melogan.runtime as R
+    from src.gan.models import Generator
+    B = 8
+    P0 = O.make_cond_params(8)
+    cb = O.make_cond_batch(80, B)
+    ref = O.cond_generator_grads(P0, cb)
+    old = R.PRECISION
+    R.set_precision(precision)
+    try:
+        G = Generator(noise_dim=128, latent_dim=64, mode="conditioning", max_notes=512, note_dim=4, numeric_embed_dim=128)
+        assert G.input_dim == 128 + 128 + 64
+        G.load_state_dict(P0, strict=False)
+        G.cuda().train()
+        emb = cb["emb"].cuda().requires_grad_(True)
+        notes, latent = G(cb["noise"].cuda(), cb["cond"].cuda(), emb)
+        loss = (notes * cb["w_notes"].cuda()).sum() + (latent * cb["w_latent"].cuda()).sum()
+        loss.backward()
+    finally:
+        R.set_precision(old)
+    if precision == "fp32":
+        assert_close(notes, ref["notes"], 1e-5, "notes (conditioning)")
+        assert_close(latent, ref["latent"], 1e-5, "latent (conditioning)")
+        assert_close(emb.grad, ref["demb"], 5e-5, "d embedding (conditioning)")
+        for k, p in G.named_parameters():
+            if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias"):
+                continue
+            assert_close(p.grad, ref["grads"][k], 1e-4, "G grad (conditioning) " + k)
+    else:
+        from gan_testlib import assert_close_l2
+        assert_close_l2(notes, ref["notes"], 1e-2, "notes (conditioning, bf16)")
+        assert_close_l2(latent, ref["latent"], 1e-2, "latent (conditioning, bf16)")
+        assert_close_l2(G.noise_to_latent.net[0].weight.grad, ref["grads"]["noise_to_latent.net.0.weight"], 0.3,
+                        "first Linear grad (conditioning, bf16)")
+    with pytest.raises(AssertionError):
+        G(cb["noise"].cuda(), None, emb)

