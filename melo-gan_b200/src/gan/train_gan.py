@@ -11,6 +11,7 @@ src/gan/train_gan.py; each step body runs as one fused native call through melog
 YAML: MELOGAN_PRECISION=fp32|bf16; under torchrun the batch is sharded over the ranks (NCCL all-reduce).
 """
 import argparse
+import glob
 import os
 from pathlib import Path
 
@@ -27,15 +28,70 @@ def load_config(path):
         return yaml.safe_load(f)
 
 
+_PATH_COLUMNS = ['npz_path', 'processed_file', 'processed', 'full_path', 'filepath', 'file', 'filename', 'file_key']
+
+
+def _resolve_npz_path(processed_dir, raw_cell, row):
+    """Manifest cell -> processed .npz, in the reference's order (src/gan/dataset.py:128-156): the cell itself as a path,
+    then a stem search in PROCESSED_DIR, then the row's npz_path column."""
+    raw_cell = str(raw_cell)
+    candidate = raw_cell if os.path.isabs(raw_cell) else os.path.join(processed_dir, raw_cell)
+    if raw_cell.lower().endswith('.npz') and os.path.exists(candidate):
+        return candidate
+    stem = os.path.splitext(os.path.basename(raw_cell))[0]
+    found = sorted(glob.glob(os.path.join(processed_dir, f"*{stem}*.npz")))
+    if found:
+        return found[0]
+    alt = row.get('npz_path', '')
+    if isinstance(alt, str) and alt:
+        candidate = alt if os.path.isabs(alt) else os.path.join(processed_dir, alt)
+        if os.path.exists(candidate):
+            return candidate
+    return None
+
+
+def load_split_npz(cfg, split_csv):
+    """Slow path of the reference's GANDataset (src/gan/dataset.py:58-112,176-200): one .npz per manifest row with keys
+    notes (MAX_NOTES, 4), numeric_features (padded / truncated to NUMERIC_INPUT_DIM, zeros if absent) and mood (else the
+    manifest's emotion / mood / label column).  Read ONCE into arrays: the step path only ever sees device tensors."""
+    import pandas as pd
+    df = pd.read_csv(split_csv)
+    col = next((c for c in _PATH_COLUMNS if c in df.columns), None)
+    if col is None:
+        raise KeyError(f"Split CSV must contain one of {_PATH_COLUMNS}. Found columns: {list(df.columns)}")
+    processed_dir, nd = cfg.get('PROCESSED_DIR', 'data/processed'), int(cfg.get('NUMERIC_INPUT_DIM', 6))
+    mood_col = next((c for c in ('emotion', 'mood', 'label') if c in df.columns), None)
+    notes, numeric, moods = [], [], []
+    for _, r in df.iterrows():
+        path = _resolve_npz_path(processed_dir, r[col], r)
+        if path is None:
+            print(f"[WARN] Could not find processed .npz for manifest row: {dict(r)}")
+            continue
+        with np.load(path, allow_pickle=True) as data:
+            notes.append(np.asarray(data['notes'], dtype=np.float32))
+            num = np.zeros(nd, dtype=np.float32)
+            if 'numeric_features' in data:
+                v = np.asarray(data['numeric_features'], dtype=np.float32).flatten()
+                num[:min(v.size, nd)] = v[:nd]
+            numeric.append(num)
+            mood = data['mood'].item() if 'mood' in data and np.asarray(data['mood']).ndim == 0 else None
+            moods.append(mood if mood is not None else (r[mood_col] if mood_col else None))
+    if not notes:
+        raise FileNotFoundError(f"no processed .npz resolved from {split_csv} under {processed_dir}")
+    labels = np.array([emotion_to_index(m) for m in moods], dtype=np.int64)
+    return np.stack(notes), np.stack(numeric), labels
+
+
 def load_split_arrays(cfg, split_csv):
     """Fast path of the reference's GANDataset (src/gan/dataset.py:30-56): <SPLITS_DIR>/<split>/{notes,emotion,
-    numeric_features}.npy.  The per-file .npz path is the data-loading row of SURVEY.md 8(f) and is not built."""
+    numeric_features}.npy; without them, the per-file .npz path (load_split_npz)."""
     splits_dir = cfg.get('SPLITS_DIR', 'data/splits')
     name = Path(split_csv).stem
     base = os.path.join(splits_dir, name)
     paths = [os.path.join(base, f) for f in ("notes.npy", "emotion.npy", "numeric_features.npy")]
     if not all(os.path.exists(p) for p in paths):
-        raise FileNotFoundError(f"expected pre-saved arrays {paths} (the .npz-per-file loader is out of scope here)")
+        print(f"[INFO] Loading data by reading individual .npz files for split: {name}")
+        return load_split_npz(cfg, split_csv)
     notes, emotions, numeric = (np.load(p, allow_pickle=True) for p in paths)
     if not (len(notes) == len(emotions) == len(numeric)):
         raise ValueError("NPY file length mismatch (notes, emotions, numeric_features)")

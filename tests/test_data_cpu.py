@@ -1,0 +1,60 @@
+"""the on-disk formats either side of the step -- the .npy fast path and the per-file .npz slow path of the
+reference's GANDataset (src/gan/dataset.py:30-56,58-112,176-200) -- read into the arrays the trainer keeps resident."""
+import os
+
+import numpy as np
+import pytest
+
+from src.gan.train_gan import load_split_arrays, load_split_npz
+
+
+def _write_split(tmp, n=6):
+    rng = np.random.default_rng(1)
+    proc = tmp / "processed"
+    proc.mkdir()
+    rows, want = ["filename,emotion"], []
+    emos = ["happy", "sad", "angry", "calm", "sad", "happy"]
+    for i in range(n):
+        notes = rng.uniform(-1, 1, (512, 4)).astype(np.float32)
+        kw = {"notes": notes, "tempo": 120.0, "filename": f"song{i}.mid"}
+        if i % 3 != 2:
+            kw["numeric_features"] = rng.normal(size=6 if i % 2 == 0 else 4).astype(np.float32)   # 4 -> zero-padded to 6
+        if i == 1:
+            kw["mood"] = "calm"                       # the archive's own mood wins over the manifest column
+        np.savez(proc / f"song{i}_processed.npz", **kw)
+        rows.append(f"song{i}.mid,{emos[i]}")
+        want.append((notes, kw.get("numeric_features"), "calm" if i == 1 else emos[i]))
+    (tmp / "splits").mkdir()
+    csv = tmp / "splits" / "train_split.csv"
+    csv.write_text("\n".join(rows) + "\n")
+    return {"PROCESSED_DIR": str(proc), "SPLITS_DIR": str(tmp / "splits"), "NUMERIC_INPUT_DIM": 6}, str(csv), want
+
+
+def test_npz_slow_path_matches_the_archives(tmp_path):
+    cfg, csv, want = _write_split(tmp_path)
+    notes, numeric, labels = load_split_npz(cfg, csv)
+    assert notes.shape == (6, 512, 4) and numeric.shape == (6, 6) and labels.dtype == np.int64
+    idx = {"happy": 0, "sad": 1, "angry": 2, "calm": 3}
+    for i, (n, f, mood) in enumerate(want):
+        np.testing.assert_array_equal(notes[i], n)
+        exp = np.zeros(6, np.float32)
+        if f is not None:
+            exp[:f.size] = f
+        np.testing.assert_array_equal(numeric[i], exp)
+        assert labels[i] == idx[mood]
+
+
+def test_fast_path_is_preferred_and_falls_back(tmp_path):
+    cfg, csv, want = _write_split(tmp_path)
+    a = load_split_arrays(cfg, csv)                        # no .npy arrays yet -> slow path
+    d = tmp_path / "splits" / "train_split"
+    d.mkdir()
+    np.save(d / "notes.npy", a[0][::-1].copy())
+    np.save(d / "emotion.npy", np.array(["calm"] * 6))
+    np.save(d / "numeric_features.npy", a[1])
+    b = load_split_arrays(cfg, csv)                        # pre-saved arrays win (dataset.py:30-56)
+    np.testing.assert_array_equal(b[0], a[0][::-1])
+    assert (b[2] == 3).all()
+    (tmp_path / "splits" / "bad.csv").write_text("x,y\n1,2\n")
+    with pytest.raises(KeyError):
+        load_split_npz(cfg, str(tmp_path / "splits" / "bad.csv"))
