@@ -1,5 +1,5 @@
 """Smoke check of the GAN hot path: one small critic step and one generator step on cuda:0 (fp32 mode and bf16
-tensor-core mode) compared with the oracle.  Called by __graft_entry__.smoke(); the oracle is the checker only."""
+tensor-core mode) compared with the oracle.  Called by __graft_entry__.smoke() only (kept under tests/: the product package never imports oracle/)."""
 import torch
 
 
