@@ -15,9 +15,16 @@
 //     128 B = 64 channels, one row per position); split over CTAs along the positions, fp32 atomics
 //     into the reference-layout gradient.
 //
-// Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  3-stage smem ring (full/empty mbarriers),
-// tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
+// Two kernels run tc_tapgemm.  tc_tapgemm_kernel: one tile per CTA (192 threads: warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer, warps 2..5 = epilogue, TMEM lane quarter = warp_id % 4), 3-stage smem ring (full/empty
+// mbarriers), tcgen05.commit releases a stage back to the producer and finally signals the epilogue.
+// tc_tapgemm_ws_kernel (the one that carries the training cycle): weight-stationary and persistent -- the packed weights
+// of ALL taps of one 64/128-wide output slab stay in shared memory, activation tiles stream through a ring, taps of one
+// plane share a tile with a halo (row-offset descriptors), two TMEM accumulators, one epilogue warpgroup per 32
+// accumulator columns, results leave through a 128B-swizzled staging tile and TMA bulk stores, mask tiles arrive by TMA.
+// The same kernels run the float32 Linears of bf16 mode as kind::tf32 (TF32 template flag: fp32 operands straight from
+// HBM, 32 elements per 128-byte k-block).  MELOGAN_TRACE=1 prints one line per launch; MELOGAN_TC_DEBUG is an ablation
+// switch for profiling (bits: 1 no stores, 2 no MMA, 4 no activation loads, 8 no mask loads).
 #pragma once
 #include <cuda.h>
 
