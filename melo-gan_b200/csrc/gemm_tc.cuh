@@ -211,6 +211,7 @@ struct TcTapArgs {
     float alpha; int accumulate;
     int tma_mask;                       // ... and the mask tile (f' of the saved activation) arrives by TMA as well
     int tma_store;                      // weight-stationary kernel: tiles leave through shared memory + TMA bulk stores
+    int reverse;                        // walk the M tiles from the last to the first (see run_tc_tap)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
 
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     const uint32_t tmem0 = H.tmem_base;
 
     auto tile_coords = [&](int tile, int& b0, int& m0) {
+        if (P.reverse) tile = mtiles - 1 - tile;
         if (P.mpt == kTileM) { const int tm = P.Mper / kTileM; b0 = tile / tm; m0 = (tile % tm) * kTileM; }
         else { b0 = tile * P.bpt; m0 = 0; }
     };
@@ -1075,6 +1077,12 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
     if (!am_halo) build_tap_groups(a, 0);
+    {   // Consecutive layers are 0.4-0.8 GB producer -> consumer hand-offs through a 126 MB L2: the consumer starts where
+        // the producer stopped (its last tiles are still resident) if successive launches walk the rows in opposite order.
+        static const bool snake = getenv("MELOGAN_NO_SNAKE") == nullptr;
+        static unsigned launch_no = 0;
+        a.reverse = snake ? (int)(launch_no++ & 1u) : 0;
+    }
     { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = dbg; }
     const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
