@@ -1243,7 +1243,11 @@ int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
     if (nrows <= 0) return 1;
     const int BNK = (P.K % 128 == 0) ? 128 : 64;
     const int tiles = (P.N / 128) * P.ntaps * (P.K / BNK);
-    long long want = ((long long)num_sms() * 3 + tiles - 1) / tiles;
+    // one full wave: as many CTAs as the GPU holds at once (2 per SM at BNK = 128, 3 at 64, by shared memory), never one
+    // more -- a 445th CTA on 444 slots runs alone after everybody else and doubles the kernel
+    const size_t smem_cta = (BNK == 128 ? sizeof(WgradSmem<128>) : sizeof(WgradSmem<64>)) + 1024;
+    const long long cap = (long long)num_sms() * (long long)((227 * 1024) / smem_cta);
+    long long want = cap / tiles;
     long long maxs = (nrows + 255) / 256;                    // at least 4 chunks per CTA
     long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
     if (splits > 65535) splits = 65535;
