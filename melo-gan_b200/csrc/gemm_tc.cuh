@@ -1247,7 +1247,8 @@ int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
     // more -- a 445th CTA on 444 slots runs alone after everybody else and doubles the kernel
     const size_t smem_cta = (BNK == 128 ? sizeof(WgradSmem<128>) : sizeof(WgradSmem<64>)) + 1024;
     const long long cap = (long long)num_sms() * (long long)((227 * 1024) / smem_cta);
-    long long want = cap / tiles;
+    static const int waves = getenv("MELOGAN_WGRAD_WAVES") ? atoi(getenv("MELOGAN_WGRAD_WAVES")) : 1;
+    long long want = cap * (waves > 0 ? waves : 1) / tiles;
     long long maxs = (nrows + 255) / 256;                    // at least 4 chunks per CTA
     long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
     if (splits > 65535) splits = 65535;
