@@ -53,13 +53,13 @@ __device__ __forceinline__ int trunc_clip(float x, int lo, int hi) {
     return min(max(v, lo), hi);
 }
 
-__global__ void __launch_bounds__(kThreads, 2) extract_notes_gan_kernel(GanParams P) {
+__global__ void __launch_bounds__(kThreads, 4) extract_notes_gan_kernel(GanParams P) {
+    // Only the onset clock lives in shared memory (2 KB per roll): the serial phase 2 keeps one lane per roll busy, so its
+    // throughput is the number of rolls resident per SM; pitch / velocity / duration are recomputed in phase 3 from the
+    // rolls (an L2 hit: the tile was read a few microseconds earlier) instead of being parked in 6 more bytes per row.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_tex = reinterpret_cast<float*>(smem_raw);                       // [16][513] step -> exclusive clock
-    float* s_dur = s_tex + kRollsPerCta * kTexStride;                        // [16][512] duration, <0 = floor
-    unsigned short* s_pv = reinterpret_cast<unsigned short*>(s_dur + kRollsPerCta * kMaxRows);  // pitch|vel<<8
-    int* s_ndbl = reinterpret_cast<int*>(s_pv + kRollsPerCta * kMaxRows);    // [16] rows on the float64 clock
-    int* s_bad = s_ndbl + kRollsPerCta;                                      // [16]
+    int* s_ndbl = reinterpret_cast<int*>(s_tex + kRollsPerCta * kTexStride); // [16] rows on the float64 clock
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = P.nrows;
@@ -71,10 +71,8 @@ __global__ void __launch_bounds__(kThreads, 2) extract_notes_gan_kernel(GanParam
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long roll0 = tile * kRollsPerCta;
         const int nr = (int)min((long long)kRollsPerCta, P.nrolls - roll0);
-        if (tid < kRollsPerCta) s_bad[tid] = 0;
-        __syncthreads();
 
-        // ---- phase 1: per-row arithmetic, rows of the tile are contiguous in HBM ----
+        // ---- phase 1: the step column, rows of the tile are contiguous in HBM ----
         const int total = nr * T;
         const float4* src = P.rolls + roll0 * T;
 #pragma unroll 4
@@ -83,23 +81,6 @@ __global__ void __launch_bounds__(kThreads, 2) extract_notes_gan_kernel(GanParam
             const int r = idx / T, i = idx - r * T;
             const float s32 = unit_to_beats(q.w);
             s_tex[r * kTexStride + i] = (s32 > floor_step32) ? s32 : -1.0f;  // max(0.1, .) keeps python 0.1
-            const float d32 = unit_to_beats(q.z);
-            s_dur[r * kMaxRows + i] = (d32 > floor_dur32) ? d32 : -1.0f;
-            unsigned short code = 0xFFFFu;  // gated
-            if (!(q.y < thr32)) {           // utils.py:135; NaN velocity is not gated
-                const float pf = __fmul_rn(__fadd_rn(q.x, 1.0f), 63.5f);
-                const float vf = __fadd_rn(60.0f, __fmul_rn(__fdiv_rn(__fsub_rn(q.y, thr32), vrange32), 67.0f));
-                if (!isfinite(pf) || !isfinite(vf)) {
-                    s_bad[r] = 1;  // int(nan)/int(inf) raises in the reference
-                    code = 0;
-                } else {
-                    const int pc = trunc_clip(pf, 36, 96);
-                    const int pit = (pc / 12) * 12 + P.lut[pc % 12];
-                    const int vel = trunc_clip(vf, 0, 127);
-                    code = (unsigned short)(pit | (vel << 8));
-                }
-            }
-            s_pv[r * kMaxRows + i] = code;
         }
         __syncthreads();
 
@@ -123,19 +104,40 @@ __global__ void __launch_bounds__(kThreads, 2) extract_notes_gan_kernel(GanParam
         }
         __syncthreads();
 
-        // ---- phase 3: compaction + onset/offset, one warp per roll ----
+        // ---- phase 3: per-row pitch / velocity / duration, compaction, onset / offset; one warp per roll ----
         for (int r = warp; r < nr; r += kThreads / 32) {
             const long long obase = (roll0 + r) * (long long)T;
             const int ndbl = s_ndbl[r];
             int base = 0;
+            unsigned bad_any = 0;
             for (int i0 = 0; i0 < T; i0 += 32) {
                 const int i = i0 + lane;
-                const unsigned short code = (i < T) ? s_pv[r * kMaxRows + i] : (unsigned short)0xFFFFu;
+                unsigned short code = 0xFFFFu;  // gated (or past the end)
+                float d32 = -1.0f;
+                bool bad = false;
+                if (i < T) {
+                    const float4 q = __ldg(src + r * T + i);
+                    const float dd = unit_to_beats(q.z);
+                    d32 = (dd > floor_dur32) ? dd : -1.0f;
+                    if (!(q.y < thr32)) {           // utils.py:135; NaN velocity is not gated
+                        const float pf = __fmul_rn(__fadd_rn(q.x, 1.0f), 63.5f);
+                        const float vf = __fadd_rn(60.0f, __fmul_rn(__fdiv_rn(__fsub_rn(q.y, thr32), vrange32), 67.0f));
+                        if (!isfinite(pf) || !isfinite(vf)) {
+                            bad = true;  // int(nan)/int(inf) raises in the reference
+                            code = 0;
+                        } else {
+                            const int pc = trunc_clip(pf, 36, 96);
+                            const int pit = (pc / 12) * 12 + P.lut[pc % 12];
+                            const int vel = trunc_clip(vf, 0, 127);
+                            code = (unsigned short)(pit | (vel << 8));
+                        }
+                    }
+                }
+                bad_any |= __ballot_sync(0xffffffffu, bad);
                 const bool keep = code != 0xFFFFu;
                 const unsigned ball = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     const int slot = base + __popc(ball & ((1u << lane) - 1u));
-                    const float d32 = s_dur[r * kMaxRows + i];
                     double st, en;
                     if (i < ndbl) {
                         const double t64 = c_floor_clock[i];
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) extract_notes_gan_kernel(GanParam
                 }
                 base += __popc(ball);
             }
-            if (lane == 0) P.counts[roll0 + r] = s_bad[r] ? -1 : base;
+            if (lane == 0) P.counts[roll0 + r] = bad_any ? -1 : base;
         }
         __syncthreads();
     }
@@ -186,8 +188,7 @@ __global__ void __launch_bounds__(256) extract_notes_abs_kernel(const float4* __
     }
 }
 
-constexpr size_t kGanSmem = sizeof(float) * kRollsPerCta * kTexStride + sizeof(float) * kRollsPerCta * kMaxRows +
-                            sizeof(unsigned short) * kRollsPerCta * kMaxRows + sizeof(int) * 2 * kRollsPerCta;
+constexpr size_t kGanSmem = sizeof(float) * kRollsPerCta * kTexStride + sizeof(int) * kRollsPerCta;
 
 int init_once() {
     static int done = 0;  // 0 = not yet, 1 = ok
@@ -242,7 +243,7 @@ extern "C" int mg_extract_notes_gan(const float* rolls, long long nrolls, int nr
     snap_lut(allowed_mask, P.lut);
     P.counts = counts; P.pitch = pitch; P.velocity = velocity; P.start = start; P.end = end;
     const long long ntiles = (nrolls + kRollsPerCta - 1) / kRollsPerCta;
-    const int grid = (int)((ntiles < (long long)mg::num_sms() * 2) ? ntiles : (long long)mg::num_sms() * 2);
+    const int grid = (int)((ntiles < (long long)mg::num_sms() * 4) ? ntiles : (long long)mg::num_sms() * 4);
     mg::ProbeScope probe(mg::PROBE_NOTES, 0.0, (double)nrolls * (nrows * 16.0 + 4.0), mg::as_stream(stream));
     extract_notes_gan_kernel<<<grid, kThreads, kGanSmem, mg::as_stream(stream)>>>(P);
     MG_LAUNCH_OK();
