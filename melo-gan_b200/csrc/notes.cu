@@ -53,7 +53,7 @@ __device__ __forceinline__ int trunc_clip(float x, int lo, int hi) {
     return min(max(v, lo), hi);
 }
 
-__global__ void __launch_bounds__(kThreads, 4) extract_notes_gan_kernel(GanParams P) {
+__global__ void __launch_bounds__(kThreads, 6) extract_notes_gan_kernel(GanParams P) {
     // Only the onset clock lives in shared memory (2 KB per roll): the serial phase 2 keeps one lane per roll busy, so its
     // throughput is the number of rolls resident per SM; pitch / velocity / duration are recomputed in phase 3 from the
     // rolls (an L2 hit: the tile was read a few microseconds earlier) instead of being parked in 6 more bytes per row.
@@ -243,7 +243,7 @@ extern "C" int mg_extract_notes_gan(const float* rolls, long long nrolls, int nr
     snap_lut(allowed_mask, P.lut);
     P.counts = counts; P.pitch = pitch; P.velocity = velocity; P.start = start; P.end = end;
     const long long ntiles = (nrolls + kRollsPerCta - 1) / kRollsPerCta;
-    const int grid = (int)((ntiles < (long long)mg::num_sms() * 4) ? ntiles : (long long)mg::num_sms() * 4);
+    const int grid = (int)((ntiles < (long long)mg::num_sms() * 6) ? ntiles : (long long)mg::num_sms() * 6);
     mg::ProbeScope probe(mg::PROBE_NOTES, 0.0, (double)nrolls * (nrows * 16.0 + 4.0), mg::as_stream(stream));
     extract_notes_gan_kernel<<<grid, kThreads, kGanSmem, mg::as_stream(stream)>>>(P);
     MG_LAUNCH_OK();
