@@ -2,7 +2,8 @@
 """bench.py -- GAN train-step throughput of the B200-native Melo-GAN hot path.
 
     python bench.py --gpus 1 --steps 10 --warmup 3            (N > 1: launched by torch.distributed.run)
-    python bench.py --impl reference ...                        (the reference's CPU path, oracle port)
+    python bench.py --impl reference ...                        (the reference's CPU path: unmodified modules under
+                                                                 baseline/_ref, else the oracle port)
 
 One "step" is one training CYCLE of the reference loop (src/gan/train_gan.py:168-251 with
 CRITIC_ITERS=5): 5 critic steps on 5 fresh batches of B real rolls each + 1 generator step, Adam
@@ -70,27 +71,51 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_cycle_baseline(budget_s=18.0, B=32):
-    """The reference's CPU training cycle (oracle port: same ATen ops, same order, see oracle/gan_oracle.py)
-    on all host cores, bounded to about `budget_s` seconds."""
+def _ref_cycle():
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_cycle
+    return ref_cycle
+
+
+def cpu_reference_cycles(budget_s, max_cycles, B=32, warmup=1):
+    """The reference's CPU training cycle on all host cores, bounded to about `budget_s` seconds.
+    kind "reference": the UNMODIFIED reference modules under baseline/_ref (staged by __graft_entry__.build()) driven
+    by the loop body of src/gan/train_gan.py:183-251 (baseline/ref_cycle.py); kind "port": the oracle's restatement
+    of the same ATen calls (oracle/gan_oracle.py) when the reference sources did not travel."""
     import torch
-    from oracle import gan_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = O.make_params(1)
-    batches = [O.make_batch(900 + i, B) for i in range(5)]
-    st_d, st_g = {}, {}
-    O.train_cycle(params, batches, st_d, st_g)          # warm-up cycle
+    rcm = _ref_cycle()
+    if rcm.available():
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            rc = rcm.ReferenceCycle("cpu")
+        batches, labels = rc.batches(B)
+        step = lambda: rc.cycle(batches, labels)
+        kind = "reference"
+    else:
+        from oracle import gan_oracle as O
+        params = O.make_params(1)
+        batches = [O.make_batch(900 + i, B) for i in range(5)]
+        st_d, st_g = {}, {}
+        step = lambda: O.train_cycle(params, batches, st_d, st_g)
+        kind = "port"
+    for _ in range(max(1, warmup)):
+        step()
     n, t0 = 0, time.perf_counter()
     while True:
-        O.train_cycle(params, batches, st_d, st_g)
+        step()
         n += 1
         el = time.perf_counter() - t0
-        if el > budget_s or n >= 50:
+        if el > budget_s or n >= max_cycles:
             break
-    return {"value": 5 * B * n / el, "unit": "rolls/s", "cores": cores, "kind": "port",
+    return {"value": 5 * B * n / el, "unit": "rolls/s", "cores": cores, "kind": kind,
             "sample": f"{n} cycles of 5 D-steps + 1 G-step at B={B} (config/gan_config.yaml BATCH_SIZE), "
-                      f"torch {torch.__version__} CPU, {cores} threads, {el:.1f} s", "ms_per_cycle": 1e3 * el / n}
+                      f"torch {torch.__version__} CPU, {cores} threads, {el:.1f} s", "ms_per_cycle": 1e3 * el / n}, n, el
+
+
+def cpu_cycle_baseline(budget_s=18.0, B=32):
+    return cpu_reference_cycles(budget_s, 50, B)[0]
 
 
 def run_reference(args):
@@ -98,29 +123,156 @@ def run_reference(args):
     if rank != 0:
         return
     B = 32
-    import torch
-    from oracle import gan_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    params = O.make_params(1)
-    batches = [O.make_batch(900 + i, B) for i in range(5)]
-    st_d, st_g = {}, {}
-    for _ in range(max(1, min(args.warmup, 2))):
-        O.train_cycle(params, batches, st_d, st_g)
-    steps = max(1, min(args.steps, 12))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.train_cycle(params, batches, st_d, st_g)
-    el = time.perf_counter() - t0
-    v = 5 * B * steps / el
+    cb, steps, el = cpu_reference_cycles(60.0, max(1, min(args.steps, 40)), B, warmup=max(1, min(args.warmup, 3)))
+    v = cb["value"]
+    what = "unmodified reference modules, baseline/_ref" if cb["kind"] == "reference" else "oracle port"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rolls/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"GAN cycle (5 D + 1 G), config/gan_config.yaml, B={B}, reference CPU path (oracle port)"},
-            "cpu_baseline": {"value": v, "unit": "rolls/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} cycles at B={B}, {cores} threads"},
+            "config": {"workload": f"GAN cycle (5 D + 1 G), config/gan_config.yaml, B={B}, reference CPU path ({what})"},
+            "cpu_baseline": {"value": v, "unit": "rolls/s", "cores": cb["cores"], "kind": cb["kind"],
+                             "sample": f"{steps} cycles at B={B}, {cb['cores']} threads"},
             "e2e": {"value": v, "unit": "rolls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# extra records of the default single-GPU line
+# ------------------------------------------------------------------------------------------------
+def probe_family(L, family, fn):
+    import ctypes
+    L.mg_probe_begin(family)
+    fn()
+    pr = (ctypes.c_double * 4)()
+    L.mg_probe_end(pr)
+    return {"launches": pr[0], "ms": pr[1], "flops": pr[2], "bytes": pr[3]}
+
+
+def hbm_record(name, pr, peak_gbs, note):
+    gbs = pr["bytes"] / (pr["ms"] * 1e-3) / 1e9 if pr["ms"] > 0 else 0.0
+    return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s",
+            "frac": gbs / peak_gbs if peak_gbs else None, "launches_per_step": pr["launches"], "kernel_ms_per_step": pr["ms"],
+            "algorithmic_bytes_per_step": pr["bytes"], "note": note}
+
+
+def notes_records(L, dev, peak_gbs, R=262144):
+    """Config #5 kernels: N-1 (src/gan/utils.py:130-155) and N-2 (tools/roll_to_midi.py:10-21) over R resident rolls
+    (2 GiB >> L2), CUDA events around 10 launches each."""
+    import torch
+    from melogan import notes as N
+
+    def timed(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+
+    rolls = torch.rand(R, 512, 4, device=dev) * 2 - 1
+    out = N.extract_notes_gan(rolls, 140.0, "major", 0, check=False)
+    emitted = int(out.counts.sum().item())
+    del out
+    # per-launch output buffers are allocated by the wrapper (cached by torch's allocator after the warm-up)
+    ms1 = timed(lambda: N.extract_notes_gan(rolls, 140.0, "major", 0, check=False))
+    b1 = R * (8192 + 4) + emitted * 18
+    rolls.mul_(50).add_(50)
+    ms2 = timed(lambda: N.extract_notes_abs(rolls, check=False))
+    b2 = R * (8192 + 9216)
+    del rolls
+    torch.cuda.empty_cache()
+    rec = lambda name, ms, b, note: {"kernel": name, "rolls": R, "ms": ms, "rolls_per_s": R / ms * 1e3, "bound": "hbm",
+                                     "achieved": b / ms / 1e6, "peak": peak_gbs, "unit": "GB/s", "frac": b / ms / 1e6 / peak_gbs,
+                                     "algorithmic_bytes": b, "note": note}
+    return [rec("extract_notes_gan_kernel (N-1)", ms1, b1, f"8192 B read + 4 B count per roll + 18 B per emitted note "
+                                                             f"({emitted / R:.0f} notes per roll on U(-1,1) rolls)"),
+            rec("extract_notes_abs_kernel (N-2)", ms2, b2, "8192 B read + 9216 B written per roll")]
+
+
+def parity_check(tr, cfg, ed_cfg, reals, numerics, labels, dev):
+    """One critic step and one generator step of the BENCHED configuration (bf16 mode, bench batch, trained-for-a-few-
+    steps parameters) against this engine's own fp32 parity mode (CUDA-core kernels, pinned to the oracle at 1e-5 by
+    tests/) on identical parameters, inputs and injected noise / alpha / dropout masks.  north_star: 1e-2 in bf16 mode."""
+    import torch
+    from melogan.trainer import GanTrainer
+    B = tr.B
+    g = torch.Generator(device=dev).manual_seed(1234)
+    h = tr.mask1.shape[1], tr.mask2.shape[1]
+    noise = torch.randn((B, cfg['NOISE_DIM']), generator=g, device=dev)
+    alpha = torch.rand(B, generator=g, device=dev)
+    m1 = (torch.rand((B, h[0]), generator=g, device=dev) < tr.keep).float()
+    m2 = (torch.rand((B, h[1]), generator=g, device=dev) < tr.keep).float()
+    real, numeric = reals[0][0].contiguous(), numerics[0][0].contiguous()
+    bns = (tr.G.decoder.deconv[1], tr.G.decoder.deconv[4])
+    saved = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
+
+    def restore():
+        for bn, (rm, rv) in zip(bns, saved):
+            bn.running_mean.copy_(rm); bn.running_var.copy_(rv)
+
+    def one(engine):
+        md = engine.critic_step(real, numeric, noise, alpha, m1, m2).clone()
+        restore()
+        mg = engine.generator_step(numeric, noise, labels, m1, m2).clone()
+        restore()
+        torch.cuda.synchronize(dev)
+        return [float(x) for x in md.cpu()] + [float(x) for x in mg.cpu()]
+
+    got = one(tr.engine)
+    tr.engine.close()                                 # the fp32 context needs the memory
+    torch.cuda.empty_cache()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        tr32 = GanTrainer(cfg, ed_cfg, batch=B, precision="fp32", device=dev, modules=(tr.E_num, tr.G, tr.D, tr.ED))
+    want = one(tr32.engine)
+    tr32.engine.close()
+    torch.cuda.empty_cache()
+    names = ["loss_d", "gp", "d_real", "d_fake", "g_adv", "g_emo"]
+    rec, ok = {}, True
+    for n, a, b in zip(names, got, want):
+        denom = max(abs(b), 1e-2 if n in ("d_real", "d_fake", "g_adv") else 1e-6)   # the critic scores start near 0
+        r = abs(a - b) / denom
+        rec[n] = {"bf16": a, "fp32": b, "rel": r}
+        if n in ("loss_d", "gp", "g_emo") and not r <= 1e-2:
+            ok = False
+    rec["tolerance"] = 1e-2
+    rec["ok"] = ok
+    rec["what"] = f"one critic + one generator step at B={B}: bf16 tensor-core mode vs the engine's fp32 parity mode, same inputs"
+    return rec
+
+
+def stock_torch_yardstick(dev, B, budget_cycles=3):
+    """The reference modules run by stock PyTorch eager (cuDNN / cuBLAS) on THIS GPU, same cycle, same batch:
+    the "reference's Blackwell kernels" this framework has to beat (SURVEY.md 8d / BASELINE.md 3.4)."""
+    import torch
+    rcm = _ref_cycle()
+    if not rcm.available():
+        return {"unavailable": "reference sources not staged under baseline/_ref"}
+    out = {"B": B, "torch": torch.__version__}
+    import contextlib
+    for name, ac in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        b = B
+        while True:
+            try:
+                with contextlib.redirect_stdout(sys.stderr):
+                    r = rcm.time_cycles(str(dev), b, steps=budget_cycles, warmup=1, autocast=ac)
+                out[name] = {"rolls_per_s": r["rolls_per_s"], "ms_per_cycle": r["ms_per_cycle"], "B": b}
+                break
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                b //= 2
+                if b < 256:
+                    out[name] = {"unavailable": "out of memory"}
+                    break
+            except Exception as e:       # e.g. an op without a bf16 double-backward kernel
+                out[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+                break
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -135,6 +287,8 @@ def main():
                     help="bf16 = tcgen05 tensor-core mode (north_star tolerance 1e-2); fp32 = CUDA-core parity mode (1e-5)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the HBM-kernel, note-extraction, parity and yardstick records")
+    ap.add_argument("--no-yardstick", action="store_true", help="skip the stock-PyTorch-eager run of the reference modules")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -249,13 +403,11 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
 
     # per-kernel roofline of the dominant kernel family, measured live with CUDA events (eager pass)
-    family = 3 if args.precision == "bf16" else 1
-    L.mg_probe_begin(family)
-    tr.train_cycle(reals[0], numerics[0], labels)
     import ctypes
-    pr = (ctypes.c_double * 4)()
-    L.mg_probe_end(pr)
-    probe_launches, probe_ms, probe_flops, probe_bytes = pr[0], pr[1], pr[2], pr[3]
+    family = 3 if args.precision == "bf16" else 1
+    eager_cycle = lambda: tr.train_cycle(reals[0], numerics[0], labels)
+    pr = probe_family(L, family, eager_cycle)
+    probe_launches, probe_ms, probe_flops, probe_bytes = pr["launches"], pr["ms"], pr["flops"], pr["bytes"]
     if family == 3 and probe_launches == 0:      # bf16 mode without tensor-core kernels yet
         family = 1
     peaks = {}
@@ -270,12 +422,44 @@ def main():
     # the same launches against the HBM roofline: algorithmic bytes (activation once + output + mask/derivative tiles)
     peak_gbs = float(peaks.get("hbm_gbs", 6546.6))
     achieved_gbs = (probe_bytes / (probe_ms * 1e-3) / 1e9) if probe_ms > 0 else 0.0
-    traffic = None
+    # DRAM traffic of the SAME launches: profiles/r02_tc_traffic.json holds, per layer of the cycle, the dram read+write
+    # bytes of one `ncu --set full` capture of scripts/bench_layers.py next to that launch's algorithmic bytes
+    traffic, traffic_note = None, "no ncu capture committed"
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_tc_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch_avg")
+        with open(os.path.join(ROOT, "profiles", "r02_tc_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch_cycle_weighted")
+        traffic_note = (f"dram read+write bytes per launch, cycle-weighted over the {tj.get('launches_per_cycle')} tap-GEMM launches of "
+                        f"one cycle (ncu --set full of scripts/bench_layers.py, profiles/r02_tc_traffic.json); algorithmic bytes of the "
+                        f"same launches = {tj.get('algorithmic_bytes_per_launch_cycle_weighted'):.3e} per launch "
+                        f"(ratio {tj.get('ratio'):.2f}); live probe of this run: {probe_bytes / max(probe_launches, 1):.3e}")
     except Exception:
         pass
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # HBM-class kernels north_star names: fused Adam, the element-wise / reduction family, note extraction
+        hbm = []
+        pa = probe_family(L, 6, eager_cycle)
+        hbm.append(hbm_record("adam_kernel (fused Adam over the flat groups)", pa, peak_gbs, "28 B per parameter and step"))
+        pe = probe_family(L, 7, eager_cycle)
+        hbm.append(hbm_record("element-wise / reduction family (colreduce, BatchNorm apply + backward, pooling, row broadcast)",
+                              pe, peak_gbs, "one read (+ one write) of the activation per kernel"))
+        extra["roofline_hbm"] = hbm
+        try:
+            extra["notes"] = notes_records(L, dev, peak_gbs)
+        except Exception as e:
+            extra["notes"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            extra["parity_check"] = parity_check(tr, cfg, ed_cfg, reals, numerics, labels, dev)
+        except Exception as e:
+            extra["parity_check"] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+        del reals, numerics
+        torch.cuda.empty_cache()
+        if not args.no_yardstick:
+            try:
+                extra["stock_torch_eager_same_gpu"] = stock_torch_yardstick(dev, B)
+            except Exception as e:
+                extra["stock_torch_eager_same_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     rolls_per_step = K * B * world
     value = rolls_per_step / (ms_dev / args.steps * 1e-3)
@@ -300,15 +484,14 @@ def main():
                                                    3: "tc_gemm_kernel (tcgen05 bf16 implicit GEMM)"}[family],
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_note": "dram read+write bytes per launch, mean over the ncu --set full capture in profiles/ "
-                                     "(r01_tc_traffic.json); algorithmic bytes per launch = "
-                                     f"{probe_bytes / max(probe_launches, 1):.3e}",
+                     "traffic_note": traffic_note,
                      "launches_per_step": probe_launches, "kernel_ms_per_step": probe_ms,
                      "share_of_step": probe_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
                      "hbm_view": {"achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s",
                                   "frac": achieved_gbs / peak_gbs if peak_gbs else None}},
         "whole_step_model_tflops": value * MFLOP_PER_ROLL * 1e6 / 1e12 / max(world, 1),
     }
+    line.update(extra)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_cycle_baseline()

@@ -274,6 +274,45 @@ int mg_rng_fill_counter(float* out, long long n, int kind, float p, unsigned lon
                         const unsigned long long* counter_dev, unsigned long long counter_mul, void* stream);
 int mg_counter_add(unsigned long long* counter_dev, unsigned long long inc, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-layer harness (tests/test_tc_layers_gpu.py, scripts/bench_layers.py): runs ONE contraction of the
+ * training cycle -- exactly the call the step bodies make for that layer (same dispatch, same kernel
+ * selection) -- on caller-supplied device tensors, so that every (layer shape x kernel variant) of the
+ * benched configuration can be pinned against a float64 contraction of the same operands and timed alone.
+ * The reference computes these with torch's conv1d / conv_transpose1d / linear and their autograd:
+ * src/gan/models.py:20-29,46-83,140-169, src/emotion_discriminator/ed_model.py:35-69.
+ *
+ * op: 0 conv1d forward          in [R, Lin, Cin] -> out [R, Lin/stride, Cout]; W [Cout][Cin][ks] (or the strides given)
+ *     1 stride-1 conv dgrad     in = dOut [R, L, Cout] -> out = dIn [R, L, Cin];  W [Cout][Cin][ks]
+ *     2 k5 s2 up-sampling       in [R, Lin, Cin] -> out [R, 2 Lin, Cout] (ConvTranspose1d forward / strided-conv dgrad),
+ *                               W element (t, n, k) at W[t + n * w_nstride + k * w_kstride]
+ *     3 linear forward          in [R, Cin] -> out [R, Cout]; W [Cout][Cin]; n_perm_* permutes the output columns
+ *     4 linear dgrad            in = dZ [R, Cout] -> out = dX [R, Cin]; W [Cout][Cin]
+ *     5 conv1d wgrad            in = dOut [R, Lin/stride, Cout], in2 = x [R, Lin, Cin] -> dW [Cout][Cin][ks] +=
+ *     6 ConvTranspose1d wgrad   in = x [R, Lin, Cin], in2 = dOut [R, 2 Lin, Cout] -> dW [Cin][Cout][5] +=
+ *     7 linear wgrad            in = dZ [R, Cout], in2 = A [R, Cin] -> dW [Cout][Cin] +=
+ * dtype flags: 0 = float32, 1 = bfloat16 (in / in2, out / aux, mul_src).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.2),
+ * 3 GELU (+ aux = GELU'), mul_mode: 0 none, 1 LeakyReLU' sign of mul_src, 2 ReLU' sign, 3 value.
+ * tf32 = 1 lets float32 Linears take the kind::tf32 tensor-core path as bf16 mode does.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mg_debug_layer {
+    int op, in_bf16, out_bf16, mask_bf16, tf32;
+    int R, Lin, Cin, Cout, ks, stride, pad;
+    int act, mul_mode, accumulate;
+    int w_nstride, w_kstride;          /* -1 = the layer's natural layout */
+    int n_perm_q, n_perm_p;
+    const void* in; const void* in2; void* out; void* aux; const void* mul_src;
+    const float* W; const float* bias; const float* col_scale; float* dW;
+} mg_debug_layer;
+int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
+/* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",
+ * "dbg" (ablation bits, -1 = off), "reverse" (-1 = alternate), "no_tma_store", "no_tma_mask", "no_reuse";
+ * "reset" restores the product heuristics.  Returns MG_ERR_INVALID for an unknown key. */
+int mg_debug_set(const char* key, int value);
+/* One line describing the last tensor-core launch of this thread (kernel variant, grid, stages, ...); "" if the
+ * last contraction did not run on the tensor cores. */
+const char* mg_debug_last_launch(void);
+
 #ifdef __cplusplus
 }
 #endif

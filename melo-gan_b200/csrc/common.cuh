@@ -15,7 +15,7 @@ void count_launch();   // every kernel launch of this library goes through MG_LA
 
 // Optional per-kernel-family probe (bench.py roofline): CUDA events around each launch of one family.
 enum ProbeFamily { PROBE_NONE = 0, PROBE_TAPGEMM = 1, PROBE_WGRAD = 2, PROBE_TC_GEMM = 3, PROBE_TC_WGRAD = 4,
-                   PROBE_NOTES = 5, PROBE_ADAM = 6 };
+                   PROBE_NOTES = 5, PROBE_ADAM = 6, PROBE_ELEM = 7 };
 struct ProbeScope {
     bool on = false;
     cudaStream_t st;

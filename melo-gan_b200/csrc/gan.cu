@@ -362,8 +362,11 @@ int disc_forward(mg_gan* c, const float* notes, const float* emb, int R, float* 
                            nullptr, nullptr, nullptr, MUL_NONE, st)));
     MG_TRY((conv_fwd<T, T>((const T*)c->d_h2, (T*)c->d_h3, c->D.c4_w, c->D.c4_b, R, 2 * L0, 128, 256, 5, 2, 2, ACT_LRELU,
                            nullptr, nullptr, nullptr, MUL_NONE, st)));
-    pool_rows_kernel<T, float><<<R, 256, 0, st>>>((const T*)c->d_h3, c->d_pool, R, L0, 256, 1.0f / (float)L0);
-    MG_LAUNCH_OK();
+    {
+        ProbeScope probe(PROBE_ELEM, 0.0, (double)R * L0 * 256 * sizeof(T), st);
+        pool_rows_kernel<T, float><<<R, 256, 0, st>>>((const T*)c->d_h3, c->d_pool, R, L0, 256, 1.0f / (float)L0);
+        MG_LAUNCH_OK();
+    }
     MG_TRY((linear_fwd<float, float>(c->d_pool, c->d_hf, c->D.fc_w, c->D.fc_b, R, 256, 256, ACT_LRELU, nullptr, st)));
     float* score = score_out ? score_out : c->d_score;
     critic_score_kernel<<<(R + 7) / 8, 256, 0, st>>>(c->d_hf, emb, c->D.rf_w, c->D.rf_b, R, c->B, 256,
@@ -388,6 +391,7 @@ int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int x
     MG_TRY((linear_dgrad<float, float>(c->d_dzf, c->d_dp, c->D.fc_w, R, 256, 256, nullptr, MUL_NONE, st)));
     {
         const int chunks = (int)((per / 4 + 1023) / 1024);
+        ProbeScope probe(PROBE_ELEM, 0.0, (double)R * per * 2 * sizeof(T), st);
         bcast_rows_mul_kernel<float, T><<<dim3(chunks, R), 256, 0, st>>>(c->d_dp, (const T*)c->d_h3, (T*)c->d_dz3, L0, 256,
                                                                         1.0f / (float)L0, nullptr, MUL_LRELU_SIGN);
         MG_LAUNCH_OK();
@@ -491,8 +495,11 @@ int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const 
                            MUL_LRELU_SIGN, st)));
     float* poolx = c->d_pool + (size_t)2 * B * 256;
     float* hfx = c->d_hf + (size_t)2 * B * 256;
-    pool_rows_kernel<T, float><<<B, 256, 0, st>>>(h3x, poolx, B, L0, 256, 1.0f / (float)L0);
-    MG_LAUNCH_OK();
+    {
+        ProbeScope probe(PROBE_ELEM, 0.0, (double)B * L0 * 256 * sizeof(T), st);
+        pool_rows_kernel<T, float><<<B, 256, 0, st>>>(h3x, poolx, B, L0, 256, 1.0f / (float)L0);
+        MG_LAUNCH_OK();
+    }
     // q = Wfc dgp, then hf' = lrelu'(hf) * q in place (so that d w_rf[0:256] picks up sum mf*q with seed 1)
     MG_TRY((linear_fwd<float, float>(poolx, c->d_q, c->D.fc_w, nullptr, B, 256, 256, ACT_NONE, nullptr, st)));
     {
@@ -536,8 +543,11 @@ int ed_forward(mg_gan* c, const float* notes, float* logits_out, cudaStream_t st
     for (int i = 1; i < 4; ++i)
         MG_TRY((conv_fwd<T, T>((const T*)c->ed_h[i - 1], (T*)c->ed_h[i], c->ED.conv[i].w, c->ed_shift[i], B, T4, ci[i],
                                co[i], 3, 1, 1, ACT_GELU, c->ed_scale[i], c->ed_g[i], nullptr, MUL_NONE, st)));
-    pool_rows_kernel<T, float><<<B, 256, 0, st>>>((const T*)c->ed_h[3], c->ed_pool, B, T4, 256, 1.0f / (float)T4);
-    MG_LAUNCH_OK();
+    {
+        ProbeScope probe(PROBE_ELEM, 0.0, (double)B * T4 * 256 * sizeof(T), st);
+        pool_rows_kernel<T, float><<<B, 256, 0, st>>>((const T*)c->ed_h[3], c->ed_pool, B, T4, 256, 1.0f / (float)T4);
+        MG_LAUNCH_OK();
+    }
     MG_TRY((linear_fwd<float, float>(c->ed_pool, c->ed_pj, c->ED.pj_w, c->ED.pj_b, B, 256, 256, ACT_NONE, nullptr, st)));
     MG_TRY((linear_fwd<float, float>(c->ed_pj, c->ed_c1, c->ED.c0_w, c->ED.c0_b, B, 256, 256, ACT_GELU, c->ed_c1g, st)));
     MG_TRY((linear_fwd<float, float>(c->ed_c1, c->ed_c2, c->ED.c3_w, c->ED.c3_b, B, 256, 128, ACT_GELU, c->ed_c2g, st)));
@@ -557,6 +567,7 @@ int ed_backward_input(mg_gan* c, const float* dlogits, float* dnotes, int accumu
     // d(conv3 pre-BN output) = dpool/T * gelu'(.) * bn_scale3
     {
         const int chunks = (T4 * 256 / 4 + 1023) / 1024;
+        ProbeScope probe(PROBE_ELEM, 0.0, (double)B * T4 * 256 * 2 * sizeof(T), st);
         bcast_rows_mul_kernel<float, T><<<dim3(chunks, B), 256, 0, st>>>(c->ed_d256a, (const T*)c->ed_g[3], (T*)c->ed_dzA, T4,
                                                                         256, 1.0f / (float)T4, c->ed_scale[3], MUL_VALUE);
         MG_LAUNCH_OK();

@@ -235,6 +235,7 @@ int colreduce(mg_gan* c, const T* x, int ldx, const void* y, int ldy, const floa
     if (rpc < 64) rpc = 64;
     rpc = (rpc + 7) / 8 * 8;
     const int nchunk = (int)((rows + rpc - 1) / rpc);
+    ProbeScope probe(PROBE_ELEM, 0.0, (double)rows * C * (sizeof(T) + (OP == COL_BN_BWD ? sizeof(TY) : 0)), st);
     ColReduceArgs a{};
     a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.mean = mean; a.invstd = invstd; a.roww = roww;
     a.roww_div = roww_div > 0 ? roww_div : 1; a.r0 = r0; a.r1 = r1; a.C = C; a.partial = c->partial;
@@ -277,6 +278,7 @@ int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, flo
     }
     MG_LAUNCH_OK();
     const long long n4 = rows * C / 4;
+    ProbeScope probe(PROBE_ELEM, 0.0, (double)rows * C * (4 + sizeof(T)), st);
     bn_relu_apply_kernel<float, T><<<grid_for(n4), 256, 0, st>>>(x, y, n4, C, mean, invstd, gamma, beta);
     MG_LAUNCH_OK();
     return MG_OK;
@@ -293,6 +295,7 @@ int bn_backward(mg_gan* c, const float* x, const float* dy, T* dx, long long row
     add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
     MG_LAUNCH_OK();
     const long long n4 = rows * C / 4;
+    ProbeScope probe(PROBE_ELEM, 0.0, (double)rows * C * (8 + sizeof(T)), st);
     bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
                                                          c->g_bn_sums);
     MG_LAUNCH_OK();

@@ -25,6 +25,10 @@ Scratch g_scratch;
 }  // namespace
 
 Scratch& scratch() { return g_scratch; }
+static Tuning g_tuning;
+Tuning& tuning() { return g_tuning; }
+static thread_local LaunchInfo g_last_launch;
+LaunchInfo& last_launch() { return g_last_launch; }
 
 int ensure_scratch(size_t elems) {
     if (elems <= g_scratch.slot_elems) return MG_OK;

@@ -107,6 +107,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -211,6 +213,8 @@ struct TcTapArgs {
     float alpha; int accumulate;
     int tma_mask;                       // ... and the mask tile (f' of the saved activation) arrives by TMA as well
     int tma_store;                      // weight-stationary kernel: tiles leave through shared memory + TMA bulk stores
+    int nsb;                            // ... through a ring of nsb (1 or 2) staging tiles: the bulk store of one tile drains
+                                        // while the next tile is read from TMEM, computed and staged
     int reverse;                        // walk the M tiles from the last to the first (see run_tc_tap)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
@@ -439,8 +443,8 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
                                                const CUtensorMap* m_map, const float* s_bias, const float* s_scale,
                                                uint32_t tmem_acc, int b0, int m0, int n0, int warp, int lane, int et,
                                                uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int c_begin,
-                                               unsigned char* staging, unsigned char* maskbuf, uint64_t* mask_bar,
-                                               uint32_t mask_parity, int next_row0) {
+                                               unsigned char* staging0, int& sbuf, unsigned char* maskbuf,
+                                               uint64_t* mask_bar, uint32_t mask_parity, int next_row0) {
     constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
     const int q = warp & 3, r = q * 32 + lane;
     const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
@@ -458,7 +462,10 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
     tmem_ld32_async(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin, raw);
     tmem_wait_ld();
     tc_fence_before();
-    if (et == 0) bulk_wait_read0();                              // the previous tile's stores have left the staging tile
+    // staging ring: with two tiles the bulk store of the previous tile keeps draining while this one is computed
+    constexpr size_t kStageTile = (size_t)128 * BN * sizeof(TO);
+    unsigned char* staging = staging0 + (size_t)sbuf * kStageTile;
+    if (et == 0) { if (P.nsb > 1) bulk_wait_read<1>(); else bulk_wait_read0(); }   // this staging tile has left
     asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");      // every thread holds its accumulator row: TMEM is free
     if (et == 0) mbar_arrive(empty_bar);
     if (P.tma_mask) {                                            // this thread's 64 mask bytes from the TMA-loaded tile
@@ -504,8 +511,10 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, mask_bar, maskbuf + bx * 16384, n0 + bx * 64, next_row0);
     }
+    if (P.nsb > 1) sbuf ^= 1;
     if (P.aux) {                                                 // second tile (activation derivative), bf16 only
-        if (et == 0) bulk_wait_read0();
+        staging = staging0 + (size_t)sbuf * kStageTile;
+        if (et == 0) { if (P.nsb > 1) bulk_wait_read<1>(); else bulk_wait_read0(); }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
 #pragma unroll
         for (int g8 = 0; g8 < 32; g8 += 8) {
@@ -519,6 +528,7 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
             for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, staging + bx * 16384, n0 + bx * EPB, row0);
             bulk_commit();
         }
+        if (P.nsb > 1) sbuf ^= 1;
     }
 }
 
@@ -665,7 +675,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     const uint32_t a_tx = (uint32_t)(kTileM + P.halo) * kTileK * 2;                           // bytes one A box delivers
     const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
     unsigned char* staging = asm_ + (size_t)nstages * a_stage;                                 // [BN*sizeof(TO)/128][128][128 B]
-    unsigned char* maskbuf = staging + (size_t)128 * BN * sizeof(TO);                          // [BN/64][128][128 B] (bf16 masks)
+    unsigned char* maskbuf = staging + (size_t)(P.nsb > 1 ? 2 : 1) * 128 * BN * sizeof(TO);   // [BN/64][128][128 B] (bf16 masks)
     const int n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
@@ -773,7 +783,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             H.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-        int tcount = 0;
+        int tcount = 0, sbuf = 0;
         for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
             const int acc = tcount & 1;
             int b0, m0;
@@ -793,7 +803,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                 }
                 drain_tile_tma<BN, kEpi, TO, TMSK>(P, &o_map, &x_map, &m_map, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0,
                                                    m0, n0, warp, lane, et, &H.tmem_full[acc], (tcount >> 1) & 1,
-                                                   &H.tmem_empty[acc], grp * 32, staging, maskbuf, &H.mask_full, tcount & 1,
+                                                   &H.tmem_empty[acc], grp * 32, staging, sbuf, maskbuf, &H.mask_full, tcount & 1,
                                                    next_row0);
                 continue;
             }
@@ -1057,6 +1067,27 @@ inline void build_tap_groups(TcTapArgs& a, int halo_max) {
 
 bool reuse_enabled();        // MELOGAN_DISABLE_TAP_REUSE=1: one activation tile per tap (A/B profiling)
 
+// Kernel-selection overrides for the per-layer harness (mg_debug_set, csrc/debug.cu); all zero = the product heuristics.
+struct Tuning {
+    int force_bn = 0;        // 64 / 128: slab width of the weight-stationary kernel
+    int max_stages = 0;      // cap of the activation ring
+    int staging_bufs = 0;    // 1 / 2 staging tiles (0 = two when they fit)
+    int no_ws = 0;           // one tile per CTA
+    int dbg = -1;            // MELOGAN_TC_DEBUG ablation bits (-1 = environment)
+    int reverse = -1;        // fixed tile order (-1 = alternate)
+    int no_tma_store = 0, no_tma_mask = 0, no_reuse = 0;
+};
+Tuning& tuning();
+// What the last tensor-core launch on this thread looked like (tests assert that the variant they mean to pin ran).
+struct LaunchInfo {
+    int kind = 0;            // 0 none, 1 tap-GEMM, 2 wgrad
+    long long rows = 0;
+    int N = 0, K = 0, taps = 0, groups = 0, halo = 0, BN = 0, out_bytes = 0, ws = 0, stages = 0, act = 0, mul = 0, aux = 0;
+    int tma_store = 0, tma_mask = 0, nsb = 0, reverse = 0, ctas_x = 0, slabs = 0, tf32 = 0, splits = 0;
+    double flops = 0, bytes = 0;
+};
+LaunchInfo& last_launch();
+
 // Launch a tap-GEMM whose tensor maps and TcTapArgs are ready: weight-stationary persistent form when the slab's
 // weights fit in shared memory next to >= 3 activation stages and every CTA gets >= 4 tiles, else one tile per CTA.
 // am_halo (optional): the same activation view with boxes of 128 + a.halo rows, a.ngroups/g_* describing the tap groups.
@@ -1077,27 +1108,39 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
     if (!am_halo) build_tap_groups(a, 0);
+    const Tuning& tn = tuning();
     {   // Consecutive layers are 0.4-0.8 GB producer -> consumer hand-offs through a 126 MB L2: the consumer starts where
         // the producer stopped (its last tiles are still resident) if successive launches walk the rows in opposite order.
         static const bool snake = getenv("MELOGAN_NO_SNAKE") == nullptr;
         static unsigned launch_no = 0;
         a.reverse = snake ? (int)(launch_no++ & 1u) : 0;
+        if (tn.reverse >= 0) a.reverse = tn.reverse;
     }
-    { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = dbg; }
+    { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = tn.dbg >= 0 ? tn.dbg : dbg; }
     const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
-    const bool ws = ws_enabled() && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x && a.ntaps * (K / a.ktile) <= kWsMaxLoads;
+    const bool ws = ws_enabled() && !tn.no_ws && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x &&
+                    a.ntaps * (K / a.ktile) <= kWsMaxLoads;
     if (trace)
         fprintf(stderr, "[tc_tap] rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%zu ws=%d stages=%d act=%d mul=%d aux=%d\n",
                 rows, a.N, K, a.ntaps, a.ngroups, a.halo, BN, sizeof(TO), (int)ws, ws ? (int)((avail - wbytes) / a_stage) : 3, a.act,
                 a.mul_mode, a.aux != nullptr);
+    LaunchInfo& li = last_launch();
+    const double flops0 = li.kind == 1 ? li.flops : 0.0, bytes0 = li.kind == 1 ? li.bytes : 0.0;   // sub-pixel phases add up
+    li = LaunchInfo();
+    li.kind = 1; li.rows = rows; li.N = a.N; li.K = K; li.taps = a.ntaps; li.groups = a.ngroups; li.halo = a.halo; li.BN = BN;
+    li.out_bytes = (int)sizeof(TO); li.ws = ws; li.stages = 3; li.act = a.act; li.mul = a.mul_mode; li.aux = a.aux != nullptr;
+    li.reverse = a.reverse; li.ctas_x = ws ? ctas_x : mtiles; li.slabs = nslabs; li.tf32 = TF32;
+    li.flops = flops0 + 2.0 * (double)rows * a.N * a.ntaps * K;
+    li.bytes = bytes0 + (double)rows * (K * (TF32 ? 4.0 : 2.0) + a.N * sizeof(TO) * (a.aux ? 2.0 : 1.0) +
+                                        (a.mul_mode != MUL_NONE ? a.N * (double)sizeof(TMSK) : 0.0));
     if (ws) {
         // tiles leave through a staging tile + TMA bulk stores when the output rows are uniformly strided and the staging
         // tile fits next to >= 3 activation stages
         const size_t staging = (size_t)128 * BN * sizeof(TO);
         CUtensorMap om = am, xm = am;
-        a.tma_store = 0;
-        if (tma_store_enabled() && !a.accumulate && a.o_bstride == (long long)a.Mper * a.o_mstride &&
+        a.tma_store = 0; a.nsb = 1;
+        if (tma_store_enabled() && !tn.no_tma_store && !a.accumulate && a.o_bstride == (long long)a.Mper * a.o_mstride &&
             wbytes + 3 * a_stage + staging <= avail && (a.o_mstride * sizeof(TO)) % 16 == 0 &&
             ((uintptr_t)((TO*)a.Out + a.o_off)) % 16 == 0 && (!a.aux || sizeof(TO) == 2)) {
             int rc = make_out_map(&om, (TO*)a.Out + a.o_off, (int)sizeof(TO), a.N, rows, a.o_mstride);
@@ -1112,15 +1155,22 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         CUtensorMap mm = am;
         const size_t maskbytes = (size_t)128 * BN * 2;
         a.tma_mask = 0;
-        if (a.tma_store && a.mul_mode != MUL_NONE && sizeof(TMSK) == 2 && mask_tma_enabled() &&
+        if (a.tma_store && a.mul_mode != MUL_NONE && sizeof(TMSK) == 2 && mask_tma_enabled() && !tn.no_tma_mask &&
             wbytes + 3 * a_stage + staging + maskbytes <= avail && ((uintptr_t)((const TMSK*)a.mul_src + a.o_off)) % 16 == 0) {
             const int rc = make_out_map(&mm, (const TMSK*)a.mul_src + a.o_off, 2, a.N, rows, a.o_mstride);
             if (rc != MG_OK) return rc;
             a.tma_mask = 1;
         }
-        const size_t extra = (a.tma_store ? staging : 0) + (a.tma_mask ? maskbytes : 0);
+        // a second staging tile when it still leaves 4 activation stages: the drain of the bulk store (shared memory ->
+        // L2) then overlaps the next tile's TMEM read and epilogue math instead of serialising with them
+        if (a.tma_store && tn.staging_bufs != 1 &&
+            wbytes + 4 * a_stage + 2 * staging + (a.tma_mask ? maskbytes : 0) <= avail)
+            a.nsb = 2;
+        const size_t extra = (a.tma_store ? staging * a.nsb : 0) + (a.tma_mask ? maskbytes : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
+        if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
+        li.stages = nstages; li.tma_store = a.tma_store; li.tma_mask = a.tma_mask; li.nsb = a.nsb;
         const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage + extra;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
@@ -1191,13 +1241,14 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
         static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;
         if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64))) BN = 64;
     }
+    if (tuning().force_bn == 64 || (tuning().force_bn == 128 && P.N % 128 == 0)) BN = tuning().force_bn;
     int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt, EB);
     if (rc != MG_OK) return rc;
     rc = make_weight_map(&bm, wp, P.K, (long long)P.ntaps * P.N, BN, EB);
     if (rc != MG_OK) return rc;
     CUtensorMap amh;
     const CUtensorMap* halo_map = nullptr;
-    if (reuse_enabled() && a.mpt == 128 && P.ntaps > 1) {
+    if (reuse_enabled() && !tuning().no_reuse && a.mpt == 128 && P.ntaps > 1) {
         build_tap_groups(a, 8);
         if (a.ngroups < a.ntaps) {
             rc = make_act_map(&amh, P.A, P.K, LA, P.B, stride, 128 + a.halo, 1, EB);
@@ -1264,6 +1315,12 @@ int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
     rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, nsamples, stride, a.rpt, a.spt);
     if (rc != MG_OK) return rc;
     ProbeScope probe(PROBE_TC_WGRAD, 2.0 * (double)nrows * P.N * P.ntaps * P.K, (double)nrows * (P.N + P.K) * 2.0, st);
+    {
+        LaunchInfo& li = last_launch();
+        li = LaunchInfo();
+        li.kind = 2; li.rows = nrows; li.N = P.N; li.K = P.K; li.taps = P.ntaps; li.BN = BNK; li.splits = (int)splits;
+        li.flops = 2.0 * (double)nrows * P.N * P.ntaps * P.K; li.bytes = (double)nrows * (P.N + P.K) * 2.0;
+    }
     rc = (BNK == 128) ? launch_tc_wgrad<128>(gm, am, a, (int)splits, st) : launch_tc_wgrad<64>(gm, am, a, (int)splits, st);
     return rc == MG_OK ? 1 : rc;
 }

@@ -68,6 +68,10 @@ _SIGNATURES = {
     "mg_vae_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_vae_buffer": ([_vp, ctypes.c_char_p, _vp, _vp], _i),
     "mg_vae_loss_step": ([_vp, _vp, _vp, _d, _vp, _vp], _i),
+    # per-layer harness (tests/tc_layers.py owns the mg_debug_layer struct)
+    "mg_debug_layer_run": ([_vp, _vp], _i),
+    "mg_debug_set": ([ctypes.c_char_p, _i], _i),
+    "mg_debug_last_launch": ([], ctypes.c_char_p),
     "mg_critic_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_generator_step": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
 }

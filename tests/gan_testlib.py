@@ -75,3 +75,25 @@ def make_engine(B, params, precision="fp32"):
 
 def cuda_batch(batch):
     return {k: v.cuda() for k, v in batch.items()}
+
+
+def make_flat_trainer(B, params, precision="fp32", lr_d=1e-4, lr_g=1e-4, betas=(0.5, 0.9)):
+    """Engine + flat parameter groups + fused Adam wired like melogan.trainer.GanTrainer, but fed with explicit
+    noise / alpha / masks so that a run can follow the oracle's random draws step by step."""
+    from melogan.optim import FlatParams, FusedAdam
+    eng = E.GanEngine(B, precision=precision)
+    cp = cuda_params(params)
+    leafD = [torch.nn.Parameter(cp["D"][k]) for k in E.D_KEYS]
+    leafG = [torch.nn.Parameter(cp["G"][k]) for k in E.G_PARAM_KEYS] + [torch.nn.Parameter(cp["E"][k]) for k in E.E_KEYS]
+    flatD, flatG = FlatParams(leafD), FlatParams(leafG)
+    optD, optG = FusedAdam(flatD, lr=lr_d, betas=betas), FusedAdam(flatG, lr=lr_g, betas=betas)
+    nG = len(E.G_PARAM_KEYS)
+    Dp = {k: p.data for k, p in zip(E.D_KEYS, leafD)}
+    Dg = {k: p.grad for k, p in zip(E.D_KEYS, leafD)}
+    Gp = {k: p.data for k, p in zip(E.G_PARAM_KEYS, leafG[:nG])}
+    Gp.update({k: cp["G"][k] for k in E.G_BUFFER_KEYS})
+    Gg = {k: p.grad for k, p in zip(E.G_PARAM_KEYS, leafG[:nG])}
+    Ep = {k: p.data for k, p in zip(E.E_KEYS, leafG[nG:])}
+    Eg = {k: p.grad for k, p in zip(E.E_KEYS, leafG[nG:])}
+    eng.bind(E.MOD_E, Ep, Eg); eng.bind(E.MOD_G, Gp, Gg); eng.bind(E.MOD_D, Dp, Dg); eng.bind(E.MOD_ED, cp["ED"], None)
+    return {"eng": eng, "optD": optD, "optG": optG, "D": Dp, "G": Gp, "E": Ep, "keep": (leafD, leafG, flatD, flatG, cp)}

@@ -1,0 +1,82 @@
+"""Every tensor-core contraction of the BENCHED configuration (bf16 mode, per-GPU batch 8192: the grids, slab widths,
+halo tap groups, tile orders, staging rings and wgrad splits the bench actually runs) against a float64 contraction of
+the same bf16-exact operands, through the C ABI (mg_debug_layer_run calls the very helper the step bodies call).
+
+Bars: float32 results (pre-BatchNorm activations, weight gradients, TF32 Linears) within 1e-5 of the tensor's scale --
+only the fp32 accumulation order differs; bf16 results within ONE bf16 ulp of the float64 value.  A wrong halo row, tap
+or tile edge is an O(1) error and cannot hide here (the whole-step bf16 tests allow 4-8 % for mask flips)."""
+import os
+
+import pytest
+import torch
+
+import tc_layers as TL
+
+pytestmark = pytest.mark.gpu
+
+B = int(os.environ.get("MELOGAN_TEST_LAYER_BATCH", "8192"))
+SPECS = TL.cycle_layers(B)
+F32_TOL, WGRAD_TOL, ULP_TOL = 1e-5, 5e-5, 1.0
+
+
+def _check(layer, info):
+    s = layer.s
+    if s["op"] >= 5:
+        ref = layer.reference_wgrad()
+        rel, _ = TL.compare(layer.dW, ref, False)
+        assert rel <= WGRAD_TOL, f"{s['name']}: wgrad rel err {rel:.3e} ({info})"
+        return rel, 0.0
+    R = s["R"]
+    chunk = max(1, min(R, (1 << 24) // max(1, layer.out[0].numel())))
+    worst_rel = worst_ulp = 0.0
+    stored = bool(s["out_bf16"])
+    for r0 in range(0, R, chunk):
+        r1 = min(R, r0 + chunk)
+        y, aux = layer.reference(r0, r1)
+        rel, ulp = TL.compare(layer.out[r0:r1], y, stored)
+        worst_rel, worst_ulp = max(worst_rel, rel), max(worst_ulp, ulp)
+        if aux is not None:
+            rel, ulp = TL.compare(layer.aux[r0:r1], aux, stored)
+            worst_rel, worst_ulp = max(worst_rel, rel), max(worst_ulp, ulp)
+    if stored:
+        assert worst_ulp <= ULP_TOL, f"{s['name']}: {worst_ulp:.2f} bf16 ulps off (rel {worst_rel:.2e}) ({info})"
+    else:
+        assert worst_rel <= F32_TOL, f"{s['name']}: rel err {worst_rel:.3e} ({info})"
+    return worst_rel, worst_ulp
+
+
+@pytest.mark.parametrize("spec", SPECS, ids=[s["name"] for s in SPECS])
+def test_layer_matches_float64(spec):
+    TL.debug_set("reset", 0)
+    layer = TL.Layer(spec, seed=11)
+    for reverse in (0, 1):                      # both tile orders of the snake walk
+        TL.debug_set("reverse", reverse)
+        info = layer.run()
+        torch.cuda.synchronize()
+        assert info.startswith("tc_"), f"{spec['name']} did not run on the tensor cores: '{info}'"
+        rel, ulp = _check(layer, info)
+        print(f"{spec['name']:18s} reverse={reverse} rel={rel:.2e} ulp={ulp:.2f}  {info}")
+    TL.debug_set("reset", 0)
+
+
+@pytest.mark.parametrize("name,knobs", [
+    ("D.conv4.fwd", {"force_bn": 64}), ("D.conv4.fwd", {"staging_bufs": 1}), ("D.conv2.fwd", {"staging_bufs": 1}),
+    ("D.conv2.fwd", {"no_reuse": 1}), ("ED.conv2.fwd", {"force_bn": 64}), ("ED.conv1.fwd", {"no_tma_store": 1}),
+    ("D.conv4.dgrad", {"no_tma_mask": 1}), ("D.conv2.dgrad", {"no_ws": 1}), ("ED.conv3.dgrad", {"max_stages": 3}),
+])
+def test_kernel_variants_match_float64(name, knobs):
+    """The other kernel variants the heuristics can pick at other batch sizes (narrow slabs, single staging tile, one
+    tile per CTA, per-thread mask loads and stores, no tap reuse) on the same layers."""
+    spec = dict(next(s for s in TL.cycle_layers(min(B, 2048)) if s["name"] == name))
+    TL.debug_set("reset", 0)
+    for k, v in knobs.items():
+        TL.debug_set(k, v)
+    try:
+        layer = TL.Layer(spec, seed=5)
+        info = layer.run()
+        torch.cuda.synchronize()
+        assert info.startswith("tc_"), info
+        rel, ulp = _check(layer, info)
+        print(f"{name:18s} {knobs} rel={rel:.2e} ulp={ulp:.2f}  {info}")
+    finally:
+        TL.debug_set("reset", 0)
