@@ -91,6 +91,14 @@ uint32_t mg_scale_mask(const char* scale_name, int root_key);
 int mg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                  double lr, double beta1, double beta2, double eps, double weight_decay, int decoupled,
                  float grad_scale, long long step, long long* step_dev, uint16_t* bf16_copy, void* stream);
+/* Same update with torch.nn.utils.clip_grad_norm_(params, max_norm) fused in front of it (reference
+ * src/ae/train_ae.py:121): the L2 norm of grad_scale * grad over the whole flat group is reduced on the device, the
+ * gradient is scaled by min(1, max_norm / (norm + 1e-6)) inside the update; norm_out_dev (1 float, may be NULL) receives
+ * the pre-clip norm.  No host synchronisation: CUDA-graph capturable. */
+int mg_adam_step_clipped(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, int decoupled, float grad_scale,
+                         float max_norm, float* norm_out_dev, long long step, long long* step_dev, uint16_t* bf16_copy,
+                         void* stream);
 
 
 /* ==========================================================================================
@@ -257,6 +265,16 @@ int mg_probe_end(double* out);
  * the CUDA-core kernels (same bf16 operands; used for A/B parity tests).  Returns the previous setting.
  * The environment variable MELOGAN_DISABLE_TC=1 sets the initial value to 0. */
 int mg_tc_enable(int on);
+
+/* Packed-weight cache of the tensor-core kernels (bf16 mode), per context.  Off (default): every contraction re-packs its
+ * weights into [tap][n][k] tiles right before the launch, so weights may be changed by anybody at any time.  On: one
+ * persistent packed copy per (weight tensor, layout), re-packed only after mg_adam_step / mg_adam_step_clipped updated the
+ * flat group the tensor lives in, after mg_gan_bind, or after mg_weight_cache_invalidate() -- the caller promises that
+ * nothing else writes the bound parameters (melogan.trainer does; load_state_dict / rebind invalidate).  The frozen
+ * emotion discriminator of the generator step (reference src/gan/train_gan.py:131-133) is then packed once, the
+ * generator's weights once per cycle instead of once per launch.  Returns the previous setting. */
+int mg_gan_weight_cache(mg_gan* ctx, int on);
+int mg_weight_cache_invalidate(void);
 
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);

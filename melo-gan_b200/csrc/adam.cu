@@ -15,18 +15,59 @@ namespace {
 struct AdamScalars {
     float neg_step_size;  // -(lr / (1 - beta1^t))
     float bc2_sqrt;       // sqrt(1 - beta2^t)
+    float clip;           // clip_grad_norm_ coefficient min(1, max_norm / (||g|| + 1e-6)); 1 without clipping
+    float pad;
 };
+
+// sum of squares of the flat gradient, one double per CTA (clip_grad_norm_: reference src/ae/train_ae.py:121)
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ grad, long long n, double* __restrict__ parts) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4* g4 = reinterpret_cast<const float4*>(grad);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (long long i = tid; i < n4; i += stride) {
+        const float4 g = __ldg(g4 + i);
+        a0 = fmaf(g.x, g.x, a0); a1 = fmaf(g.y, g.y, a1); a2 = fmaf(g.z, g.z, a2); a3 = fmaf(g.w, g.w, a3);
+    }
+    for (long long i = (n4 << 2) + tid; i < n; i += stride) a0 = fmaf(grad[i], grad[i], a0);
+    double acc = (double)a0 + (double)a1 + (double)a2 + (double)a3;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double warp_sum[8];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += warp_sum[w];
+        parts[blockIdx.x] = t;
+    }
+}
 
 // One thread: advance the device step counter and derive the bias corrections in float64
 // (python computes them with float64 `**`).  Keeps the whole update CUDA-graph capturable.
 __global__ void adam_prepare_kernel(long long* step_dev, long long step_host, double lr, double beta1, double beta2,
-                                    AdamScalars* out) {
+                                    AdamScalars* out, const double* parts, int nparts, float grad_scale, float max_norm,
+                                    float* norm_out) {
+    double ss = 0.0;                                   // one warp: lanes share the partial sums
+    if (parts) {
+        for (int i = threadIdx.x; i < nparts; i += 32) ss += parts[i];
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (threadIdx.x != 0) return;
     long long t = step_host;
     if (step_dev) { t = *step_dev + 1; *step_dev = t; }
     const double bc1 = 1.0 - pow(beta1, (double)t);
     const double bc2 = 1.0 - pow(beta2, (double)t);
     out->neg_step_size = (float)(-(lr / bc1));
     out->bc2_sqrt = (float)sqrt(bc2);
+    float clip = 1.0f;
+    if (parts) {   // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to <= 1
+        const float total = (float)(sqrt(ss) * (double)grad_scale);
+        if (norm_out) *norm_out = total;
+        const float coef = max_norm / (total + 1e-6f);
+        clip = coef < 1.0f ? coef : 1.0f;
+    }
+    out->clip = clip;
 }
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float w_lerp, float one_minus_w,
@@ -49,6 +90,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, co
                                                    float grad_scale, const AdamScalars* __restrict__ sc,
                                                    __nv_bfloat16* __restrict__ bf16_copy) {
     const AdamScalars s = *sc;
+    grad_scale *= s.clip;
     const float omw = 1.0f - w;  // torch evaluates (1 - weight) in the tensor dtype
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -83,6 +125,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, co
 }
 
 AdamScalars* g_scalars[16] = {nullptr};  // one slot per device
+double* g_parts[16] = {nullptr};         // per device: 4 rings of per-CTA partial sums of squares
+constexpr int kMaxParts = 2048;
+
+int adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+              double beta2, double eps, double weight_decay, int decoupled, float grad_scale, float max_norm,
+              float* norm_out_dev, long long step, long long* step_dev, uint16_t* bf16_copy, void* stream);
 
 }  // namespace
 
@@ -90,6 +138,23 @@ extern "C" int mg_adam_step(float* param, const float* grad, float* exp_avg, flo
                             double lr, double beta1, double beta2, double eps, double weight_decay,
                             int decoupled, float grad_scale, long long step, long long* step_dev,
                             uint16_t* bf16_copy, void* stream) {
+    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_scale, 0.0f,
+                     nullptr, step, step_dev, bf16_copy, stream);
+}
+
+extern "C" int mg_adam_step_clipped(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                    double lr, double beta1, double beta2, double eps, double weight_decay, int decoupled,
+                                    float grad_scale, float max_norm, float* norm_out_dev, long long step,
+                                    long long* step_dev, uint16_t* bf16_copy, void* stream) {
+    MG_REQUIRE(max_norm > 0.0f, "adam_step_clipped: max_norm must be positive");
+    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_scale, max_norm,
+                     norm_out_dev, step, step_dev, bf16_copy, stream);
+}
+
+namespace {
+int adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+              double beta2, double eps, double weight_decay, int decoupled, float grad_scale, float max_norm,
+              float* norm_out_dev, long long step, long long* step_dev, uint16_t* bf16_copy, void* stream) {
     MG_REQUIRE(n >= 0, "adam: negative n");
     if (n == 0) return MG_OK;
     MG_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam: null pointer");
@@ -105,13 +170,26 @@ extern "C" int mg_adam_step(float* param, const float* grad, float* exp_avg, flo
     static thread_local unsigned slot = 0;
     AdamScalars* sc = g_scalars[dev] + (slot++ & 63);
     cudaStream_t st = mg::as_stream(stream);
-    adam_prepare_kernel<<<1, 1, 0, st>>>(step_dev, step, lr, beta1, beta2, sc);
-    MG_LAUNCH_OK();
-    const float decay_mul = (weight_decay != 0.0) ? (float)(1.0 - lr * weight_decay) : 1.0f;
     long long blocks = ((n >> 2) + 255) / 256;
     const long long cap = (long long)mg::num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    const double* parts = nullptr;
+    int nparts = 0;
+    if (max_norm > 0.0f) {   // fused clip_grad_norm_: one extra read of the gradient (4 B/param), no host round trip
+        if (!g_parts[dev]) MG_CUDA_OK(cudaMalloc(&g_parts[dev], sizeof(double) * kMaxParts * 4));
+        static thread_local unsigned pslot = 0;
+        double* p = g_parts[dev] + (size_t)(pslot++ & 3) * kMaxParts;
+        nparts = (int)(blocks < kMaxParts ? blocks : kMaxParts);
+        mg::ProbeScope probe(mg::PROBE_ADAM, 0.0, 4.0 * (double)n, st);
+        grad_sumsq_kernel<<<nparts, 256, 0, st>>>(grad, n, p);
+        MG_LAUNCH_OK();
+        parts = p;
+    }
+    adam_prepare_kernel<<<1, 32, 0, st>>>(step_dev, step, lr, beta1, beta2, sc, parts, nparts, grad_scale, max_norm, norm_out_dev);
+    MG_LAUNCH_OK();
+    const float decay_mul = (weight_decay != 0.0) ? (float)(1.0 - lr * weight_decay) : 1.0f;
+    mg::tc_weights_changed(param, n);     // packed tensor-core copies of these parameters are stale from here on
     mg::ProbeScope probe(mg::PROBE_ADAM, 0.0, 28.0 * (double)n + (bf16_copy ? 2.0 * (double)n : 0.0), st);
     adam_kernel<<<(int)blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
                                              (float)(1.0 - beta2), (float)eps, decay_mul,
@@ -119,3 +197,4 @@ extern "C" int mg_adam_step(float* param, const float* grad, float* exp_avg, flo
     MG_LAUNCH_OK();
     return MG_OK;
 }
+}  // namespace

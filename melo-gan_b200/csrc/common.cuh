@@ -12,6 +12,7 @@ namespace mg {
 void set_error(const char* fmt, ...);
 int num_sms();
 void count_launch();   // every kernel launch of this library goes through MG_LAUNCH_OK()
+void tc_weights_changed(const float* param, long long n);   // gemm_tc.cu: invalidates packed-weight cache entries
 
 // Optional per-kernel-family probe (bench.py roofline): CUDA events around each launch of one family.
 enum ProbeFamily { PROBE_NONE = 0, PROBE_TAPGEMM = 1, PROBE_WGRAD = 2, PROBE_TC_GEMM = 3, PROBE_TC_WGRAD = 4,

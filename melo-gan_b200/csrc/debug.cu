@@ -69,7 +69,7 @@ extern "C" int mg_debug_layer_run(const mg_debug_layer* Lp, void* stream) {
         MG_TRY(tc::ensure_scratch(need));
     }
     tc::last_launch() = tc::LaunchInfo();
-    tc::set_tf32(L.tf32 != 0);
+    tc::set_tf32(L.tf32 != 0); tc::set_cache_mode(false);
     using bf = __nv_bfloat16;
     if (L.op >= 5) {
         if (L.in_bf16 == 1 && L.out_bf16 == 1) return run_wgrad<bf, bf>(L, st);      // out_bf16 = dtype of in2 here

@@ -779,7 +779,8 @@ int generator_step(mg_gan* c, const float* numeric, const float* noise, const lo
     } while (0)
 // TF32 tensor cores for the fp32 Linears are a bf16-mode choice; fp32 parity mode never takes them
 #define MG_DISPATCH(c, fn, ...) \
-    (mg::tc::set_tf32((c)->bf16), (c)->bf16 ? fn<__nv_bfloat16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+    (mg::tc::set_tf32((c)->bf16), mg::tc::set_cache_mode((c)->weight_cache), \
+     (c)->bf16 ? fn<__nv_bfloat16>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
     MG_REQUIRE(cfg && out, "gan_create: null argument");
@@ -881,7 +882,16 @@ extern "C" int mg_gan_bind(mg_gan* c, int module, void* const* params, int npara
     }
     c->bound[module] = true;
     c->has_grads[module] = grads != nullptr;
+    mg::tc::weights_changed(nullptr, 0);     // new parameter storage: every packed copy is stale
     return MG_OK;
+}
+
+extern "C" int mg_gan_weight_cache(mg_gan* c, int on) {
+    MG_CTX_CHECK(c);
+    const int prev = c->weight_cache ? 1 : 0;
+    c->weight_cache = on != 0;
+    mg::tc::weights_changed(nullptr, 0);
+    return prev;
 }
 
 extern "C" int mg_feature_encoder_forward(mg_gan* c, const float* numeric, const float* mask1, const float* mask2,
@@ -993,6 +1003,7 @@ extern "C" int mg_gradient_penalty(mg_gan* c, const float* real, const float* fa
     MG_REQUIRE(real && fake && alpha, "gradient_penalty: null pointer");
     // GP alone: zero seeds for the real/fake rows, unit weight on the penalty
     mg::tc::set_tf32(c->bf16);
+    mg::tc::set_cache_mode(c->weight_cache);
     return c->bf16 ? critic_loss_backward<__nv_bfloat16>(c, real, fake, emb, alpha, metrics_out, as_stream(stream), 0.f, 0.f, 1.f)
                    : critic_loss_backward<float>(c, real, fake, emb, alpha, metrics_out, as_stream(stream), 0.f, 0.f, 1.f);
 }
@@ -1021,6 +1032,7 @@ extern "C" int mg_emotion_train_forward(mg_gan* c, const float* notes, const flo
     MG_REQUIRE(dropout_p == 0.0 || (mask1 && mask2), "emotion_train_forward: dropout masks required");
     if (dropout_p == 0.0) { mask1 = mask2 = nullptr; }
     mg::tc::set_tf32(c->bf16);
+    mg::tc::set_cache_mode(c->weight_cache);
     return c->bf16 ? ed_train_forward<__nv_bfloat16>(c, notes, mask1, mask2, (float)dropout_p, logits_out, as_stream(stream))
                    : ed_train_forward<float>(c, notes, mask1, mask2, (float)dropout_p, logits_out, as_stream(stream));
 }

@@ -33,6 +33,7 @@ struct mg_gan {
     bool bound[4] = {false, false, false, false};
     bool has_grads[4] = {false, false, false, false};
     bool ed_folded = false;
+    bool weight_cache = false;     // mg_gan_weight_cache: packed tensor-core weights persist between launches
 
     // ---- workspaces (one arena) ----
     char* arena = nullptr;

@@ -95,14 +95,18 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 
 // bf16-mode epilogues: GELU and its derivative from ONE exp (erf by Abramowitz-Stegun 7.1.26, |err| < 1.5e-7,
 // which is far below the bf16 storage rounding of the result); about 4x fewer instructions than erff + expf.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
+    // flush-to-zero MUFU forms: the default __expf / __fdividef wrap each MUFU in a denormal range fix-up (4 extra
+    // instructions each) that cannot trigger here -- the exponent argument is <= 0 and 1 + 0.33 |x| >= 1
     const float ax = fabsf(x) * 0.70710678118654752f;          // |x| / sqrt(2)
-    const float e = __expf(-ax * ax);                          // exp(-x^2 / 2)
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    const float e = ex2_ftz(ax * ax * -1.4426950408889634f);   // exp(-x^2 / 2)
+    const float t = rcp_ftz(fmaf(0.3275911f, ax, 1.0f));
     const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
                                 0.254829592f);
-    const float erf_abs = 1.0f - poly * e;
-    const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+    const float h = 0.5f * poly * e;                           // 0.5 * erfc(|x| / sqrt 2) = Phi(-|x|)
+    const float cdf = x > 0.0f ? 1.0f - h : h;
     y = x * cdf;
     dy = fmaf(x * 0.3989422804014327f, e, cdf);
 }

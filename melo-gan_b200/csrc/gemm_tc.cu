@@ -1,6 +1,8 @@
 // gemm_tc.cu -- host helpers of the tcgen05 kernels: TMA tensor-map encoding, packed-weight scratch ring.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "gemm_tc.cuh"
 
 namespace mg {
@@ -25,6 +27,51 @@ Scratch g_scratch;
 }  // namespace
 
 Scratch& scratch() { return g_scratch; }
+// ---- packed-weight cache ----
+namespace {
+struct CacheEntry {
+    PackArgs key;
+    void* buf = nullptr;
+    size_t bytes = 0;
+    bool current = false;
+};
+std::vector<CacheEntry> g_cache;
+thread_local bool g_cache_on = false;   // set per API call from the context (set_cache_mode)
+bool same_key(const PackArgs& a, const PackArgs& b) {
+    if (a.W != b.W || a.ntaps != b.ntaps || a.N != b.N || a.K != b.K || a.f32 != b.f32 || a.w_nstride != b.w_nstride ||
+        a.w_kstride != b.w_kstride || a.n_perm_q != b.n_perm_q || a.n_perm_p != b.n_perm_p || a.k_perm_q != b.k_perm_q ||
+        a.k_perm_p != b.k_perm_p)
+        return false;
+    for (int t = 0; t < a.ntaps; ++t)
+        if (a.w_toff[t] != b.w_toff[t]) return false;
+    return true;
+}
+}  // namespace
+
+void* cache_lookup(const PackArgs& key, size_t bytes, bool* is_current) {
+    *is_current = false;
+    if (!g_cache_on) return nullptr;
+    for (CacheEntry& e : g_cache)
+        if (same_key(e.key, key) && e.bytes >= bytes) {
+            *is_current = e.current;
+            e.current = true;              // the caller packs now (stream-ordered before its consumer) if it was stale
+            return e.buf;
+        }
+    CacheEntry e;
+    e.key = key; e.bytes = bytes;
+    if (cudaMalloc(&e.buf, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // e.g. under stream capture
+    e.current = true;
+    g_cache.push_back(e);
+    return e.buf;
+}
+
+void weights_changed(const float* param, long long n) {
+    for (CacheEntry& e : g_cache)
+        if (!param || (e.key.W >= param && e.key.W < param + n)) e.current = false;
+}
+
+void set_cache_mode(bool on) { g_cache_on = on; }
+
 static Tuning g_tuning;
 Tuning& tuning() { return g_tuning; }
 static thread_local LaunchInfo g_last_launch;
@@ -162,7 +209,9 @@ int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, i
 }
 
 }  // namespace tc
+void tc_weights_changed(const float* param, long long n) { tc::weights_changed(param, n); }
 }  // namespace mg
 
 // A/B switch between the tcgen05 kernels and the CUDA-core kernels in bf16 mode (tests, profiling).
 extern "C" int mg_tc_enable(int on) { return mg::tc::set_enabled(on); }
+extern "C" int mg_weight_cache_invalidate(void) { mg::tc::weights_changed(nullptr, 0); return MG_OK; }

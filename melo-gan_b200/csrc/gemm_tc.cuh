@@ -359,18 +359,78 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
 // cycle they cost 11 of 37 ms.  Here every epilogue thread writes its 32 columns into a 128B-swizzled staging tile
 // (conflict-free: 8 consecutive rows hit 8 different 16-byte pieces) and ONE thread issues cp.async.bulk.tensor stores:
 // full 128-byte lines, no LSU work, asynchronous to the next tile's drain.
-template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TMSK>
-__device__ __forceinline__ void epi_math32(const TcTapArgs& P, const uint32_t (&raw)[32], const uint4 (&mreg)[4],
-                                           const TMSK* __restrict__ mrow, bool row_ok, const float4* sc4, const float4* bi4,
-                                           int c0, float (&x)[32], uint4 (&gpk)[4]) {
+// Epilogue math of 8 accumulator columns of one row: y = act(acc * scale + bias) [* mask], gd = act'(.) for GELU.
+// Working in chunks of 8 (one 16-byte staging store) keeps the live state at the 32 raw accumulators plus one chunk:
+// holding a whole row of results and derivatives (the first form of this drain) spilled at the 96-register cap of the
+// 576-thread CTA and the spills, not the arithmetic, were what the GELU layers ran at.
+template <int ACT, int MUL, bool AFF, bool AUX, bool GEN>
+__device__ __forceinline__ void epi_chunk8(const TcTapArgs& P, const uint32_t* raw8, const float (&ms)[8], const float4* sc4,
+                                           const float4* bi4, int col, float (&y8)[8], float (&gd)[8]) {
     const int act = GEN ? P.act : ACT, mul = GEN ? P.mul_mode : MUL;
-    const bool aff = GEN ? true : AFF, aux = GEN ? (P.aux != nullptr) : AUX;
+    const bool aff = GEN ? true : AFF;
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        float scv[4] = {1.f, 1.f, 1.f, 1.f}, biv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (aff) {
+            const float4 sc = sc4[(col + h) >> 2], bi = bi4[(col + h) >> 2];
+            scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+            biv[0] = bi.x; biv[1] = bi.y; biv[2] = bi.z; biv[3] = bi.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y = __uint_as_float(raw8[h + j]);
+            if (aff) y = fmaf(y, scv[j], biv[j]);
+            gd[h + j] = 0.0f;
+            if (act == ACT_RELU) y = fmaxf(y, 0.0f);
+            else if (act == ACT_LRELU) y = fmaxf(y, 0.2f * y);
+            else if (act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[h + j]); y = yy; }
+            if (mul == MUL_LRELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.2f);
+            else if (mul == MUL_RELU_SIGN) y = ms[h + j] > 0.0f ? y : 0.0f;
+            else if (mul == MUL_VALUE) y *= ms[h + j];
+            y8[h + j] = y;
+        }
+    }
+}
+
+// staging tile: boxes of [128 rows][128 bytes], piece p of row r at (p ^ (r & 7)) * 16
+__device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(x[4], x[5]), d = __floats2bfloat162_rn(x[6], x[7]);
+    return make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b), *reinterpret_cast<unsigned*>(&c),
+                      *reinterpret_cast<unsigned*>(&d));
+}
+__device__ __forceinline__ void stage8(unsigned char* staging, int r, int cc, const float (&x)[8], __nv_bfloat16) {
+    const int box = cc >> 6, pidx = (cc & 63) >> 3;
+    *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) = pack8(x);
+}
+__device__ __forceinline__ void stage8(unsigned char* staging, int r, int cc, const float (&x)[8], float) {
+#pragma unroll
+    for (int g4 = 0; g4 < 8; g4 += 4) {
+        const int c = cc + g4, box = c >> 5, pidx = (c & 31) >> 2;
+        *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) =
+            make_uint4(__float_as_uint(x[g4]), __float_as_uint(x[g4 + 1]), __float_as_uint(x[g4 + 2]), __float_as_uint(x[g4 + 3]));
+    }
+}
+
+// One epilogue thread = one accumulator row x 32 columns: math in chunks of 8, results (and the GELU derivative tile)
+// straight into the staging tile(s).
+template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TO, typename TMSK>
+__device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&raw)[32], const TMSK* __restrict__ mrow, bool row_ok,
+                                          const unsigned char* maskrow, const uint4 (&mreg)[4], const float4* sc4,
+                                          const float4* bi4, int c_begin, int r, unsigned char* stage_out,
+                                          unsigned char* stage_aux) {
+    const int mul = GEN ? P.mul_mode : MUL;
+    const bool aux = GEN ? (P.aux != nullptr) : AUX;
 #pragma unroll
     for (int g8 = 0; g8 < 32; g8 += 8) {
-        float ms[8], gd[8];
+        float ms[8], y8[8], gd[8];
         if (mul != MUL_NONE) {
             if (sizeof(TMSK) == 2) {
-                const uint4 mv = mreg[g8 >> 3];
+                uint4 mv = mreg[g8 >> 3];      // prefetched from global memory before the accumulator wait ...
+                if (maskrow) {                 // ... or read from the TMA-loaded mask tile (same swizzle as the staging tile)
+                    const int cc = c_begin + g8, box = cc >> 6, pidx = (cc & 63) >> 3;
+                    mv = *reinterpret_cast<const uint4*>(maskrow + box * 16384 + ((pidx ^ (r & 7)) << 4));
+                }
                 const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -381,63 +441,20 @@ __device__ __forceinline__ void epi_math32(const TcTapArgs& P, const uint32_t (&
 #pragma unroll
                 for (int h = 0; h < 8; h += 4) {
                     float t4[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (row_ok) ld4(mrow + c0 + g8 + h, t4);
+                    if (row_ok) ld4(mrow + c_begin + g8 + h, t4);
                     ms[h] = t4[0]; ms[h + 1] = t4[1]; ms[h + 2] = t4[2]; ms[h + 3] = t4[3];
                 }
             }
         }
-#pragma unroll
-        for (int h = 0; h < 8; h += 4) {
-            float scv[4] = {1.f, 1.f, 1.f, 1.f}, biv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (aff) {
-                const float4 sc = sc4[(c0 + g8 + h) >> 2], bi = bi4[(c0 + g8 + h) >> 2];
-                scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
-                biv[0] = bi.x; biv[1] = bi.y; biv[2] = bi.z; biv[3] = bi.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float y = __uint_as_float(raw[g8 + h + j]);
-                if (aff) y = fmaf(y, scv[j], biv[j]);
-                gd[h + j] = 0.0f;
-                if (act == ACT_RELU) y = fmaxf(y, 0.0f);
-                else if (act == ACT_LRELU) y = fmaxf(y, 0.2f * y);
-                else if (act == ACT_GELU) { float yy; gelu_fast(y, yy, gd[h + j]); y = yy; }
-                if (mul == MUL_LRELU_SIGN) y *= (ms[h + j] > 0.0f ? 1.0f : 0.2f);
-                else if (mul == MUL_RELU_SIGN) y = ms[h + j] > 0.0f ? y : 0.0f;
-                else if (mul == MUL_VALUE) y *= ms[h + j];
-                x[g8 + h + j] = y;
-            }
-        }
-        if (aux) {      // derivative tile, kept packed as bf16 until the staging buffer is free again (bf16 outputs only)
-            __nv_bfloat162 a = __floats2bfloat162_rn(gd[0], gd[1]), b = __floats2bfloat162_rn(gd[2], gd[3]);
-            __nv_bfloat162 c = __floats2bfloat162_rn(gd[4], gd[5]), d = __floats2bfloat162_rn(gd[6], gd[7]);
-            gpk[g8 >> 3] = make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b),
-                                      *reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
-        }
+        epi_chunk8<ACT, MUL, AFF, AUX, GEN>(P, &raw[g8], ms, sc4, bi4, c_begin + g8, y8, gd);
+        stage8(stage_out, r, c_begin + g8, y8, TO());
+        if (aux) stage8(stage_aux, r, c_begin + g8, gd, TO());
     }
 }
 
-// staging tile: boxes of [128 rows][128 bytes], piece p of row r at (p ^ (r & 7)) * 16
-__device__ __forceinline__ void stage_row32(unsigned char* staging, int r, int col, const float (&x)[32], __nv_bfloat16) {
-#pragma unroll
-    for (int g8 = 0; g8 < 32; g8 += 8) {
-        const int cc = col + g8, box = cc >> 6, pidx = (cc & 63) >> 3;
-        __nv_bfloat162 a = __floats2bfloat162_rn(x[g8], x[g8 + 1]), b = __floats2bfloat162_rn(x[g8 + 2], x[g8 + 3]);
-        __nv_bfloat162 c = __floats2bfloat162_rn(x[g8 + 4], x[g8 + 5]), d = __floats2bfloat162_rn(x[g8 + 6], x[g8 + 7]);
-        *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) =
-            make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b), *reinterpret_cast<unsigned*>(&c),
-                       *reinterpret_cast<unsigned*>(&d));
-    }
-}
-__device__ __forceinline__ void stage_row32(unsigned char* staging, int r, int col, const float (&x)[32], float) {
-#pragma unroll
-    for (int g4 = 0; g4 < 32; g4 += 4) {
-        const int cc = col + g4, box = cc >> 5, pidx = (cc & 31) >> 2;
-        *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) =
-            make_uint4(__float_as_uint(x[g4]), __float_as_uint(x[g4 + 1]), __float_as_uint(x[g4 + 2]), __float_as_uint(x[g4 + 3]));
-    }
-}
-
+// Drain one accumulator tile through the staging ring.  A tile takes one staging slot, two with a derivative (aux)
+// tile; with P.nsb slots in the ring the bulk stores of the previous tile keep draining while this one is computed
+// whenever nsb >= 2 x (slots per tile).
 template <int BN, int kEpi, typename TO, typename TMSK>
 __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
                                                const CUtensorMap* m_map, const float* s_bias, const float* s_scale,
@@ -446,11 +463,14 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
                                                unsigned char* staging0, int& sbuf, unsigned char* maskbuf,
                                                uint64_t* mask_bar, uint32_t mask_parity, int next_row0) {
     constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
+    constexpr size_t kStageTile = (size_t)128 * BN * sizeof(TO);
     const int q = warp & 3, r = q * 32 + lane;
     const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
     const bool row_ok = bb < P.B;
     const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
     const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
+    const bool has_aux = P.aux != nullptr;
+    const int per_tile = has_aux ? 2 : 1;
     uint4 mreg[4] = {};
     if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok && !(P.dbg & 8) && !P.tma_mask) {
 #pragma unroll
@@ -462,18 +482,16 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
     tmem_ld32_async(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin, raw);
     tmem_wait_ld();
     tc_fence_before();
-    // staging ring: with two tiles the bulk store of the previous tile keeps draining while this one is computed
-    constexpr size_t kStageTile = (size_t)128 * BN * sizeof(TO);
-    unsigned char* staging = staging0 + (size_t)sbuf * kStageTile;
-    if (et == 0) { if (P.nsb > 1) bulk_wait_read<1>(); else bulk_wait_read0(); }   // this staging tile has left
+    // the slot(s) this tile stages into have been read by the bulk stores issued from them one ring turn ago
+    if (et == 0) { if (P.nsb >= 2 * per_tile) bulk_wait_read<1>(); else bulk_wait_read0(); }
     asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");      // every thread holds its accumulator row: TMEM is free
     if (et == 0) mbar_arrive(empty_bar);
-    if (P.tma_mask) {                                            // this thread's 64 mask bytes from the TMA-loaded tile
+    unsigned char* stage_out = staging0 + (size_t)sbuf * kStageTile;
+    unsigned char* stage_aux = staging0 + (size_t)(sbuf + 1) * kStageTile;
+    const unsigned char* maskrow = nullptr;
+    if (P.tma_mask) {                                            // this thread's mask bytes come from the TMA-loaded tile
         mbar_wait(mask_bar, mask_parity);
-        const int box = c_begin >> 6, p0 = (c_begin & 63) >> 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            mreg[i] = *reinterpret_cast<const uint4*>(maskbuf + box * 16384 + r * 128 + (((p0 + i) ^ (r & 7)) << 4));
+        maskrow = maskbuf + r * 128;
     }
     const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
     const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
@@ -482,28 +500,30 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
     if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = 1 + P.act;
     else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
     else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
-    float x[32];
-    uint4 gpk[4] = {};
-#define MG_MATH(ACT_, MUL_, AFF_, AUX_, GEN_) \
-    epi_math32<ACT_, MUL_, AFF_, AUX_, GEN_, TMSK>(P, raw, mreg, Mb + o, row_ok, sc4, bi4, c_begin, x, gpk)
+    const bool mask_ok = row_ok && !(P.dbg & 8);
+#define MG_ROW(ACT_, MUL_, AFF_, AUX_, GEN_) \
+    epi_row32<ACT_, MUL_, AFF_, AUX_, GEN_, TO, TMSK>(P, raw, Mb + o, mask_ok, maskrow, mreg, sc4, bi4, c_begin, r, stage_out, stage_aux)
     switch (variant) {
-        case 1: MG_MATH(ACT_NONE, MUL_NONE, true, false, false); break;
-        case 2: MG_MATH(ACT_RELU, MUL_NONE, true, false, false); break;
-        case 3: MG_MATH(ACT_LRELU, MUL_NONE, true, false, false); break;
-        case 4: MG_MATH(ACT_GELU, MUL_NONE, true, true, false); break;
-        case 5: MG_MATH(ACT_NONE, MUL_LRELU_SIGN, false, false, false); break;
-        case 6: MG_MATH(ACT_NONE, MUL_RELU_SIGN, false, false, false); break;
-        case 7: MG_MATH(ACT_NONE, MUL_VALUE, false, false, false); break;
-        default: MG_MATH(ACT_NONE, MUL_NONE, true, true, true); break;
+        case 1: MG_ROW(ACT_NONE, MUL_NONE, true, false, false); break;
+        case 2: MG_ROW(ACT_RELU, MUL_NONE, true, false, false); break;
+        case 3: MG_ROW(ACT_LRELU, MUL_NONE, true, false, false); break;
+        case 4: MG_ROW(ACT_GELU, MUL_NONE, true, true, false); break;
+        case 5: MG_ROW(ACT_NONE, MUL_LRELU_SIGN, false, false, false); break;
+        case 6: MG_ROW(ACT_NONE, MUL_RELU_SIGN, false, false, false); break;
+        case 7: MG_ROW(ACT_NONE, MUL_VALUE, false, false, false); break;
+        default: MG_ROW(ACT_NONE, MUL_NONE, true, true, true); break;
     }
-#undef MG_MATH
-    stage_row32(staging, r, c_begin, x, TO());
+#undef MG_ROW
     fence_proxy_async();
     asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
     const int row0 = b0 * P.Mper + m0;
     if (et == 0 && !(P.dbg & 1)) {
 #pragma unroll
-        for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, staging + bx * 16384, n0 + bx * EPB, row0);
+        for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, stage_out + bx * 16384, n0 + bx * EPB, row0);
+        if (has_aux) {
+#pragma unroll
+            for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, stage_aux + bx * 16384, n0 + bx * EPB, row0);
+        }
         bulk_commit();
     }
     if (P.tma_mask && et == 0 && next_row0 >= 0) {               // every thread has read this tile's mask: fetch the next
@@ -511,25 +531,8 @@ __device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtenso
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, mask_bar, maskbuf + bx * 16384, n0 + bx * 64, next_row0);
     }
-    if (P.nsb > 1) sbuf ^= 1;
-    if (P.aux) {                                                 // second tile (activation derivative), bf16 only
-        staging = staging0 + (size_t)sbuf * kStageTile;
-        if (et == 0) { if (P.nsb > 1) bulk_wait_read<1>(); else bulk_wait_read0(); }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-#pragma unroll
-        for (int g8 = 0; g8 < 32; g8 += 8) {
-            const int cc = c_begin + g8, box = cc >> 6, pidx = (cc & 63) >> 3;
-            *reinterpret_cast<uint4*>(staging + box * 16384 + r * 128 + ((pidx ^ (r & 7)) << 4)) = gpk[g8 >> 3];
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-        if (et == 0) {
-#pragma unroll
-            for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, staging + bx * 16384, n0 + bx * EPB, row0);
-            bulk_commit();
-        }
-        if (P.nsb > 1) sbuf ^= 1;
-    }
+    sbuf += per_tile;
+    if (sbuf >= P.nsb) sbuf = 0;
 }
 
 template <int BN>
@@ -675,7 +678,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     const uint32_t a_tx = (uint32_t)(kTileM + P.halo) * kTileK * 2;                           // bytes one A box delivers
     const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
     unsigned char* staging = asm_ + (size_t)nstages * a_stage;                                 // [BN*sizeof(TO)/128][128][128 B]
-    unsigned char* maskbuf = staging + (size_t)(P.nsb > 1 ? 2 : 1) * 128 * BN * sizeof(TO);   // [BN/64][128][128 B] (bf16 masks)
+    unsigned char* maskbuf = staging + (size_t)P.nsb * 128 * BN * sizeof(TO);                  // [BN/64][128][128 B] (bf16 masks)
     const int n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
@@ -972,6 +975,13 @@ struct Scratch {             // ring of packed-weight slots (stream-ordered reus
 };
 Scratch& scratch();
 int ensure_scratch(size_t elems);   // allocate the ring (not capturable: call before any CUDA-graph capture)
+// Packed-weight cache (mg_gan_weight_cache): one persistent packed copy per (weight tensor, layout); an entry is
+// re-packed only after mg_adam_step touched its source (weights_changed) or after mg_weight_cache_invalidate.  Returns
+// the entry's buffer and whether it already holds the current weights; nullptr when the cache is off (or cannot
+// allocate, e.g. a new layout during CUDA-graph capture) -- the caller then packs into the scratch ring as before.
+void* cache_lookup(const PackArgs& key, size_t bytes, bool* is_current);
+void weights_changed(const float* param, long long n);
+void set_cache_mode(bool on);       // per API call, from the context's mg_gan_weight_cache setting (like set_tf32)
 bool enabled();              // MELOGAN_DISABLE_TC=1 forces the CUDA-core kernels (A/B testing)
 bool ws_enabled();           // MELOGAN_DISABLE_WS=1 keeps the non-persistent tensor-core kernel (A/B profiling)
 
@@ -1137,16 +1147,20 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ws) {
         // tiles leave through a staging tile + TMA bulk stores when the output rows are uniformly strided and the staging
         // tile fits next to >= 3 activation stages
-        const size_t staging = (size_t)128 * BN * sizeof(TO);
+        const int per_tile = a.aux ? 2 : 1;                        // staging slots one tile needs (result + derivative tile)
+        const size_t staging = (size_t)128 * BN * sizeof(TO) * per_tile;
         CUtensorMap om = am, xm = am;
-        a.tma_store = 0; a.nsb = 1;
-        if (tma_store_enabled() && !tn.no_tma_store && !a.accumulate && a.o_bstride == (long long)a.Mper * a.o_mstride &&
-            wbytes + 3 * a_stage + staging <= avail && (a.o_mstride * sizeof(TO)) % 16 == 0 &&
+        a.tma_store = 0; a.nsb = per_tile;
+        // output rows uniformly strided: conv outputs [b][m][n], and Linears (one row per sample)
+        const long long row_stride = a.Mper == 1 ? a.o_bstride : a.o_mstride;
+        if (tma_store_enabled() && !tn.no_tma_store && !a.accumulate &&
+            (a.Mper == 1 || a.o_bstride == (long long)a.Mper * a.o_mstride) &&
+            wbytes + 3 * a_stage + staging <= avail && (row_stride * sizeof(TO)) % 16 == 0 &&
             ((uintptr_t)((TO*)a.Out + a.o_off)) % 16 == 0 && (!a.aux || sizeof(TO) == 2)) {
-            int rc = make_out_map(&om, (TO*)a.Out + a.o_off, (int)sizeof(TO), a.N, rows, a.o_mstride);
+            int rc = make_out_map(&om, (TO*)a.Out + a.o_off, (int)sizeof(TO), a.N, rows, row_stride);
             if (rc != MG_OK) return rc;
             if (a.aux) {
-                rc = make_out_map(&xm, (TO*)a.aux + a.o_off, (int)sizeof(TO), a.N, rows, a.o_mstride);
+                rc = make_out_map(&xm, (TO*)a.aux + a.o_off, (int)sizeof(TO), a.N, rows, row_stride);
                 if (rc != MG_OK) return rc;
             }
             a.tma_store = 1;
@@ -1157,7 +1171,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         a.tma_mask = 0;
         if (a.tma_store && a.mul_mode != MUL_NONE && sizeof(TMSK) == 2 && mask_tma_enabled() && !tn.no_tma_mask &&
             wbytes + 3 * a_stage + staging + maskbytes <= avail && ((uintptr_t)((const TMSK*)a.mul_src + a.o_off)) % 16 == 0) {
-            const int rc = make_out_map(&mm, (const TMSK*)a.mul_src + a.o_off, 2, a.N, rows, a.o_mstride);
+            const int rc = make_out_map(&mm, (const TMSK*)a.mul_src + a.o_off, 2, a.N, rows, row_stride);
             if (rc != MG_OK) return rc;
             a.tma_mask = 1;
         }
@@ -1165,8 +1179,8 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         // L2) then overlaps the next tile's TMEM read and epilogue math instead of serialising with them
         if (a.tma_store && tn.staging_bufs != 1 &&
             wbytes + 4 * a_stage + 2 * staging + (a.tma_mask ? maskbytes : 0) <= avail)
-            a.nsb = 2;
-        const size_t extra = (a.tma_store ? staging * a.nsb : 0) + (a.tma_mask ? maskbytes : 0);
+            a.nsb = 2 * per_tile;
+        const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
@@ -1216,20 +1230,28 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     a.aux = P.aux; a.alpha = P.alpha; a.accumulate = P.accumulate;
     a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
 
-    // pack the weight taps [ntaps][N][K] bf16 into the next scratch slot
+    // pack the weight taps [ntaps][N][K] (bf16, or fp32 for the TF32 path): into the packed-weight cache when the host has
+    // promised that weights only change through mg_adam_step (melogan.trainer), else into the next scratch slot
     Scratch& sc = scratch();
     const size_t need = (size_t)P.ntaps * P.N * P.K;
-    if (need * EB > sc.slot_elems * 2) return 0;
-    __nv_bfloat16* wp = sc.slot[sc.next];
-    sc.next = (sc.next + 1) & 3;
     PackArgs pk{};
-    pk.W = P.W; pk.w_nstride = P.w_nstride; pk.w_kstride = P.w_kstride; pk.n_perm_q = P.n_perm_q; pk.n_perm_p = P.n_perm_p;
-    pk.k_perm_q = P.k_perm_q; pk.k_perm_p = P.k_perm_p; pk.ntaps = P.ntaps; pk.N = P.N; pk.K = P.K; pk.out = wp; pk.f32 = TF32 ? 1 : 0;
     for (int t = 0; t < P.ntaps; ++t) pk.w_toff[t] = P.w_toff[t];
-    long long blocks = ((long long)need + 255) / 256;
-    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    pack_weight_kernel<<<(int)blocks, 256, 0, st>>>(pk);
-    MG_LAUNCH_OK();
+    pk.W = P.W; pk.w_nstride = P.w_nstride; pk.w_kstride = P.w_kstride; pk.n_perm_q = P.n_perm_q; pk.n_perm_p = P.n_perm_p;
+    pk.k_perm_q = P.k_perm_q; pk.k_perm_p = P.k_perm_p; pk.ntaps = P.ntaps; pk.N = P.N; pk.K = P.K; pk.f32 = TF32 ? 1 : 0;
+    bool packed = false;
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(cache_lookup(pk, need * EB, &packed));
+    if (!wp) {
+        if (need * EB > sc.slot_elems * 2) return 0;
+        wp = sc.slot[sc.next];
+        sc.next = (sc.next + 1) & 3;
+    }
+    if (!packed) {
+        pk.out = wp;
+        long long blocks = ((long long)need + 255) / 256;
+        if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+        pack_weight_kernel<<<(int)blocks, 256, 0, st>>>(pk);
+        MG_LAUNCH_OK();
+    }
 
     CUtensorMap am, bm;
     int BN = (P.N % 128 == 0) ? 128 : 64;

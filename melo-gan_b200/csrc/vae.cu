@@ -353,7 +353,7 @@ extern "C" int mg_vae_forward(mg_vae* v, const float* x, const float* eps, int t
                               float* mu_out, float* logvar_out, void* stream) {
     MG_REQUIRE(v && v->bound, "vae_forward: context not bound");
     MG_REQUIRE(x && eps, "vae_forward: null pointer");
-    mg::tc::set_tf32(v->bf16);
+    mg::tc::set_tf32(v->bf16); mg::tc::set_cache_mode(false);
     return v->bf16 ? vae_forward<__nv_bfloat16>(v, x, eps, train, recon_out, z_out, mu_out, logvar_out, as_stream(stream))
                    : vae_forward<float>(v, x, eps, train, recon_out, z_out, mu_out, logvar_out, as_stream(stream));
 }
@@ -363,7 +363,7 @@ extern "C" int mg_vae_backward(mg_vae* v, const float* x, const float* drecon, c
     MG_REQUIRE(v && v->bound && v->has_grads, "vae_backward: context needs bound gradients");
     MG_REQUIRE(x && drecon, "vae_backward: null pointer");
     if (!v->fwd_done) { mg::set_error("vae_backward before vae_forward"); return MG_ERR_STATE; }
-    mg::tc::set_tf32(v->bf16);
+    mg::tc::set_tf32(v->bf16); mg::tc::set_cache_mode(false);
     return v->bf16 ? vae_backward<__nv_bfloat16>(v, x, drecon, dz, dmu, dlogvar, as_stream(stream))
                    : vae_backward<float>(v, x, drecon, dz, dmu, dlogvar, as_stream(stream));
 }

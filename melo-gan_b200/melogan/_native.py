@@ -32,10 +32,13 @@ _SIGNATURES = {
     "mg_extract_notes_abs": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_extract_notes_abs_host": ([_vp, _ll, _i, _vp, _vp, _vp, _vp], _i),
     "mg_adam_step": ([_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _i, _f, _ll, _vp, _vp, _vp], _i),
+    "mg_adam_step_clipped": ([_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _i, _f, _f, _vp, _ll, _vp, _vp, _vp], _i),
     "mg_launch_count": ([], _ll),
     "mg_probe_begin": ([_i], _i),
     "mg_probe_end": ([_vp], _i),
     "mg_tc_enable": ([_i], _i),
+    "mg_gan_weight_cache": ([_vp, _i], _i),
+    "mg_weight_cache_invalidate": ([], _i),
     "mg_device_copy": ([_vp, _vp, _ll, _vp], _i),
     "mg_rng_fill": ([_vp, _ll, _i, _f, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp], _i),
     "mg_rng_fill_counter": ([_vp, _ll, _i, _f, ctypes.c_ulonglong, _vp, ctypes.c_ulonglong, _vp], _i),

@@ -104,6 +104,11 @@ class GanEngine:
         with torch.cuda.device(self.device):
             _native.check(getattr(_native.lib(), name)(self._h, *args))
 
+    def weight_cache(self, on=True):
+        """Keep packed tensor-core weights between launches; only for callers whose parameters change through
+        FusedAdam.step alone (include/melogan_b200.h: mg_gan_weight_cache)."""
+        return bool(_native.lib().mg_gan_weight_cache(self._h, int(on)))
+
     def workspace_bytes(self):
         return int(_native.lib().mg_gan_workspace_bytes(self._h))
 

@@ -134,6 +134,8 @@ class GanTrainer:
         self.engine.bind(E.MOD_G, Pg, Gg)
         self.engine.bind(E.MOD_D, Pd, Gd)
         self.engine.bind(E.MOD_ED, Ped, None)
+        # parameters of this trainer change through FusedAdam.step only (which invalidates the packed copies it touches)
+        self.engine.weight_cache(True)
 
     # ---- randomness ----
     def _draw(self, critic):
@@ -204,6 +206,7 @@ class GanTrainer:
     def capture_cycle(self):
         """Captures train_cycle over static input buffers; returns them.  Run at least one eager cycle first
         (first calls allocate scratch, which capture forbids).
+        In 'conditioning' mode a fourth static buffer, self.s_conds (K, B, latent), holds the AE latents of the batches.
         Single GPU: the whole cycle is ONE graph.  Data parallel: NCCL all-reduces stay outside the graphs (capturing
         them deadlocked on this stack), so every step is two graphs -- [zero grads, draw, step body] and [Adam, loss
         accumulation] -- with the eager all-reduce of the flat gradient buffer between them on the same stream."""
@@ -211,11 +214,14 @@ class GanTrainer:
         self.s_reals = torch.zeros((K, B, self.cfg['MAX_NOTES'], self.cfg['NOTE_DIM']), device=dev)
         self.s_numerics = torch.zeros((K, B, self.cfg.get('NUMERIC_INPUT_DIM', 6)), device=dev)
         self.s_labels = torch.zeros(B, dtype=torch.int64, device=dev)
+        # 'conditioning' mode: the AE latents of the K batches are a fourth static input (self.s_conds); every captured
+        # step copies its slice into the persistent buffer the native context reads
+        self.s_conds = torch.zeros((K, B, self.cond_dim), device=dev) if self.cond_dim else None
         torch.cuda.synchronize(dev)
         if self.world == 1:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.train_cycle(self.s_reals, self.s_numerics, self.s_labels)
+                self.train_cycle(self.s_reals, self.s_numerics, self.s_labels, conds=self.s_conds)
             self._graph = g
             return self.s_reals, self.s_numerics, self.s_labels
         pool = torch.cuda.graph_pool_handle()
@@ -224,6 +230,8 @@ class GanTrainer:
         for i in range(K + 1):
             pre, post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(pre, pool=pool):
+                if self.s_conds is not None:
+                    self._set_cond(self.s_conds[min(i, K - 1)])
                 if i < K:
                     self._draw(critic=True)
                     self.opt_D.zero_grad()
@@ -259,11 +267,12 @@ class GanTrainer:
             self._allreduce(self.flat_d if i < K else self.flat_g)
             self._g_post[i].replay()
 
-    def launches_per_cycle(self):
-        return None
-
     def epoch_means(self):
-        """(D_loss, G_adv, G_emo) accumulated since the last call, one host sync (train_gan.py:254-264 log line)."""
+        """(D_loss, G_adv, G_emo) accumulated since the last call, one host sync (train_gan.py:254-264 log line).
+        Data parallel: every rank's loss is the mean over its shard, so the sums are all-reduced first -- the log line
+        is the mean over the global batch, not rank 0's shard."""
+        if self.world > 1:
+            D_.allreduce_sum_(self.loss_acc, self.pg)
         a = self.loss_acc.cpu()
         self.loss_acc.zero_()
         nd, ng = max(a[6].item(), 1.0), max(a[7].item(), 1.0)
@@ -288,4 +297,4 @@ class GanTrainer:
             self.opt_D.load_state_dict(ck['opt_D'])
         if 'rng_counter' in ck:
             self.rng_counter.copy_(ck['rng_counter'].to(self.rng_counter.device))
-        self.rebind()
+        self.rebind()                      # also invalidates the packed-weight cache (mg_gan_bind)

@@ -2,8 +2,10 @@
 halo tap groups, tile orders, staging rings and wgrad splits the bench actually runs) against a float64 contraction of
 the same bf16-exact operands, through the C ABI (mg_debug_layer_run calls the very helper the step bodies call).
 
-Bars: float32 results (pre-BatchNorm activations, weight gradients, TF32 Linears) within 1e-5 of the tensor's scale --
-only the fp32 accumulation order differs; bf16 results within ONE bf16 ulp of the float64 value.  A wrong halo row, tap
+Bars: float32 results (pre-BatchNorm activations, TF32 Linears) within 1e-5 of the tensor's scale (x sqrt(K/1024) for
+the 16384-long reduction of decoder.pre.2's dgrad), weight gradients (fp32 atomics over up to 3 M rows) within 1e-4 --
+only the fp32 accumulation order differs; bf16 results within ONE bf16 ulp of the float64 value (measured: 0.50, i.e.
+correctly rounded).  A wrong halo row, tap
 or tile edge is an O(1) error and cannot hide here (the whole-step bf16 tests allow 4-8 % for mask flips)."""
 import os
 
@@ -16,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 B = int(os.environ.get("MELOGAN_TEST_LAYER_BATCH", "8192"))
 SPECS = TL.cycle_layers(B)
-F32_TOL, WGRAD_TOL, ULP_TOL = 1e-5, 5e-5, 1.0
+F32_TOL, WGRAD_TOL, ULP_TOL = 1e-5, 1e-4, 1.0
 
 
 def _check(layer, info):
@@ -41,7 +43,10 @@ def _check(layer, info):
     if stored:
         assert worst_ulp <= ULP_TOL, f"{s['name']}: {worst_ulp:.2f} bf16 ulps off (rel {worst_rel:.2e}) ({info})"
     else:
-        assert worst_rel <= F32_TOL, f"{s['name']}: rel err {worst_rel:.3e} ({info})"
+        # fp32 accumulation noise grows with the reduction length (decoder.pre.2's dgrad sums 16384 products)
+        ktot = s["Cin"] * max(s["ks"], 1) if s["op"] != 4 else s["Cout"]
+        tol = F32_TOL * max(1.0, (ktot / 1024.0) ** 0.5)
+        assert worst_rel <= tol, f"{s['name']}: rel err {worst_rel:.3e} > {tol:.1e} ({info})"
     return worst_rel, worst_ulp
 
 
