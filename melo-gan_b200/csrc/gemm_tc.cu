@@ -171,6 +171,29 @@ int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, 
     return MG_OK;
 }
 
+int make_act_map_interleaved(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
+                             int box_samples, int elem_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MG_ERR_CUDA; }
+    const cuuint64_t row_bytes = (cuuint64_t)C * (cuuint64_t)elem_bytes;
+    cuuint64_t gdim[4], gstr[3];
+    gdim[0] = (cuuint64_t)C; gdim[1] = (cuuint64_t)B;
+    gstr[0] = row_bytes * (cuuint64_t)L;                     // sample
+    if (stride == 1) { gdim[2] = 1; gdim[3] = (cuuint64_t)L; gstr[1] = row_bytes; gstr[2] = row_bytes; }
+    else { gdim[2] = 2; gdim[3] = (cuuint64_t)(L / 2); gstr[1] = row_bytes; gstr[2] = 2 * row_bytes; }
+    const cuuint32_t box[4] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_samples, 1, (cuuint32_t)box_rows};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(interleaved act C=%d L=%d B=%lld stride=%d box=%d,%d) failed: %d", C, L, B, stride,
+                  box_rows, box_samples, (int)r);
+        return MG_ERR_CUDA;
+    }
+    return MG_OK;
+}
+
 int make_view_map(CUtensorMap* map, const void* base, long long inner, long long planes, long long plane_stride,
                   long long rows, long long row_stride, long long samples, long long sample_stride, int box_rows,
                   int box_samples) {

@@ -206,6 +206,11 @@ struct TcTapArgs {
     int g_p[kTcMaxTaps], g_dmin[kTcMaxTaps], g_first[kTcMaxTaps], g_count[kTcMaxTaps], g_tap[kTcMaxTaps];
     int mpt, bpt;                       // tile = bpt samples x mpt rows, mpt * bpt = 128
     int Mper, B, N;
+    int mper_shift, mpt_shift;          // log2(Mper), log2(mpt): both are powers of two (set by run_tc_tap)
+    int il, il_shift;                   // halo tiles of bpt > 1 samples are loaded ROW-INTERLEAVED ([row][sample][k], il = bpt):
+                                        // a tap's row shift d is then the byte offset d * il * 128 for every sample of the tile
+                                        // at once (sample-major boxes cannot be entered at a common shift).  Accumulator lane r
+                                        // holds tile row (r % il) * mpt + r / il.  il = 1: plain layout, lane = row.
     int n_perm_q, n_perm_p;             // bias index permutation (the packed weight is already permuted)
     void* Out; long long o_bstride; int o_mstride; int o_off;
     const float* bias; const float* col_scale; int act;
@@ -310,7 +315,8 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
                                            int b0, int m0, int n0, int warp, int lane, uint64_t* wait_bar,
                                            uint32_t wait_parity, int c_begin = 0) {
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int r = q * 32 + lane;             // tile row
+        const int lane_row = q * 32 + lane;
+        const int r = ((lane_row & (P.il - 1)) << P.mpt_shift) + (lane_row >> P.il_shift);   // tile row (see TcTapArgs::il)
         const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
         const bool row_ok = bb < P.B && !(P.dbg & 1);
         TO* __restrict__ Ob = static_cast<TO*>(P.Out);
@@ -363,7 +369,7 @@ __device__ __forceinline__ void drain_tile(const TcTapArgs& P, const float* s_bi
 // Working in chunks of 8 (one 16-byte staging store) keeps the live state at the 32 raw accumulators plus one chunk:
 // holding a whole row of results and derivatives (the first form of this drain) spilled at the 96-register cap of the
 // 576-thread CTA and the spills, not the arithmetic, were what the GELU layers ran at.
-template <int ACT, int MUL, bool AFF, bool AUX, bool GEN>
+template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool SCL = true>
 __device__ __forceinline__ void epi_chunk8(const TcTapArgs& P, const uint32_t* raw8, const float (&ms)[8], const float4* sc4,
                                            const float4* bi4, int col, float (&y8)[8], float (&gd)[8]) {
     const int act = GEN ? P.act : ACT, mul = GEN ? P.mul_mode : MUL;
@@ -372,14 +378,17 @@ __device__ __forceinline__ void epi_chunk8(const TcTapArgs& P, const uint32_t* r
     for (int h = 0; h < 8; h += 4) {
         float scv[4] = {1.f, 1.f, 1.f, 1.f}, biv[4] = {0.f, 0.f, 0.f, 0.f};
         if (aff) {
-            const float4 sc = sc4[(col + h) >> 2], bi = bi4[(col + h) >> 2];
-            scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+            const float4 bi = bi4[(col + h) >> 2];
             biv[0] = bi.x; biv[1] = bi.y; biv[2] = bi.z; biv[3] = bi.w;
+            if (SCL) {                        // SCL = false: no folded-BN scale and alpha == 1 -- one FADD, half the LDS
+                const float4 sc = sc4[(col + h) >> 2];
+                scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float y = __uint_as_float(raw8[h + j]);
-            if (aff) y = fmaf(y, scv[j], biv[j]);
+            if (aff) y = SCL ? fmaf(y, scv[j], biv[j]) : y + biv[j];
             gd[h + j] = 0.0f;
             if (act == ACT_RELU) y = fmaxf(y, 0.0f);
             else if (act == ACT_LRELU) y = fmaxf(y, 0.2f * y);
@@ -414,7 +423,7 @@ __device__ __forceinline__ void stage8(unsigned char* staging, int r, int cc, co
 
 // One epilogue thread = one accumulator row x 32 columns: math in chunks of 8, results (and the GELU derivative tile)
 // straight into the staging tile(s).
-template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TO, typename TMSK>
+template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TO, typename TMSK, bool SCL = true>
 __device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&raw)[32], const TMSK* __restrict__ mrow, bool row_ok,
                                           const unsigned char* maskrow, const uint4 (&mreg)[4], const float4* sc4,
                                           const float4* bi4, int c_begin, int r, unsigned char* stage_out,
@@ -446,93 +455,106 @@ __device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&r
                 }
             }
         }
-        epi_chunk8<ACT, MUL, AFF, AUX, GEN>(P, &raw[g8], ms, sc4, bi4, c_begin + g8, y8, gd);
+        epi_chunk8<ACT, MUL, AFF, AUX, GEN, SCL>(P, &raw[g8], ms, sc4, bi4, c_begin + g8, y8, gd);
         stage8(stage_out, r, c_begin + g8, y8, TO());
         if (aux) stage8(stage_aux, r, c_begin + g8, gd, TO());
     }
 }
 
-// Drain one accumulator tile through the staging ring.  A tile takes one staging slot, two with a derivative (aux)
-// tile; with P.nsb slots in the ring the bulk stores of the previous tile keep draining while this one is computed
-// whenever nsb >= 2 x (slots per tile).
-template <int BN, int kEpi, typename TO, typename TMSK>
-__device__ __forceinline__ void drain_tile_tma(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
-                                               const CUtensorMap* m_map, const float* s_bias, const float* s_scale,
-                                               uint32_t tmem_acc, int b0, int m0, int n0, int warp, int lane, int et,
-                                               uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int c_begin,
-                                               unsigned char* staging0, int& sbuf, unsigned char* maskbuf,
-                                               uint64_t* mask_bar, uint32_t mask_parity, int next_row0) {
+// The whole epilogue of the weight-stationary kernel for one compile-time epilogue variant: the tile loop lives INSIDE
+// the variant (ncu, round 2: with the variant switch, three integer divisions for the tile coordinates and two
+// 512-thread barriers per tile the drain executed ~470 instructions per warp and tile of which ~150 were the epilogue
+// math; issue-bound at 4 warps per scheduler, it -- not HBM, not the tensor pipe -- set the pace of every layer).
+//   * tile coordinates by shift/mask (Mper and mpt are powers of two), everything tile-invariant hoisted;
+//   * TMEM hand-back by one mbarrier arrive per WARP right after its tcgen05.ld (no CTA-wide barrier);
+//   * ONE named barrier per tile (staging tile complete -> TMA store); the staging slot is recycled by waiting, before
+//     that barrier, for the bulk store issued one tile earlier (it has had a whole tile of math to drain).
+template <int BN, int kEpi, int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool SCL, typename TO, typename TMSK, typename HDR>
+__device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
+                                                 const CUtensorMap* m_map, HDR& H, uint32_t tmem0, int n0, int mtiles,
+                                                 unsigned char* staging0, unsigned char* maskbuf) {
     constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
     constexpr size_t kStageTile = (size_t)128 * BN * sizeof(TO);
-    const int q = warp & 3, r = q * 32 + lane;
-    const int bb = b0 + r / P.mpt, mm = m0 + r % P.mpt;
-    const bool row_ok = bb < P.B;
-    const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
-    const long long o = (long long)bb * P.o_bstride + (long long)mm * P.o_mstride + P.o_off + n0;
-    const bool has_aux = P.aux != nullptr;
+    const int et = threadIdx.x - 64, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, lane_row = q * 32 + lane, c_begin = (et >> 7) * 32;
+    const int r = ((lane_row & (P.il - 1)) << P.mpt_shift) + (lane_row >> P.il_shift);   // tile row this TMEM lane holds
+    const bool has_aux = GEN ? (P.aux != nullptr) : AUX;
     const int per_tile = has_aux ? 2 : 1;
-    uint4 mreg[4] = {};
-    if (sizeof(TMSK) == 2 && P.mul_mode != MUL_NONE && row_ok && !(P.dbg & 8) && !P.tma_mask) {
+    const bool ring2 = P.nsb >= 2 * per_tile;        // a free staging slot while the previous tile's store drains
+    const int mul = GEN ? P.mul_mode : MUL;
+    const bool tma_mask = mul != MUL_NONE && P.tma_mask;
+    const bool reg_mask = mul != MUL_NONE && !P.tma_mask;
+    const int rdiv = r >> P.mpt_shift, rmod = r & (P.mpt - 1);
+    const TMSK* __restrict__ Mb = static_cast<const TMSK*>(P.mul_src);
+    const float4* sc4 = reinterpret_cast<const float4*>(H.scale);
+    const float4* bi4 = reinterpret_cast<const float4*>(H.bias);
+    const uint32_t tmem_lane = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin;
+    const unsigned char* maskrow = tma_mask ? maskbuf + r * 128 : nullptr;
+    const int gstep = (int)gridDim.x;
+    int sbuf = 0, tcount = 0;
+    if (tma_mask && et == 0 && (int)blockIdx.x < mtiles) {
+        const int t0 = P.reverse ? mtiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
+        mbar_expect_tx(&H.mask_full, (uint32_t)(BN / 64) * 16384u);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(Mb + o + c_begin) + i);
+        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, &H.mask_full, maskbuf + bx * 16384, n0 + bx * 64, t0 * 128);
     }
-    mbar_wait(full_bar, parity);
-    tc_fence_after();
-    uint32_t raw[32];
-    tmem_ld32_async(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin, raw);
-    tmem_wait_ld();
-    tc_fence_before();
-    // the slot(s) this tile stages into have been read by the bulk stores issued from them one ring turn ago
-    if (et == 0) { if (P.nsb >= 2 * per_tile) bulk_wait_read<1>(); else bulk_wait_read0(); }
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");      // every thread holds its accumulator row: TMEM is free
-    if (et == 0) mbar_arrive(empty_bar);
-    unsigned char* stage_out = staging0 + (size_t)sbuf * kStageTile;
-    unsigned char* stage_aux = staging0 + (size_t)(sbuf + 1) * kStageTile;
-    const unsigned char* maskrow = nullptr;
-    if (P.tma_mask) {                                            // this thread's mask bytes come from the TMA-loaded tile
-        mbar_wait(mask_bar, mask_parity);
-        maskrow = maskbuf + r * 128;
-    }
-    const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
-    const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
-    const bool affine = P.bias != nullptr || P.col_scale != nullptr || P.alpha != 1.0f;
-    int variant = 0;
-    if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = 1 + P.act;
-    else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
-    else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
-    const bool mask_ok = row_ok && !(P.dbg & 8);
-#define MG_ROW(ACT_, MUL_, AFF_, AUX_, GEN_) \
-    epi_row32<ACT_, MUL_, AFF_, AUX_, GEN_, TO, TMSK>(P, raw, Mb + o, mask_ok, maskrow, mreg, sc4, bi4, c_begin, r, stage_out, stage_aux)
-    switch (variant) {
-        case 1: MG_ROW(ACT_NONE, MUL_NONE, true, false, false); break;
-        case 2: MG_ROW(ACT_RELU, MUL_NONE, true, false, false); break;
-        case 3: MG_ROW(ACT_LRELU, MUL_NONE, true, false, false); break;
-        case 4: MG_ROW(ACT_GELU, MUL_NONE, true, true, false); break;
-        case 5: MG_ROW(ACT_NONE, MUL_LRELU_SIGN, false, false, false); break;
-        case 6: MG_ROW(ACT_NONE, MUL_RELU_SIGN, false, false, false); break;
-        case 7: MG_ROW(ACT_NONE, MUL_VALUE, false, false, false); break;
-        default: MG_ROW(ACT_NONE, MUL_NONE, true, true, true); break;
-    }
-#undef MG_ROW
-    fence_proxy_async();
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-    const int row0 = b0 * P.Mper + m0;
-    if (et == 0 && !(P.dbg & 1)) {
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < mtiles; tile += gstep, ++tcount) {
+        const int acc = tcount & 1;
+        const int row0 = (P.reverse ? mtiles - 1 - tile : tile) * 128;
+        const int bb = (row0 >> P.mper_shift) + rdiv;
+        const bool row_ok = bb < P.B;
+        uint4 mreg[4] = {};
+        const TMSK* mrow = nullptr;
+        if (reg_mask) {                                          // per-thread mask loads, in flight during the accumulator wait
+            const long long o = (long long)bb * P.o_bstride + (long long)((row0 & (P.Mper - 1)) + rmod) * P.o_mstride + P.o_off + n0;
+            mrow = Mb + o;
+            if (sizeof(TMSK) == 2 && row_ok && !(P.dbg & 8)) {
 #pragma unroll
-        for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, stage_out + bx * 16384, n0 + bx * EPB, row0);
-        if (has_aux) {
-#pragma unroll
-            for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, stage_aux + bx * 16384, n0 + bx * EPB, row0);
+                for (int i = 0; i < 4; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(mrow + c_begin) + i);
+            }
         }
-        bulk_commit();
-    }
-    if (P.tma_mask && et == 0 && next_row0 >= 0) {               // every thread has read this tile's mask: fetch the next
-        mbar_expect_tx(mask_bar, (uint32_t)(BN / 64) * 16384u);
+        mbar_wait(&H.tmem_full[acc], (uint32_t)(tcount >> 1) & 1u);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32_async(tmem_lane + (uint32_t)(acc * BN), raw);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&H.tmem_empty[acc]);          // this warp's lanes of the accumulator are free again
+        if (!ring2) {                                            // single staging slot: the previous store must have left it
+            if (et == 0) bulk_wait_read0();
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+        }
+        unsigned char* stage_out = staging0 + (size_t)sbuf * kStageTile;
+        unsigned char* stage_aux = staging0 + (size_t)(sbuf + 1) * kStageTile;
+        if (tma_mask) mbar_wait(&H.mask_full, (uint32_t)tcount & 1u);
+        epi_row32<ACT, MUL, AFF, AUX, GEN, TO, TMSK, SCL>(P, raw, mrow, row_ok && !(P.dbg & 8), maskrow, mreg, sc4, bi4, c_begin, r,
+                                                          stage_out, stage_aux);
+        fence_proxy_async();
+        if (ring2 && et == 0) bulk_wait_read0();                 // the store issued one tile ago has drained its slot
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+        if (et == 0) {
+            if (!(P.dbg & 1)) {
 #pragma unroll
-        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, mask_bar, maskbuf + bx * 16384, n0 + bx * 64, next_row0);
+                for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, stage_out + bx * 16384, n0 + bx * EPB, row0);
+                if (has_aux) {
+#pragma unroll
+                    for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, stage_aux + bx * 16384, n0 + bx * EPB, row0);
+                }
+                bulk_commit();
+            }
+            if (tma_mask && tile + gstep < mtiles) {             // every thread has read this tile's mask: fetch the next
+                const int nrow0 = (P.reverse ? mtiles - 1 - (tile + gstep) : tile + gstep) * 128;
+                mbar_expect_tx(&H.mask_full, (uint32_t)(BN / 64) * 16384u);
+#pragma unroll
+                for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, &H.mask_full, maskbuf + bx * 16384, n0 + bx * 64, nrow0);
+            }
+        }
+        sbuf += per_tile;
+        if (sbuf >= P.nsb) sbuf = 0;
     }
-    sbuf += per_tile;
-    if (sbuf >= P.nsb) sbuf = 0;
+    if (et == 0) bulk_wait0();                                   // all bulk stores complete before the CTA retires
 }
 
 template <int BN>
@@ -675,7 +697,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
     constexpr uint32_t kWBytes = BN * kTileK * 2;
-    const uint32_t a_tx = (uint32_t)(kTileM + P.halo) * kTileK * 2;                           // bytes one A box delivers
+    const uint32_t a_tx = (uint32_t)(kTileM + P.halo * P.il) * kTileK * 2;                    // bytes one A box delivers
     const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
     unsigned char* staging = asm_ + (size_t)nstages * a_stage;                                 // [BN*sizeof(TO)/128][128][128 B]
     unsigned char* maskbuf = staging + (size_t)P.nsb * 128 * BN * sizeof(TO);                  // [BN/64][128][128 B] (bf16 masks)
@@ -684,7 +706,11 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstages; ++s) { mbar_init(&H.full[s], 1); mbar_init(&H.empty[s], 1); }
         mbar_init(&H.wfull, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&H.tmem_full[a], 1); mbar_init(&H.tmem_empty[a], 1); }
+        // TMA-store drain: every epilogue WARP hands its TMEM lanes back; row-per-thread drain: one arrive after a barrier
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&H.tmem_full[a], 1);
+            mbar_init(&H.tmem_empty[a], P.tma_store ? (uint32_t)(WsCfg<BN>::kEpiThreads / 32) : 1u);
+        }
         mbar_init(&H.mask_full, 1);
         fence_barrier_init();
         fence_proxy_async();
@@ -699,7 +725,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                 H.ldtab[g * P.kblocks + kc] = make_int4(kc * P.ktile, P.g_p[g], P.g_dmin[g], 0);
                 for (int j = 0; j < P.g_count[g]; ++j, ++i) {
                     const int t = P.g_tap[P.g_first[g] + j];
-                    H.mmatab[i] = make_int4((P.a_dm[t] - P.g_dmin[g]) * 128, (t * P.kblocks + kc) * (int)kWBytes,
+                    H.mmatab[i] = make_int4((P.a_dm[t] - P.g_dmin[g]) * P.il * 128, (t * P.kblocks + kc) * (int)kWBytes,
                                             j == P.g_count[g] - 1, 0);
                 }
             }
@@ -709,10 +735,11 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     tc_fence_after();
     const uint32_t tmem0 = H.tmem_base;
 
-    auto tile_coords = [&](int tile, int& b0, int& m0) {
+    auto tile_coords = [&](int tile, int& b0, int& m0) {      // tile -> first sample, first row inside it (powers of two)
         if (P.reverse) tile = mtiles - 1 - tile;
-        if (P.mpt == kTileM) { const int tm = P.Mper / kTileM; b0 = tile / tm; m0 = (tile % tm) * kTileM; }
-        else { b0 = tile * P.bpt; m0 = 0; }
+        const int row0 = tile * kTileM;
+        b0 = row0 >> P.mper_shift;
+        m0 = row0 & (P.Mper - 1);
     };
 
     if (warp == 0) {
@@ -733,7 +760,8 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                     if (P.dbg & 4) { mbar_expect_tx(&H.full[s], 0); }
                     else {
                         mbar_expect_tx(&H.full[s], a_tx);
-                        tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, L.x, L.y, m0 + L.z, b0);
+                        if (P.il > 1) tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, L.x, b0, L.y, m0 + L.z);
+                        else tma_load_4d(&a_map, &H.full[s], asm_ + (size_t)s * a_stage, L.x, L.y, m0 + L.z, b0);
                     }
                     if (++s == nstages) { s = 0; ph ^= 1; }
                 }
@@ -786,37 +814,44 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             H.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-        int tcount = 0, sbuf = 0;
-        for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
-            const int acc = tcount & 1;
-            int b0, m0;
-            tile_coords(tile, b0, m0);
-            if (P.tma_store) {
-                int next_row0 = -1;
-                if (tile + (int)gridDim.x < mtiles) {
-                    int nb0, nm0;
-                    tile_coords(tile + (int)gridDim.x, nb0, nm0);
-                    next_row0 = nb0 * P.Mper + nm0;
-                }
-                if (P.tma_mask && tcount == 0 && et == 0) {
-                    mbar_expect_tx(&H.mask_full, (uint32_t)(BN / 64) * 16384u);
-#pragma unroll
-                    for (int bx = 0; bx < BN / 64; ++bx)
-                        tma_load_2d(&m_map, &H.mask_full, maskbuf + bx * 16384, n0 + bx * 64, b0 * P.Mper + m0);
-                }
-                drain_tile_tma<BN, kEpi, TO, TMSK>(P, &o_map, &x_map, &m_map, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0,
-                                                   m0, n0, warp, lane, et, &H.tmem_full[acc], (tcount >> 1) & 1,
-                                                   &H.tmem_empty[acc], grp * 32, staging, sbuf, maskbuf, &H.mask_full, tcount & 1,
-                                                   next_row0);
-                continue;
+        if (P.tma_store) {
+            // one tile loop per compile-time epilogue variant (see ws_epilogue_loop)
+            const bool scaled = P.col_scale != nullptr || P.alpha != 1.0f;
+            const bool affine = P.bias != nullptr || scaled;
+            int variant = 0;
+            if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;     // 1..3 / 8..10
+            else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
+            else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
+#define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
+    ws_epilogue_loop<BN, kEpi, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK>(P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, \
+                                                                             staging, maskbuf)
+            switch (variant) {
+                case 1: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, true); break;
+                case 2: MG_LOOP(ACT_RELU, MUL_NONE, true, false, false, true); break;
+                case 3: MG_LOOP(ACT_LRELU, MUL_NONE, true, false, false, true); break;
+                case 4: MG_LOOP(ACT_GELU, MUL_NONE, true, true, false, true); break;
+                case 5: MG_LOOP(ACT_NONE, MUL_LRELU_SIGN, false, false, false, true); break;
+                case 6: MG_LOOP(ACT_NONE, MUL_RELU_SIGN, false, false, false, true); break;
+                case 7: MG_LOOP(ACT_NONE, MUL_VALUE, false, false, false, true); break;
+                case 8: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, false); break;
+                case 9: MG_LOOP(ACT_RELU, MUL_NONE, true, false, false, false); break;
+                case 10: MG_LOOP(ACT_LRELU, MUL_NONE, true, false, false, false); break;
+                default: MG_LOOP(ACT_NONE, MUL_NONE, true, true, true, true); break;
             }
-            drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
-                                         &H.tmem_full[acc], (tcount >> 1) & 1, grp * 32);
-            tc_fence_before();
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");   // every epilogue thread has read its TMEM lanes
-            if (et == 0) mbar_arrive(&H.tmem_empty[acc]);
+#undef MG_LOOP
+        } else {
+            int tcount = 0;
+            for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                int b0, m0;
+                tile_coords(tile, b0, m0);
+                drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
+                                             &H.tmem_full[acc], (tcount >> 1) & 1, grp * 32);
+                tc_fence_before();
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");   // every epilogue thread has read its TMEM lanes
+                if (et == 0) mbar_arrive(&H.tmem_empty[acc]);
+            }
         }
-        if (P.tma_store && et == 0) bulk_wait0();             // all bulk stores complete before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -968,6 +1003,7 @@ static __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 struct Scratch {             // ring of packed-weight slots (stream-ordered reuse)
     __nv_bfloat16* slot[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t slot_elems = 0;
@@ -989,6 +1025,10 @@ bool ws_enabled();           // MELOGAN_DISABLE_WS=1 keeps the non-persistent te
 //   stride 1: dims (C, 1, L, B);  stride 2: dims (C, 2, L/2, B)
 int make_act_map(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
                  int box_samples, int elem_bytes = 2);
+// the same activation as dims (k, sample, parity, row): a box of box_samples x box_rows lands in shared memory as
+// [row][sample][k] (see TcTapArgs::il); coordinates (k, first sample, plane, first row)
+int make_act_map_interleaved(CUtensorMap* map, const void* base, int C, int L, long long B, int stride, int box_rows,
+                             int box_samples, int elem_bytes = 2);
 // general 4-D bf16 view: dims (64-wide inner box over `inner` elements, planes, rows, samples) with explicit
 // element strides; used for the overlapping note windows and the row-mod-P planes of the banded layers
 int make_view_map(CUtensorMap* map, const void* base, long long inner, long long planes, long long plane_stride,
@@ -1045,8 +1085,6 @@ int launch_tc_wgrad(const CUtensorMap& gm, const CUtensorMap& am, const TcWgradA
     MG_LAUNCH_OK();
     return MG_OK;
 }
-
-static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 // Tap groups for the weight-stationary kernel.  halo_max = 0: every tap is its own group (one 128-row tile per tap).
 // Otherwise taps of the same plane whose row shifts lie within halo_max rows share one tile with a halo.
@@ -1105,6 +1143,14 @@ template <typename TO, typename TMSK, bool TF32 = false>
 int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN, int K, cudaStream_t st,
                const CUtensorMap* am_halo = nullptr) {
     a.ktile = TF32 ? 32 : 64;
+    if (!is_pow2(a.Mper) || !is_pow2(a.mpt) || a.mpt * a.bpt != kTileM || (a.Mper > kTileM && a.Mper % kTileM)) {
+        set_error("run_tc_tap: Mper=%d mpt=%d bpt=%d is not a power-of-two tiling", a.Mper, a.mpt, a.bpt);
+        return MG_ERR_INVALID;
+    }
+    a.mper_shift = 0; while ((1 << a.mper_shift) < a.Mper) ++a.mper_shift;
+    a.mpt_shift = 0; while ((1 << a.mpt_shift) < a.mpt) ++a.mpt_shift;
+    if (!am_halo || a.il < 1) a.il = 1;                  // interleaved halo tiles only come with a halo map
+    a.il_shift = 0; while ((1 << a.il_shift) < a.il) ++a.il_shift;
     const long long rows = (long long)a.B * a.Mper;
     const int mtiles = (int)((rows + 127) / 128);
     // algorithmic traffic: the activation once, the output (and derivative tile), the mask tile
@@ -1127,7 +1173,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         if (tn.reverse >= 0) a.reverse = tn.reverse;
     }
     { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = tn.dbg >= 0 ? tn.dbg : dbg; }
-    const size_t a_stage = (((size_t)(128 + a.halo) * 128) + 1023) / 1024 * 1024;
+    const size_t a_stage = (((size_t)(128 + a.halo * a.il) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
     const bool ws = ws_enabled() && !tn.no_ws && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x &&
                     a.ntaps * (K / a.ktile) <= kWsMaxLoads;
@@ -1190,6 +1236,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
                            : launch_tc_tap_ws<64, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
+    a.il = 1; a.il_shift = 0;                            // one tile per CTA: plain boxes, accumulator lane = tile row
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK, TF32>(am, bm, a, mtiles, st)
                        : launch_tc_tap<64, TO, TMSK, TF32>(am, bm, a, mtiles, st);
 }
@@ -1270,12 +1317,17 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     if (rc != MG_OK) return rc;
     CUtensorMap amh;
     const CUtensorMap* halo_map = nullptr;
-    if (reuse_enabled() && !tuning().no_reuse && a.mpt == 128 && P.ntaps > 1) {
+    if (reuse_enabled() && !tuning().no_reuse && P.ntaps > 1 && P.Mper > 1) {
         build_tap_groups(a, 8);
         if (a.ngroups < a.ntaps) {
-            rc = make_act_map(&amh, P.A, P.K, LA, P.B, stride, 128 + a.halo, 1, EB);
+            // one sample per tile: a box of 128 + halo rows; several samples per tile (Mper < 128): the same rows of all bpt
+            // samples row-interleaved, so that one row shift addresses every sample of the tile (TcTapArgs::il)
+            if (a.bpt == 1) rc = make_act_map(&amh, P.A, P.K, LA, P.B, stride, 128 + a.halo, 1, EB);
+            else { rc = make_act_map_interleaved(&amh, P.A, P.K, LA, P.B, stride, a.mpt + a.halo, a.bpt, EB); a.il = a.bpt; }
             if (rc != MG_OK) return rc;
             halo_map = &amh;
+        } else {
+            build_tap_groups(a, 0);
         }
     }
     rc = run_tc_tap<TO, TMSK, TF32>(am, bm, a, BN, P.K, st, halo_map);

@@ -15,6 +15,8 @@
 //            output slot (integer prefix, exact), then coalesced stores of the note fields.
 // All float32 arithmetic uses __f*_rn intrinsics so nvcc cannot contract mul+add into FMA
 // (numpy rounds after every operation).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -162,6 +164,220 @@ __global__ void __launch_bounds__(kThreads, 6) extract_notes_gan_kernel(GanParam
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// N-1, pipelined form (the one mg_extract_notes_gan launches).
+//
+// The three-phase kernel above keeps one lane per roll busy for the whole of phase 2 while every other thread of the
+// CTA waits at a barrier, and reads the rolls twice (HBM, then L2).  Here one persistent CTA per SM runs the three
+// phases of three DIFFERENT tiles at the same time:
+//
+//   stage j:   bulk copy (cp.async.bulk, no LSU work) of tile j+1: 8 rolls = 64 KB of HBM -> shared memory
+//              worker warps (2 per roll)    P3(tile j-2)  then  P1(tile j)
+//              clock warp (1 lane per roll) the serial float32 onset clock of tile j-1
+//
+//   P1  row -> (pitch | velocity << 8) code (2 B), floored duration (4 B), floored step (4 B): 10 B per row stay in
+//       shared memory, the 16-byte row is dead after P1 (its buffer is refilled by the next bulk copy);
+//   clock  per roll: 512 dependent __fadd_rn, register-blocked four steps per LDS.128 / STS.128, so that only the
+//       FADD chain is serial;  P3  ballot/popc compaction and the float64 widening of onset / offset, coalesced stores.
+// Same arithmetic, same operation order as the reference (src/gan/utils.py:130-155): bit-exact.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile = 8;                         // rolls per tile
+constexpr int kWorkerWarps = 2 * kTile;          // two warps per roll (first / second half of its rows)
+constexpr int kThreadsV2 = (kWorkerWarps + 1) * 32;
+constexpr int kClkStride = kMaxRows + 4;         // floats; 516 % 32 = 4: the clock lanes' LDS.128 hit disjoint banks
+
+struct alignas(16) NotesSmem {
+    float4 raw[2][kTile * kMaxRows];             // 2 x 64 KB, written by bulk copies
+    float clk[2][kTile][kClkStride];             // P1: step (or -1 = floor); clock warp: exclusive onset clock
+    float dur[2][kTile][kMaxRows];               // max(0.25, duration)
+    unsigned short code[2][kTile][kMaxRows];     // pitch | velocity << 8; 0xFFFF = gated; 0 = non-finite
+    double floor_clock[kMaxRows + 1];
+    unsigned long long full[2];
+    int first_nf[4][kTile][2];                   // per half: first row whose step is above the floor (or nrows)
+    int nkeep[4][kTile][2];
+    int bad[4][kTile][2];
+    int ndbl[4][kTile];
+    unsigned char snap[64];                      // pitch 36..96 -> scale-snapped pitch
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void nb_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = smem_addr(bar);
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && spins > (1u << 26)) asm volatile("trap;");
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsV2, 1) extract_notes_gan_pipe_kernel(GanParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NotesSmem& S = *reinterpret_cast<NotesSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = P.nrows;
+    const float thr32 = (float)-0.2, vrange32 = (float)(1.0 - -0.2);
+    const float floor_step32 = (float)0.1, floor_dur32 = (float)0.25;
+    const long long ntiles = (P.nrolls + kTile - 1) / kTile;
+    const int ntl = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;   // tiles of this CTA
+
+    for (int i = tid; i <= kMaxRows; i += kThreadsV2) S.floor_clock[i] = c_floor_clock[i];
+    if (tid < 61) { const int pc = 36 + tid; S.snap[tid] = (unsigned char)((pc / 12) * 12 + P.lut[pc % 12]); }
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&S.full[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_load = [&](int j) {               // one thread: tile j of this CTA -> raw[j & 1]
+        const long long roll0 = ((long long)blockIdx.x + (long long)j * gridDim.x) * kTile;
+        const int nr = (int)min((long long)kTile, P.nrolls - roll0);
+        const uint32_t bytes = (uint32_t)nr * (uint32_t)T * 16u;
+        const uint32_t bar = smem_addr(&S.full[j & 1]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(S.raw[j & 1])), "l"(P.rolls + roll0 * T), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (tid == 0 && ntl > 0) issue_load(0);
+
+    const int Th = ((T + 63) / 64) * 32;         // rows of the first half (a multiple of 32)
+    for (int j = 0; j < ntl + 2; ++j) {
+        if (tid == 0 && j + 1 < ntl) issue_load(j + 1);      // raw[(j+1)&1] was last read by P1(j-1), before the barrier
+        if (warp < kWorkerWarps) {
+            const int r = warp >> 1, h = warp & 1;
+            const int row_lo = h ? Th : 0, row_hi = h ? T : min(T, Th);
+            // ---- P3 of tile j-2 ----
+            if (j >= 2) {
+                const int jt = j - 2, cb = jt & 1, mb = jt & 3;
+                const long long roll0 = ((long long)blockIdx.x + (long long)jt * gridDim.x) * kTile;
+                const int nr = (int)min((long long)kTile, P.nrolls - roll0);
+                if (r < nr) {
+                    const long long obase = (roll0 + r) * (long long)T;
+                    const int ndbl = S.ndbl[mb][r];
+                    int base = h ? S.nkeep[mb][r][0] : 0;
+                    uint8_t* __restrict__ op = P.pitch + obase;
+                    uint8_t* __restrict__ ov = P.velocity + obase;
+                    double* __restrict__ os = P.start + obase;
+                    double* __restrict__ oe = P.end + obase;
+                    for (int i0 = row_lo; i0 < row_hi; i0 += 32) {
+                        const int i = i0 + lane;
+                        const unsigned code = i < row_hi ? S.code[cb][r][i] : 0xFFFFu;
+                        const bool keep = code != 0xFFFFu;
+                        const unsigned ball = __ballot_sync(0xffffffffu, keep);
+                        if (keep) {
+                            const int slot = base + __popc(ball & ((1u << lane) - 1u));
+                            const float d = S.dur[cb][r][i];
+                            double st, en;
+                            if (i < ndbl) {                  // rows that still see the float64 clock
+                                const double t64 = S.floor_clock[i];
+                                st = __dmul_rn(t64, P.spb64);
+                                if (d == floor_dur32) en = __dmul_rn(__dadd_rn(t64, 0.25), P.spb64);
+                                else en = (double)__fmul_rn(__fadd_rn((float)t64, d), P.spb32);
+                            } else {
+                                const float t32 = S.clk[cb][r][i];
+                                st = (double)__fmul_rn(t32, P.spb32);
+                                en = (double)__fmul_rn(__fadd_rn(t32, d), P.spb32);
+                            }
+                            op[slot] = (uint8_t)(code & 0xFFu);
+                            ov[slot] = (uint8_t)(code >> 8);
+                            os[slot] = st;
+                            oe[slot] = en;
+                        }
+                        base += __popc(ball);
+                    }
+                    if (h == 0 && lane == 0)
+                        P.counts[roll0 + r] = (S.bad[mb][r][0] | S.bad[mb][r][1]) ? -1 : S.nkeep[mb][r][0] + S.nkeep[mb][r][1];
+                }
+            }
+            // ---- P1 of tile j ----
+            if (j < ntl) {
+                const int cb = j & 1, mb = j & 3;
+                const long long roll0 = ((long long)blockIdx.x + (long long)j * gridDim.x) * kTile;
+                const int nr = (int)min((long long)kTile, P.nrolls - roll0);
+                nb_wait(&S.full[cb], (uint32_t)(j >> 1) & 1u);
+                if (r < nr) {
+                    const float4* __restrict__ src = S.raw[cb] + r * T;
+                    int first = T, nk = 0;
+                    unsigned anybad = 0;
+                    const int blk_hi = h ? ((T + 31) / 32) * 32 : Th;        // whole 32-row blocks: pads the clock row
+                    for (int i0 = row_lo; i0 < blk_hi; i0 += 32) {
+                        const int i = i0 + lane;
+                        unsigned code = 0xFFFFu;
+                        float sv = -1.0f, dv = floor_dur32;
+                        bool bad = false;
+                        if (i < row_hi) {
+                            const float4 q = src[i];                         // (pitch, velocity, duration, step)
+                            const float s32 = unit_to_beats(q.w);
+                            sv = (s32 > floor_step32) ? s32 : -1.0f;         // max(0.1, .) keeps the python float 0.1
+                            const float dd = unit_to_beats(q.z);
+                            dv = (dd > floor_dur32) ? dd : floor_dur32;
+                            if (!(q.y < thr32)) {                            // utils.py:135; NaN velocity is not gated
+                                const float pf = __fmul_rn(__fadd_rn(q.x, 1.0f), 63.5f);
+                                const float vf = __fadd_rn(60.0f, __fmul_rn(__fdiv_rn(__fsub_rn(q.y, thr32), vrange32), 67.0f));
+                                if (!(fabsf(pf) < __int_as_float(0x7f800000)) || !(fabsf(vf) < __int_as_float(0x7f800000))) {
+                                    bad = true;                              // int(nan) / int(inf) raises in the reference
+                                    code = 0;
+                                } else {
+                                    // clip(int(x), lo, hi) == int(clamp(x, lo, hi)) for truncation toward zero
+                                    const int pc = __float2int_rz(fminf(fmaxf(pf, 36.0f), 96.0f));
+                                    const int vel = __float2int_rz(fminf(fmaxf(vf, 0.0f), 127.0f));
+                                    code = (unsigned)S.snap[pc - 36] | ((unsigned)vel << 8);
+                                }
+                            }
+                            S.dur[cb][r][i] = dv;
+                            S.code[cb][r][i] = (unsigned short)code;
+                        }
+                        S.clk[cb][r][i] = sv;                                // i < 512 always; rows >= T read as floor steps
+                        const unsigned nf = __ballot_sync(0xffffffffu, sv >= 0.0f);
+                        if (first == T && nf) first = i0 + __ffs(nf) - 1;
+                        nk += __popc(__ballot_sync(0xffffffffu, code != 0xFFFFu));
+                        anybad |= __ballot_sync(0xffffffffu, bad);
+                    }
+                    if (lane == 0) { S.first_nf[mb][r][h] = first; S.nkeep[mb][r][h] = nk; S.bad[mb][r][h] = anybad != 0; }
+                }
+            }
+        } else if (j >= 1 && j - 1 < ntl) {
+            // ---- the onset clock of tile j-1: one lane per roll, strictly in row order ----
+            const int jt = j - 1, cb = jt & 1, mb = jt & 3;
+            const long long roll0 = ((long long)blockIdx.x + (long long)jt * gridDim.x) * kTile;
+            const int nr = (int)min((long long)kTile, P.nrolls - roll0);
+            if (lane < nr) {
+                float* tex = S.clk[cb][lane];
+                const int i0 = min(S.first_nf[mb][lane][0], S.first_nf[mb][lane][1]);   // halves: [0,Th) and [Th,T)
+                int ndbl = T;
+                if (i0 < T) {
+                    ndbl = i0 + 1;                       // rows 0..i0 still see the float64 clock
+                    float t32 = __fadd_rn((float)S.floor_clock[i0], tex[i0]);
+                    int i = i0 + 1;
+                    for (; (i & 3) && i < T; ++i) {
+                        const float s = tex[i];
+                        tex[i] = t32;
+                        t32 = __fadd_rn(t32, s < 0.0f ? floor_step32 : s);
+                    }
+#pragma unroll 2
+                    for (; i < T; i += 4) {              // rows T..T+3 of the padded clock row hold floor steps
+                        const float4 s4 = *reinterpret_cast<const float4*>(tex + i);
+                        const float a0 = s4.x < 0.0f ? floor_step32 : s4.x, a1 = s4.y < 0.0f ? floor_step32 : s4.y;
+                        const float a2 = s4.z < 0.0f ? floor_step32 : s4.z, a3 = s4.w < 0.0f ? floor_step32 : s4.w;
+                        float4 o;
+                        o.x = t32;
+                        o.y = __fadd_rn(o.x, a0);
+                        o.z = __fadd_rn(o.y, a1);
+                        o.w = __fadd_rn(o.z, a2);
+                        t32 = __fadd_rn(o.w, a3);
+                        *reinterpret_cast<float4*>(tex + i) = o;
+                    }
+                }
+                S.ndbl[mb][lane] = ndbl;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) extract_notes_abs_kernel(const float4* __restrict__ rolls, long long nrowsTotal,
                                                                 uint8_t* __restrict__ pitch,
                                                                 uint8_t* __restrict__ velocity,
@@ -199,6 +415,8 @@ int init_once() {
     MG_CUDA_OK(cudaMemcpyToSymbol(c_floor_clock, tab, sizeof(tab)));
     MG_CUDA_OK(cudaFuncSetAttribute(extract_notes_gan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kGanSmem));
+    MG_CUDA_OK(cudaFuncSetAttribute(extract_notes_gan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(NotesSmem)));
     done = 1;
     return MG_OK;
 }
@@ -242,10 +460,17 @@ extern "C" int mg_extract_notes_gan(const float* rolls, long long nrolls, int nr
     P.spb32 = (float)P.spb64;
     snap_lut(allowed_mask, P.lut);
     P.counts = counts; P.pitch = pitch; P.velocity = velocity; P.start = start; P.end = end;
-    const long long ntiles = (nrolls + kRollsPerCta - 1) / kRollsPerCta;
-    const int grid = (int)((ntiles < (long long)mg::num_sms() * 6) ? ntiles : (long long)mg::num_sms() * 6);
     mg::ProbeScope probe(mg::PROBE_NOTES, 0.0, (double)nrolls * (nrows * 16.0 + 4.0), mg::as_stream(stream));
-    extract_notes_gan_kernel<<<grid, kThreads, kGanSmem, mg::as_stream(stream)>>>(P);
+    static const bool three_phase = getenv("MELOGAN_NOTES_3PHASE") != nullptr;     // A/B: the unpipelined kernel
+    if (three_phase) {
+        const long long ntiles = (nrolls + kRollsPerCta - 1) / kRollsPerCta;
+        const int grid = (int)((ntiles < (long long)mg::num_sms() * 6) ? ntiles : (long long)mg::num_sms() * 6);
+        extract_notes_gan_kernel<<<grid, kThreads, kGanSmem, mg::as_stream(stream)>>>(P);
+    } else {
+        const long long ntiles = (nrolls + kTile - 1) / kTile;
+        const int grid = (int)((ntiles < (long long)mg::num_sms()) ? ntiles : (long long)mg::num_sms());
+        extract_notes_gan_pipe_kernel<<<grid, kThreadsV2, sizeof(NotesSmem), mg::as_stream(stream)>>>(P);
+    }
     MG_LAUNCH_OK();
     return MG_OK;
 }
