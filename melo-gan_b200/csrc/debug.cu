@@ -97,6 +97,7 @@ extern "C" int mg_debug_set(const char* key, int value) {
     if (!strcmp(key, "force_bn")) { t.force_bn = value; return MG_OK; }
     if (!strcmp(key, "max_stages")) { t.max_stages = value; return MG_OK; }
     if (!strcmp(key, "staging_bufs")) { t.staging_bufs = value; return MG_OK; }
+    if (!strcmp(key, "mask_bufs")) { t.mask_bufs = value; return MG_OK; }
     if (!strcmp(key, "no_ws")) { t.no_ws = value; return MG_OK; }
     if (!strcmp(key, "dbg")) { t.dbg = value; return MG_OK; }
     if (!strcmp(key, "reverse")) { t.reverse = value; return MG_OK; }

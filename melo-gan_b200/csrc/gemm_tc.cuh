@@ -171,6 +171,15 @@ __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32
           "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_async(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32_async(taddr, r); }
+__device__ __forceinline__ void tmem_ld_async(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16_async(taddr, r); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
@@ -220,6 +229,8 @@ struct TcTapArgs {
     int tma_store;                      // weight-stationary kernel: tiles leave through shared memory + TMA bulk stores
     int nsb;                            // ... through a ring of nsb (1 or 2) staging tiles: the bulk store of one tile drains
                                         // while the next tile is read from TMEM, computed and staged
+    int nmb;                            // TMA mask tiles: ring of nmb (1 or 2) buffers; with 2 the tile after next is in flight
+                                        // while this one is drained (a single buffer exposes one L2/HBM latency per tile)
     int reverse;                        // walk the M tiles from the last to the first (see run_tc_tap)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
@@ -421,17 +432,17 @@ __device__ __forceinline__ void stage8(unsigned char* staging, int r, int cc, co
     }
 }
 
-// One epilogue thread = one accumulator row x 32 columns: math in chunks of 8, results (and the GELU derivative tile)
+// One epilogue thread = one accumulator row x CPT (32 or 16) columns: math in chunks of 8, results (and the GELU derivative tile)
 // straight into the staging tile(s).
-template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TO, typename TMSK, bool SCL = true>
-__device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&raw)[32], const TMSK* __restrict__ mrow, bool row_ok,
-                                          const unsigned char* maskrow, const uint4 (&mreg)[4], const float4* sc4,
+template <int ACT, int MUL, bool AFF, bool AUX, bool GEN, typename TO, typename TMSK, bool SCL = true, int CPT = 32>
+__device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&raw)[CPT], const TMSK* __restrict__ mrow, bool row_ok,
+                                          const unsigned char* maskrow, const uint4 (&mreg)[CPT / 8], const float4* sc4,
                                           const float4* bi4, int c_begin, int r, unsigned char* stage_out,
                                           unsigned char* stage_aux) {
     const int mul = GEN ? P.mul_mode : MUL;
     const bool aux = GEN ? (P.aux != nullptr) : AUX;
 #pragma unroll
-    for (int g8 = 0; g8 < 32; g8 += 8) {
+    for (int g8 = 0; g8 < CPT; g8 += 8) {
         float ms[8], y8[8], gd[8];
         if (mul != MUL_NONE) {
             if (sizeof(TMSK) == 2) {
@@ -469,14 +480,14 @@ __device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&r
 //   * TMEM hand-back by one mbarrier arrive per WARP right after its tcgen05.ld (no CTA-wide barrier);
 //   * ONE named barrier per tile (staging tile complete -> TMA store); the staging slot is recycled by waiting, before
 //     that barrier, for the bulk store issued one tile earlier (it has had a whole tile of math to drain).
-template <int BN, int kEpi, int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool SCL, typename TO, typename TMSK, typename HDR>
+template <int BN, int kEpi, int CPT, int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool SCL, typename TO, typename TMSK, typename HDR>
 __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
                                                  const CUtensorMap* m_map, HDR& H, uint32_t tmem0, int n0, int mtiles,
                                                  unsigned char* staging0, unsigned char* maskbuf) {
     constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
     constexpr size_t kStageTile = (size_t)128 * BN * sizeof(TO);
     const int et = threadIdx.x - 64, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, lane_row = q * 32 + lane, c_begin = (et >> 7) * 32;
+    const int q = warp & 3, lane_row = q * 32 + lane, c_begin = (et >> 7) * CPT;
     const int r = ((lane_row & (P.il - 1)) << P.mpt_shift) + (lane_row >> P.il_shift);   // tile row this TMEM lane holds
     const bool has_aux = GEN ? (P.aux != nullptr) : AUX;
     const int per_tile = has_aux ? 2 : 1;
@@ -489,35 +500,42 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
     const float4* sc4 = reinterpret_cast<const float4*>(H.scale);
     const float4* bi4 = reinterpret_cast<const float4*>(H.bias);
     const uint32_t tmem_lane = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin;
-    const unsigned char* maskrow = tma_mask ? maskbuf + r * 128 : nullptr;
+    constexpr uint32_t kMaskTile = (uint32_t)(BN / 64) * 16384u;
     const int gstep = (int)gridDim.x;
     int sbuf = 0, tcount = 0;
-    if (tma_mask && et == 0 && (int)blockIdx.x < mtiles) {
-        const int t0 = P.reverse ? mtiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
-        mbar_expect_tx(&H.mask_full, (uint32_t)(BN / 64) * 16384u);
+    auto load_mask = [&](int tile, int buf) {        // one thread: the mask tile of `tile` -> ring slot buf
+        const int mrow0 = (P.reverse ? mtiles - 1 - tile : tile) * 128;
+        mbar_expect_tx(&H.mask_full[buf], kMaskTile);
 #pragma unroll
-        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, &H.mask_full, maskbuf + bx * 16384, n0 + bx * 64, t0 * 128);
+        for (int bx = 0; bx < BN / 64; ++bx)
+            tma_load_2d(m_map, &H.mask_full[buf], maskbuf + (size_t)buf * kMaskTile + bx * 16384, n0 + bx * 64, mrow0);
+    };
+    if (tma_mask && et == 0) {
+        for (int k = 0; k < P.nmb; ++k)
+            if ((int)blockIdx.x + k * gstep < mtiles) load_mask((int)blockIdx.x + k * gstep, k);
     }
+    int mbuf = 0;
+    uint32_t mpar = 0;
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < mtiles; tile += gstep, ++tcount) {
         const int acc = tcount & 1;
         const int row0 = (P.reverse ? mtiles - 1 - tile : tile) * 128;
         const int bb = (row0 >> P.mper_shift) + rdiv;
         const bool row_ok = bb < P.B;
-        uint4 mreg[4] = {};
+        uint4 mreg[CPT / 8] = {};
         const TMSK* mrow = nullptr;
         if (reg_mask) {                                          // per-thread mask loads, in flight during the accumulator wait
             const long long o = (long long)bb * P.o_bstride + (long long)((row0 & (P.Mper - 1)) + rmod) * P.o_mstride + P.o_off + n0;
             mrow = Mb + o;
             if (sizeof(TMSK) == 2 && row_ok && !(P.dbg & 8)) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(mrow + c_begin) + i);
+                for (int i = 0; i < CPT / 8; ++i) mreg[i] = __ldg(reinterpret_cast<const uint4*>(mrow + c_begin) + i);
             }
         }
         mbar_wait(&H.tmem_full[acc], (uint32_t)(tcount >> 1) & 1u);
         tc_fence_after();
-        uint32_t raw[32];
-        tmem_ld32_async(tmem_lane + (uint32_t)(acc * BN), raw);
+        uint32_t raw[CPT];
+        tmem_ld_async(tmem_lane + (uint32_t)(acc * BN), raw);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -528,9 +546,13 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
         }
         unsigned char* stage_out = staging0 + (size_t)sbuf * kStageTile;
         unsigned char* stage_aux = staging0 + (size_t)(sbuf + 1) * kStageTile;
-        if (tma_mask) mbar_wait(&H.mask_full, (uint32_t)tcount & 1u);
-        epi_row32<ACT, MUL, AFF, AUX, GEN, TO, TMSK, SCL>(P, raw, mrow, row_ok && !(P.dbg & 8), maskrow, mreg, sc4, bi4, c_begin, r,
-                                                          stage_out, stage_aux);
+        const unsigned char* maskrow = nullptr;
+        if (tma_mask) {
+            mbar_wait(&H.mask_full[mbuf], mpar);
+            maskrow = maskbuf + (size_t)mbuf * kMaskTile + r * 128;
+        }
+        epi_row32<ACT, MUL, AFF, AUX, GEN, TO, TMSK, SCL, CPT>(P, raw, mrow, row_ok && !(P.dbg & 8), maskrow, mreg, sc4, bi4, c_begin,
+                                                               r, stage_out, stage_aux);
         fence_proxy_async();
         if (ring2 && et == 0) bulk_wait_read0();                 // the store issued one tile ago has drained its slot
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
@@ -544,13 +566,10 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
                 }
                 bulk_commit();
             }
-            if (tma_mask && tile + gstep < mtiles) {             // every thread has read this tile's mask: fetch the next
-                const int nrow0 = (P.reverse ? mtiles - 1 - (tile + gstep) : tile + gstep) * 128;
-                mbar_expect_tx(&H.mask_full, (uint32_t)(BN / 64) * 16384u);
-#pragma unroll
-                for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(m_map, &H.mask_full, maskbuf + bx * 16384, n0 + bx * 64, nrow0);
-            }
+            // every thread has read this tile's mask: its ring slot takes the tile nmb steps ahead
+            if (tma_mask && tile + P.nmb * gstep < mtiles) load_mask(tile + P.nmb * gstep, mbuf);
         }
+        if (++mbuf >= P.nmb) { mbuf = 0; mpar ^= 1u; }
         sbuf += per_tile;
         if (sbuf >= P.nsb) sbuf = 0;
     }
@@ -667,10 +686,14 @@ constexpr int kWsMaxLoads = 80;      // taps x k-blocks per tile
 constexpr int kWsHeaderBytes = 4096;
 // TMA warp, MMA warp, then BN / 32 epilogue warpgroups of 4 warps; each warpgroup drains 32 accumulator columns.  The
 // drain is a chain of dependent latencies (tcgen05.ld -> math -> store), so it is hidden by warps, not by ILP.
-template <int BN> struct WsCfg { static constexpr int kGroups = BN / 32, kEpiThreads = kGroups * 128, kThreads = 64 + kEpiThreads; };
+// 16 epilogue warps for both slab widths: 32 columns per thread at BN = 128, 16 at BN = 64 (eight warps left the GELU /
+// mask epilogues of the 64-wide slabs latency-bound at two warps per scheduler)
+template <int BN> struct WsCfg {
+    static constexpr int kCpt = BN >= 128 ? 32 : 16, kGroups = BN / kCpt, kEpiThreads = kGroups * 128, kThreads = 64 + kEpiThreads;
+};
 template <int BN>
 struct WsHeader {
-    uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2], mask_full;
+    uint64_t full[kWsMaxStages], empty[kWsMaxStages], wfull, tmem_full[2], tmem_empty[2], mask_full[2];
     uint32_t tmem_base;
     alignas(16) float bias[BN], scale[BN];
     // per-tile schedules, built once per CTA so that the single-thread producer / MMA loops carry no index arithmetic:
@@ -711,7 +734,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             mbar_init(&H.tmem_full[a], 1);
             mbar_init(&H.tmem_empty[a], P.tma_store ? (uint32_t)(WsCfg<BN>::kEpiThreads / 32) : 1u);
         }
-        mbar_init(&H.mask_full, 1);
+        mbar_init(&H.mask_full[0], 1); mbar_init(&H.mask_full[1], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -823,7 +846,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
             else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
-    ws_epilogue_loop<BN, kEpi, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK>(P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, \
+    ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK>(P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, \
                                                                              staging, maskbuf)
             switch (variant) {
                 case 1: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, true); break;
@@ -845,8 +868,9 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
                 const int acc = tcount & 1;
                 int b0, m0;
                 tile_coords(tile, b0, m0);
-                drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
-                                             &H.tmem_full[acc], (tcount >> 1) & 1, grp * 32);
+                if (grp * 32 < BN)      // row-per-thread drain: 32 columns per warpgroup (the other warpgroups only keep the barrier)
+                    drain_tile<BN, 32, TO, TMSK>(P, H.bias, H.scale, tmem0 + (uint32_t)(acc * BN), b0, m0, n0, warp, lane,
+                                                 &H.tmem_full[acc], (tcount >> 1) & 1, grp * 32);
                 tc_fence_before();
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");   // every epilogue thread has read its TMEM lanes
                 if (et == 0) mbar_arrive(&H.tmem_empty[acc]);
@@ -1120,6 +1144,7 @@ struct Tuning {
     int force_bn = 0;        // 64 / 128: slab width of the weight-stationary kernel
     int max_stages = 0;      // cap of the activation ring
     int staging_bufs = 0;    // 1 / 2 staging tiles (0 = two when they fit)
+    int mask_bufs = 0;       // 1 = single TMA mask tile (0 = two when they fit)
     int no_ws = 0;           // one tile per CTA
     int dbg = -1;            // MELOGAN_TC_DEBUG ablation bits (-1 = environment)
     int reverse = -1;        // fixed tile order (-1 = alternate)
@@ -1226,7 +1251,12 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         if (a.tma_store && tn.staging_bufs != 1 &&
             wbytes + 4 * a_stage + 2 * staging + (a.tma_mask ? maskbytes : 0) <= avail)
             a.nsb = 2 * per_tile;
-        const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes : 0);
+        // a second mask tile (prefetch distance two tiles) when it still leaves 4 activation stages
+        a.nmb = 1;
+        if (a.tma_mask && tn.mask_bufs != 1 &&
+            wbytes + 4 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + 2 * maskbytes <= avail)
+            a.nmb = 2;
+        const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes * a.nmb : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
