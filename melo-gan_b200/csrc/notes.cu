@@ -6,13 +6,11 @@
 // HBM-bound byte/float work: per roll 8 KiB in, <= 512*(1+1+8+8) B + 4 B out.  The only
 // sequential part is the onset clock: the reference accumulates `current_time_beats` one row
 // at a time in float32 (float64 while only floor steps were added), and float addition is not
-// associative, so a tree/warp scan is not bit-exact.  Layout of the work:
-//   phase 1  thread-per-row, coalesced float4 loads: gate, pitch, velocity, step, duration
-//            -> shared memory (the roll never goes back to HBM);
-//   phase 2  the clock: one LANE PER ROLL walks that roll's 512 steps from shared memory in
-//            order (serial over rows, parallel over rolls: 16 chains per warp instruction);
-//   phase 3  warp-per-roll compaction: __ballot_sync + popc gives every surviving row its
-//            output slot (integer prefix, exact), then coalesced stores of the note fields.
+// associative, so a tree/warp scan is not bit-exact.  Layout of the work (details at the kernel):
+//   P1     row -> note code, floored duration, floored step, in shared memory (bulk-copied tiles);
+//   clock  one LANE PER ROLL walks that roll's 512 steps in order (serial over rows, parallel over rolls);
+//   P3     __ballot_sync + popc compaction gives every surviving row its output slot (integer prefix, exact),
+//          coalesced stores of the note fields.
 // All float32 arithmetic uses __f*_rn intrinsics so nvcc cannot contract mul+add into FMA
 // (numpy rounds after every operation).
 #include <stdlib.h>
@@ -22,9 +20,6 @@
 namespace {
 
 constexpr int kMaxRows = 512;
-constexpr int kRollsPerCta = 16;
-constexpr int kThreads = 256;
-constexpr int kTexStride = kMaxRows + 1;  // +1: lanes of phase 2 (one per roll) hit distinct banks
 
 // t = 0.0; t += 0.1 (float64) k times: the reference's clock while every step so far was the floor.
 __constant__ double c_floor_clock[kMaxRows + 1];
@@ -45,131 +40,15 @@ struct GanParams {
 
 __device__ __forceinline__ float unit_to_beats(float x) {
     // ((x + 1.0) / 2.0) * MAX_BEAT_TIME   (utils.py:133,148), one rounding per op
-    return __fmul_rn(__fdiv_rn(__fadd_rn(x, 1.0f), 2.0f), 4.0f);
-}
-
-__device__ __forceinline__ int trunc_clip(float x, int lo, int hi) {
-    // int(x) then np.clip(., lo, hi); x is finite here.  Saturate first: the clip makes it equivalent.
-    x = fminf(fmaxf(x, -1.0e9f), 1.0e9f);
-    int v = __float2int_rz(x);
-    return min(max(v, lo), hi);
-}
-
-__global__ void __launch_bounds__(kThreads, 6) extract_notes_gan_kernel(GanParams P) {
-    // Only the onset clock lives in shared memory (2 KB per roll): the serial phase 2 keeps one lane per roll busy, so its
-    // throughput is the number of rolls resident per SM; pitch / velocity / duration are recomputed in phase 3 from the
-    // rolls (an L2 hit: the tile was read a few microseconds earlier) instead of being parked in 6 more bytes per row.
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_tex = reinterpret_cast<float*>(smem_raw);                       // [16][513] step -> exclusive clock
-    int* s_ndbl = reinterpret_cast<int*>(s_tex + kRollsPerCta * kTexStride); // [16] rows on the float64 clock
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int T = P.nrows;
-    const float thr32 = (float)-0.2;            // VELOCITY_THRESHOLD as a weak scalar
-    const float vrange32 = (float)(1.0 - -0.2); // utils.py:143
-    const float floor_step32 = (float)0.1, floor_dur32 = (float)0.25;
-    const long long ntiles = (P.nrolls + kRollsPerCta - 1) / kRollsPerCta;
-
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long roll0 = tile * kRollsPerCta;
-        const int nr = (int)min((long long)kRollsPerCta, P.nrolls - roll0);
-
-        // ---- phase 1: the step column, rows of the tile are contiguous in HBM ----
-        const int total = nr * T;
-        const float4* src = P.rolls + roll0 * T;
-#pragma unroll 4
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const float4 q = __ldg(src + idx);  // (pitch, velocity, duration, step)
-            const int r = idx / T, i = idx - r * T;
-            const float s32 = unit_to_beats(q.w);
-            s_tex[r * kTexStride + i] = (s32 > floor_step32) ? s32 : -1.0f;  // max(0.1, .) keeps python 0.1
-        }
-        __syncthreads();
-
-        // ---- phase 2: the onset clock, one lane per roll, strictly in row order ----
-        if (warp == 0 && lane < nr) {
-            float* tex = s_tex + lane * kTexStride;
-            int i = 0;
-            // float64 prefix: t is floor_clock[i] while every step so far was the python-float floor
-            while (i < T && tex[i] < 0.0f) ++i;
-            int ndbl = T;
-            if (i < T) {
-                ndbl = i + 1;  // rows 0..i still see the float64 clock
-                float t32 = __fadd_rn((float)c_floor_clock[i], tex[i]);
-                for (++i; i < T; ++i) {
-                    const float s = tex[i];
-                    tex[i] = t32;
-                    t32 = __fadd_rn(t32, s < 0.0f ? floor_step32 : s);
-                }
-            }
-            s_ndbl[lane] = ndbl;
-        }
-        __syncthreads();
-
-        // ---- phase 3: per-row pitch / velocity / duration, compaction, onset / offset; one warp per roll ----
-        for (int r = warp; r < nr; r += kThreads / 32) {
-            const long long obase = (roll0 + r) * (long long)T;
-            const int ndbl = s_ndbl[r];
-            int base = 0;
-            unsigned bad_any = 0;
-            for (int i0 = 0; i0 < T; i0 += 32) {
-                const int i = i0 + lane;
-                unsigned short code = 0xFFFFu;  // gated (or past the end)
-                float d32 = -1.0f;
-                bool bad = false;
-                if (i < T) {
-                    const float4 q = __ldg(src + r * T + i);
-                    const float dd = unit_to_beats(q.z);
-                    d32 = (dd > floor_dur32) ? dd : -1.0f;
-                    if (!(q.y < thr32)) {           // utils.py:135; NaN velocity is not gated
-                        const float pf = __fmul_rn(__fadd_rn(q.x, 1.0f), 63.5f);
-                        const float vf = __fadd_rn(60.0f, __fmul_rn(__fdiv_rn(__fsub_rn(q.y, thr32), vrange32), 67.0f));
-                        if (!isfinite(pf) || !isfinite(vf)) {
-                            bad = true;  // int(nan)/int(inf) raises in the reference
-                            code = 0;
-                        } else {
-                            const int pc = trunc_clip(pf, 36, 96);
-                            const int pit = (pc / 12) * 12 + P.lut[pc % 12];
-                            const int vel = trunc_clip(vf, 0, 127);
-                            code = (unsigned short)(pit | (vel << 8));
-                        }
-                    }
-                }
-                bad_any |= __ballot_sync(0xffffffffu, bad);
-                const bool keep = code != 0xFFFFu;
-                const unsigned ball = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const int slot = base + __popc(ball & ((1u << lane) - 1u));
-                    double st, en;
-                    if (i < ndbl) {
-                        const double t64 = c_floor_clock[i];
-                        st = __dmul_rn(t64, P.spb64);
-                        if (d32 < 0.0f) en = __dmul_rn(__dadd_rn(t64, 0.25), P.spb64);
-                        else en = (double)__fmul_rn(__fadd_rn((float)t64, d32), P.spb32);
-                    } else {
-                        const float t32 = s_tex[r * kTexStride + i];
-                        st = (double)__fmul_rn(t32, P.spb32);
-                        en = (double)__fmul_rn(__fadd_rn(t32, d32 < 0.0f ? floor_dur32 : d32), P.spb32);
-                    }
-                    P.pitch[obase + slot] = (uint8_t)(code & 0xFF);
-                    P.velocity[obase + slot] = (uint8_t)(code >> 8);
-                    P.start[obase + slot] = st;
-                    P.end[obase + slot] = en;
-                }
-                base += __popc(ball);
-            }
-            if (lane == 0) P.counts[roll0 + r] = bad_any ? -1 : base;
-        }
-        __syncthreads();
-    }
+    // x / 2.0 == x * 0.5 bit for bit (both are the correctly rounded value of the same real number, subnormals included);
+    // written as a multiplication because nvcc expands __fdiv_rn into its full division sequence even for 2.0f
+    return __fmul_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), 4.0f);
 }
 
 // ---------------------------------------------------------------------------------------------
-// N-1, pipelined form (the one mg_extract_notes_gan launches).
-//
-// The three-phase kernel above keeps one lane per roll busy for the whole of phase 2 while every other thread of the
-// CTA waits at a barrier, and reads the rolls twice (HBM, then L2).  Here one persistent CTA per SM runs the three
-// phases of three DIFFERENT tiles at the same time:
+// N-1.  One persistent CTA per SM runs the three phases of three DIFFERENT tiles at the same time (round 1 ran them one
+// after the other per tile: one lane per roll busy for the whole clock phase while every other thread waited at a
+// barrier, and the rolls were read twice -- 0.41 of the HBM roof; this form: 0.65):
 //
 //   stage j:   bulk copy (cp.async.bulk, no LSU work) of tile j+1: 8 rolls = 64 KB of HBM -> shared memory
 //              worker warps (2 per roll)    P3(tile j-2)  then  P1(tile j)
@@ -184,11 +63,12 @@ __global__ void __launch_bounds__(kThreads, 6) extract_notes_gan_kernel(GanParam
 constexpr int kTile = 8;                         // rolls per tile
 constexpr int kWorkerWarps = 2 * kTile;          // two warps per roll (first / second half of its rows)
 constexpr int kThreadsV2 = (kWorkerWarps + 1) * 32;
-constexpr int kClkStride = kMaxRows + 4;         // floats; 516 % 32 = 4: the clock lanes' LDS.128 hit disjoint banks
+constexpr int kClkStride = kMaxRows + 36;        // floats; 548 % 32 = 4: the clock lanes' LDS.128 hit disjoint banks, and the
+                                                 // software-pipelined clock loop may read 12 floats past row 511
 
 struct alignas(16) NotesSmem {
     float4 raw[2][kTile * kMaxRows];             // 2 x 64 KB, written by bulk copies
-    float clk[2][kTile][kClkStride];             // P1: step (or -1 = floor); clock warp: exclusive onset clock
+    float clk[2][kTile][kClkStride];             // P1: max(0.1, step); clock warp: exclusive onset clock
     float dur[2][kTile][kMaxRows];               // max(0.25, duration)
     unsigned short code[2][kTile][kMaxRows];     // pitch | velocity << 8; 0xFFFF = gated; 0 = non-finite
     double floor_clock[kMaxRows + 1];
@@ -257,19 +137,23 @@ __global__ void __launch_bounds__(kThreadsV2, 1) extract_notes_gan_pipe_kernel(G
                 if (r < nr) {
                     const long long obase = (roll0 + r) * (long long)T;
                     const int ndbl = S.ndbl[mb][r];
-                    int base = h ? S.nkeep[mb][r][0] : 0;
+                    unsigned base = h ? (unsigned)S.nkeep[mb][r][0] : 0u;
                     uint8_t* __restrict__ op = P.pitch + obase;
                     uint8_t* __restrict__ ov = P.velocity + obase;
                     double* __restrict__ os = P.start + obase;
                     double* __restrict__ oe = P.end + obase;
-                    for (int i0 = row_lo; i0 < row_hi; i0 += 32) {
-                        const int i = i0 + lane;
-                        const unsigned code = i < row_hi ? S.code[cb][r][i] : 0xFFFFu;
+                    const unsigned short* pcode = &S.code[cb][r][row_lo + lane];
+                    const float* pclk = &S.clk[cb][r][row_lo + lane];
+                    const float* pdur = &S.dur[cb][r][row_lo + lane];
+                    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 2
+                    for (int i = row_lo + lane; i < row_hi + lane; i += 32, pcode += 32, pclk += 32, pdur += 32) {
+                        const unsigned code = i < row_hi ? (unsigned)*pcode : 0xFFFFu;
                         const bool keep = code != 0xFFFFu;
                         const unsigned ball = __ballot_sync(0xffffffffu, keep);
                         if (keep) {
-                            const int slot = base + __popc(ball & ((1u << lane) - 1u));
-                            const float d = S.dur[cb][r][i];
+                            const unsigned slot = base + (unsigned)__popc(ball & lt);   // unsigned: one IMAD.WIDE.U32 per address
+                            const float d = *pdur;
                             double st, en;
                             if (i < ndbl) {                  // rows that still see the float64 clock
                                 const double t64 = S.floor_clock[i];
@@ -277,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) extract_notes_gan_pipe_kernel(G
                                 if (d == floor_dur32) en = __dmul_rn(__dadd_rn(t64, 0.25), P.spb64);
                                 else en = (double)__fmul_rn(__fadd_rn((float)t64, d), P.spb32);
                             } else {
-                                const float t32 = S.clk[cb][r][i];
+                                const float t32 = *pclk;
                                 st = (double)__fmul_rn(t32, P.spb32);
                                 en = (double)__fmul_rn(__fadd_rn(t32, d), P.spb32);
                             }
@@ -286,57 +170,58 @@ __global__ void __launch_bounds__(kThreadsV2, 1) extract_notes_gan_pipe_kernel(G
                             os[slot] = st;
                             oe[slot] = en;
                         }
-                        base += __popc(ball);
+                        base += (unsigned)__popc(ball);
                     }
                     if (h == 0 && lane == 0)
                         P.counts[roll0 + r] = (S.bad[mb][r][0] | S.bad[mb][r][1]) ? -1 : S.nkeep[mb][r][0] + S.nkeep[mb][r][1];
                 }
             }
-            // ---- P1 of tile j ----
+            // ---- P1 of tile j ----  (branch-free: a row past the end is a gated row on both floors)
             if (j < ntl) {
                 const int cb = j & 1, mb = j & 3;
                 const long long roll0 = ((long long)blockIdx.x + (long long)j * gridDim.x) * kTile;
                 const int nr = (int)min((long long)kTile, P.nrolls - roll0);
                 nb_wait(&S.full[cb], (uint32_t)(j >> 1) & 1u);
                 if (r < nr) {
-                    const float4* __restrict__ src = S.raw[cb] + r * T;
+                    const float inf32 = __int_as_float(0x7f800000);
+                    const float4* __restrict__ src = S.raw[cb] + r * T + row_lo + lane;
+                    float* pclk = &S.clk[cb][r][row_lo + lane];
+                    float* pdur = &S.dur[cb][r][row_lo + lane];
+                    unsigned short* pcode = &S.code[cb][r][row_lo + lane];
                     int first = T, nk = 0;
-                    unsigned anybad = 0;
+                    bool anybad = false;
                     const int blk_hi = h ? ((T + 31) / 32) * 32 : Th;        // whole 32-row blocks: pads the clock row
-                    for (int i0 = row_lo; i0 < blk_hi; i0 += 32) {
-                        const int i = i0 + lane;
-                        unsigned code = 0xFFFFu;
-                        float sv = -1.0f, dv = floor_dur32;
-                        bool bad = false;
-                        if (i < row_hi) {
-                            const float4 q = src[i];                         // (pitch, velocity, duration, step)
-                            const float s32 = unit_to_beats(q.w);
-                            sv = (s32 > floor_step32) ? s32 : -1.0f;         // max(0.1, .) keeps the python float 0.1
-                            const float dd = unit_to_beats(q.z);
-                            dv = (dd > floor_dur32) ? dd : floor_dur32;
-                            if (!(q.y < thr32)) {                            // utils.py:135; NaN velocity is not gated
-                                const float pf = __fmul_rn(__fadd_rn(q.x, 1.0f), 63.5f);
-                                const float vf = __fadd_rn(60.0f, __fmul_rn(__fdiv_rn(__fsub_rn(q.y, thr32), vrange32), 67.0f));
-                                if (!(fabsf(pf) < __int_as_float(0x7f800000)) || !(fabsf(vf) < __int_as_float(0x7f800000))) {
-                                    bad = true;                              // int(nan) / int(inf) raises in the reference
-                                    code = 0;
-                                } else {
-                                    // clip(int(x), lo, hi) == int(clamp(x, lo, hi)) for truncation toward zero
-                                    const int pc = __float2int_rz(fminf(fmaxf(pf, 36.0f), 96.0f));
-                                    const int vel = __float2int_rz(fminf(fmaxf(vf, 0.0f), 127.0f));
-                                    code = (unsigned)S.snap[pc - 36] | ((unsigned)vel << 8);
-                                }
-                            }
-                            S.dur[cb][r][i] = dv;
-                            S.code[cb][r][i] = (unsigned short)code;
-                        }
-                        S.clk[cb][r][i] = sv;                                // i < 512 always; rows >= T read as floor steps
-                        const unsigned nf = __ballot_sync(0xffffffffu, sv >= 0.0f);
-                        if (first == T && nf) first = i0 + __ffs(nf) - 1;
-                        nk += __popc(__ballot_sync(0xffffffffu, code != 0xFFFFu));
-                        anybad |= __ballot_sync(0xffffffffu, bad);
+#pragma unroll 2
+                    for (int i = row_lo + lane; i < blk_hi; i += 32, src += 32, pclk += 32, pdur += 32, pcode += 32) {
+                        float4 q = make_float4(0.0f, -1.0f, -1.0f, -1.0f);   // (pitch, velocity, duration, step)
+                        if (i < row_hi) q = *src;
+                        const float s32 = unit_to_beats(q.w);
+                        const bool nonfloor = s32 > floor_step32;            // max(0.1, .) keeps the python float 0.1
+                        const float dv = fmaxf(unit_to_beats(q.z), floor_dur32);   // NaN -> the floor, as `dd > 0.25` is false
+                        const bool gate = !(q.y < thr32);                    // utils.py:135; NaN velocity is not gated
+                        const float pf = __fmul_rn(__fadd_rn(q.x, 1.0f), 63.5f);
+                        const float vf = __fadd_rn(60.0f, __fmul_rn(__fdiv_rn(__fsub_rn(q.y, thr32), vrange32), 67.0f));
+                        const bool fin = (fabsf(pf) < inf32) && (fabsf(vf) < inf32);   // int(nan) / int(inf) raises in the reference
+                        // clip(int(x), lo, hi) == int(clamp(x, lo, hi)) for truncation toward zero
+                        const int pc = __float2int_rz(fminf(fmaxf(pf, 36.0f), 96.0f));
+                        const int vel = __float2int_rz(fminf(fmaxf(vf, 0.0f), 127.0f));
+                        unsigned code = (unsigned)S.snap[pc - 36] | ((unsigned)vel << 8);
+                        code = fin ? code : 0u;
+                        code = gate ? code : 0xFFFFu;
+                        *pclk = nonfloor ? s32 : floor_step32;               // i < 512 always; rows >= T read as floor steps
+                        *pdur = dv;
+                        *pcode = (unsigned short)code;
+                        first = min(first, nonfloor ? i : T);
+                        nk += gate ? 1 : 0;
+                        anybad |= gate && !fin;
                     }
-                    if (lane == 0) { S.first_nf[mb][r][h] = first; S.nkeep[mb][r][h] = nk; S.bad[mb][r][h] = anybad != 0; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                        nk += __shfl_xor_sync(0xffffffffu, nk, o);
+                    }
+                    const unsigned badball = __ballot_sync(0xffffffffu, anybad);
+                    if (lane == 0) { S.first_nf[mb][r][h] = first; S.nkeep[mb][r][h] = nk; S.bad[mb][r][h] = badball != 0; }
                 }
             }
         } else if (j >= 1 && j - 1 < ntl) {
@@ -352,23 +237,43 @@ __global__ void __launch_bounds__(kThreadsV2, 1) extract_notes_gan_pipe_kernel(G
                     ndbl = i0 + 1;                       // rows 0..i0 still see the float64 clock
                     float t32 = __fadd_rn((float)S.floor_clock[i0], tex[i0]);
                     int i = i0 + 1;
-                    for (; (i & 3) && i < T; ++i) {
+                    for (; (i & 7) && i < T; ++i) {
                         const float s = tex[i];
                         tex[i] = t32;
-                        t32 = __fadd_rn(t32, s < 0.0f ? floor_step32 : s);
+                        t32 = __fadd_rn(t32, s);
                     }
-#pragma unroll 2
-                    for (; i < T; i += 4) {              // rows T..T+3 of the padded clock row hold floor steps
-                        const float4 s4 = *reinterpret_cast<const float4*>(tex + i);
-                        const float a0 = s4.x < 0.0f ? floor_step32 : s4.x, a1 = s4.y < 0.0f ? floor_step32 : s4.y;
-                        const float a2 = s4.z < 0.0f ? floor_step32 : s4.z, a3 = s4.w < 0.0f ? floor_step32 : s4.w;
-                        float4 o;
-                        o.x = t32;
-                        o.y = __fadd_rn(o.x, a0);
-                        o.z = __fadd_rn(o.y, a1);
-                        o.w = __fadd_rn(o.z, a2);
-                        t32 = __fadd_rn(o.w, a3);
-                        *reinterpret_cast<float4*>(tex + i) = o;
+                    // Register-blocked and software-pipelined by hand: one warp issues at most one instruction every other
+                    // cycle, so the loop is kept at LDS.128 / 4 FADD / STS.128 per four steps (P1 already resolved the
+                    // floors), two blocks per iteration with ping-pong registers (no moves), the loads of the NEXT eight
+                    // steps in flight while the eight dependent FADDs of this block run.  Reads run up to 12 floats past
+                    // the last row: that is the pad of the clock row.
+                    if (i < T) {
+                        float* p = tex + i;
+                        float4 a0 = *reinterpret_cast<const float4*>(p), a1 = *reinterpret_cast<const float4*>(p + 4);
+#define MG_CLOCK8(A0, A1, N0, N1, OFF)                                              \
+    {                                                                               \
+        N0 = *reinterpret_cast<const float4*>(p + (OFF) + 8);                       \
+        N1 = *reinterpret_cast<const float4*>(p + (OFF) + 12);                      \
+        float4 o0, o1;                                                              \
+        o0.x = t32;                                                                 \
+        o0.y = __fadd_rn(o0.x, A0.x);                                               \
+        o0.z = __fadd_rn(o0.y, A0.y);                                               \
+        o0.w = __fadd_rn(o0.z, A0.z);                                               \
+        o1.x = __fadd_rn(o0.w, A0.w);                                               \
+        o1.y = __fadd_rn(o1.x, A1.x);                                               \
+        o1.z = __fadd_rn(o1.y, A1.y);                                               \
+        o1.w = __fadd_rn(o1.z, A1.z);                                               \
+        t32 = __fadd_rn(o1.w, A1.w);                                                \
+        *reinterpret_cast<float4*>(p + (OFF)) = o0;                                 \
+        *reinterpret_cast<float4*>(p + (OFF) + 4) = o1;                             \
+    }
+                        float4 b0, b1;
+#pragma unroll 1
+                        for (; i < T; i += 16, p += 16) {      // rows past T (up to 15 of them) are pad: computed, never read
+                            MG_CLOCK8(a0, a1, b0, b1, 0)
+                            MG_CLOCK8(b0, b1, a0, a1, 8)
+                        }
+#undef MG_CLOCK8
                     }
                 }
                 S.ndbl[mb][lane] = ndbl;
@@ -404,8 +309,6 @@ __global__ void __launch_bounds__(256) extract_notes_abs_kernel(const float4* __
     }
 }
 
-constexpr size_t kGanSmem = sizeof(float) * kRollsPerCta * kTexStride + sizeof(int) * kRollsPerCta;
-
 int init_once() {
     static int done = 0;  // 0 = not yet, 1 = ok
     if (done) return MG_OK;
@@ -413,8 +316,6 @@ int init_once() {
     double t = 0.0;
     for (int k = 0; k <= kMaxRows; ++k) { tab[k] = t; t = t + 0.1; }
     MG_CUDA_OK(cudaMemcpyToSymbol(c_floor_clock, tab, sizeof(tab)));
-    MG_CUDA_OK(cudaFuncSetAttribute(extract_notes_gan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kGanSmem));
     MG_CUDA_OK(cudaFuncSetAttribute(extract_notes_gan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(NotesSmem)));
     done = 1;
@@ -461,16 +362,9 @@ extern "C" int mg_extract_notes_gan(const float* rolls, long long nrolls, int nr
     snap_lut(allowed_mask, P.lut);
     P.counts = counts; P.pitch = pitch; P.velocity = velocity; P.start = start; P.end = end;
     mg::ProbeScope probe(mg::PROBE_NOTES, 0.0, (double)nrolls * (nrows * 16.0 + 4.0), mg::as_stream(stream));
-    static const bool three_phase = getenv("MELOGAN_NOTES_3PHASE") != nullptr;     // A/B: the unpipelined kernel
-    if (three_phase) {
-        const long long ntiles = (nrolls + kRollsPerCta - 1) / kRollsPerCta;
-        const int grid = (int)((ntiles < (long long)mg::num_sms() * 6) ? ntiles : (long long)mg::num_sms() * 6);
-        extract_notes_gan_kernel<<<grid, kThreads, kGanSmem, mg::as_stream(stream)>>>(P);
-    } else {
-        const long long ntiles = (nrolls + kTile - 1) / kTile;
-        const int grid = (int)((ntiles < (long long)mg::num_sms()) ? ntiles : (long long)mg::num_sms());
-        extract_notes_gan_pipe_kernel<<<grid, kThreadsV2, sizeof(NotesSmem), mg::as_stream(stream)>>>(P);
-    }
+    const long long ntiles = (nrolls + kTile - 1) / kTile;
+    const int grid = (int)((ntiles < (long long)mg::num_sms()) ? ntiles : (long long)mg::num_sms());
+    extract_notes_gan_pipe_kernel<<<grid, kThreadsV2, sizeof(NotesSmem), mg::as_stream(stream)>>>(P);
     MG_LAUNCH_OK();
     return MG_OK;
 }
