@@ -72,6 +72,14 @@ int mg_extract_notes_abs(const float* rolls, long long nrolls, int nrows, uint8_
 int mg_extract_notes_abs_host(const float* rolls_host, long long nrolls, int nrows, uint8_t* pitch_host,
                               uint8_t* velocity_host, double* start_host, double* end_host);
 
+/* 8(f)-3  MIDIDataset.__getitem__ normalisation of raw rolls     reference src/ae/dataset.py:72-89,105
+ * notes/out (nrolls, nrows, 4) float32 device buffers, rows (pitch, start, duration, velocity) in raw units (MIDI
+ * numbers, beats); rows with pitch == -1 are padding and are copied.  pitch, velocity -> (x/128)*2-1 (velocity clipped to
+ * [0,127] first), start /= max_start_beat (cfg MAX_START_BEAT, 100), duration /= max_duration_beat (MAX_DURATION_BEAT,
+ * 20), then nan_to_num(0, 0, 0).  Bit-exact with the reference's float32 numpy arithmetic; out may alias notes. */
+int mg_ae_normalize(const float* notes, float* out, long long nrolls, int nrows, double max_start_beat,
+                    double max_duration_beat, void* stream);
+
 /* utils.py:14-26,119-121: mask of allowed pitch classes for a named scale and root key;
  * unknown names select the chromatic scale like SCALES.get(scale, SCALES['chromatic']). */
 uint32_t mg_scale_mask(const char* scale_name, int root_key);

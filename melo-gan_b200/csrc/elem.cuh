@@ -576,10 +576,15 @@ static __global__ void generator_loss_kernel(const float* __restrict__ score, co
         float se = 0.f;
         for (int k = 0; k < NC; ++k) se += expf(l[k] - mx);
         const float lse = mx + logf(se);
-        const int y = (int)labels[i];
-        ce += (double)(lse - l[y]);
+        // nn.CrossEntropyLoss raises on a target outside [0, NC) (emotion_to_index returns -1 for unknown moods); a kernel
+        // cannot raise, so such a row poisons the loss and its gradient with NaN instead of reading outside the logits row
+        const long long y64 = labels[i];
+        const bool y_ok = y64 >= 0 && y64 < NC;
+        const int y = y_ok ? (int)y64 : 0;
+        ce += y_ok ? (double)(lse - l[y]) : (double)__int_as_float(0x7fc00000);
         for (int k = 0; k < NC; ++k)
-            dlogits[(long long)i * NC + k] = emo_weight * (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) / (float)B;
+            dlogits[(long long)i * NC + k] =
+                y_ok ? emo_weight * (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) / (float)B : __int_as_float(0x7fc00000);
     }
     for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); ce += __shfl_xor_sync(0xffffffffu, ce, o); }
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = ce; }
@@ -647,11 +652,15 @@ static __global__ void ce_loss_acc_kernel(const float* __restrict__ logits, cons
         float se = 0.f;
         for (int k = 0; k < NC; ++k) se += expf(l[k] - mx);
         const float lse = mx + logf(se);
-        const int y = (int)labels[i];
-        ce += (double)(lse - l[y]);
-        hit += (am == y) ? 1.0 : 0.0;
+        const long long y64 = labels[i];                 // out-of-range targets: NaN loss and gradient (see above)
+        const bool y_ok = y64 >= 0 && y64 < NC;
+        const int y = y_ok ? (int)y64 : 0;
+        ce += y_ok ? (double)(lse - l[y]) : (double)__int_as_float(0x7fc00000);
+        hit += (y_ok && am == y) ? 1.0 : 0.0;
         if (dlogits)
-            for (int k = 0; k < NC; ++k) dlogits[(long long)i * NC + k] = (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) / (float)B;
+            for (int k = 0; k < NC; ++k)
+                dlogits[(long long)i * NC + k] =
+                    y_ok ? (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) / (float)B : __int_as_float(0x7fc00000);
     }
     for (int o = 16; o; o >>= 1) { ce += __shfl_xor_sync(0xffffffffu, ce, o); hit += __shfl_xor_sync(0xffffffffu, hit, o); }
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ce; red[1][threadIdx.x >> 5] = hit; }

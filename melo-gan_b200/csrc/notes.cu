@@ -309,6 +309,31 @@ __global__ void __launch_bounds__(256) extract_notes_abs_kernel(const float4* __
     }
 }
 
+// 8(f)-3  MIDIDataset.__getitem__ normalisation   reference src/ae/dataset.py:72-89,105
+// Rows are (pitch, start, duration, velocity) in raw units; rows whose pitch is exactly -1 are padding and stay untouched.
+// numpy float32 arithmetic, one rounding per operation (weak python scalars keep the array dtype):
+//   pitch    = (p / 128) * 2 - 1;   velocity = (clip(v, 0, 127) / 128) * 2 - 1   (np.clip propagates NaN)
+//   start    = s / MAX_START_BEAT;  duration = d / MAX_DURATION_BEAT
+// then np.nan_to_num(nan=0, posinf=0, neginf=0) over the whole roll (padding rows included).
+__device__ __forceinline__ float nan_inf_to_zero(float x) { return fabsf(x) < __int_as_float(0x7f800000) ? x : 0.0f; }
+__device__ __forceinline__ float to_unit128(float x) { return __fsub_rn(__fmul_rn(__fmul_rn(x, 0.0078125f), 2.0f), 1.0f); }
+
+__global__ void __launch_bounds__(256) ae_normalize_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                           long long nrowsTotal, float max_start, float max_dur) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrowsTotal; i += stride) {
+        float4 q = __ldg(in + i);
+        if (q.x != -1.0f) {                                   // NaN != -1: such a row is normalised (then zeroed below)
+            const float v = q.w != q.w ? q.w : fminf(fmaxf(q.w, 0.0f), 127.0f);
+            q.x = to_unit128(q.x);                            // x / 128.0 == x * 2^-7 bit for bit
+            q.y = __fdiv_rn(q.y, max_start);
+            q.z = __fdiv_rn(q.z, max_dur);
+            q.w = to_unit128(v);
+        }
+        out[i] = make_float4(nan_inf_to_zero(q.x), nan_inf_to_zero(q.y), nan_inf_to_zero(q.z), nan_inf_to_zero(q.w));
+    }
+}
+
 int init_once() {
     static int done = 0;  // 0 = not yet, 1 = ok
     if (done) return MG_OK;
@@ -382,6 +407,24 @@ extern "C" int mg_extract_notes_abs(const float* rolls, long long nrolls, int nr
     if (blocks > cap) blocks = cap;
     extract_notes_abs_kernel<<<(int)blocks, 256, 0, mg::as_stream(stream)>>>(
         reinterpret_cast<const float4*>(rolls), n, pitch, velocity, start, end, status_dev);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
+extern "C" int mg_ae_normalize(const float* notes, float* out, long long nrolls, int nrows, double max_start_beat,
+                               double max_duration_beat, void* stream) {
+    MG_REQUIRE(nrolls >= 0 && nrows >= 0, "ae_normalize: negative size");
+    const long long n = nrolls * nrows;
+    if (n == 0) return MG_OK;
+    MG_REQUIRE(notes && out, "ae_normalize: null pointer");
+    MG_REQUIRE(((uintptr_t)notes % 16) == 0 && ((uintptr_t)out % 16) == 0, "ae_normalize: buffers must be 16-byte aligned");
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)mg::num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    mg::ProbeScope probe(mg::PROBE_NOTES, 0.0, (double)n * 32.0, mg::as_stream(stream));
+    ae_normalize_kernel<<<(int)blocks, 256, 0, mg::as_stream(stream)>>>(reinterpret_cast<const float4*>(notes),
+                                                                       reinterpret_cast<float4*>(out), n,
+                                                                       (float)max_start_beat, (float)max_duration_beat);
     MG_LAUNCH_OK();
     return MG_OK;
 }

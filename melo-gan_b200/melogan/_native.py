@@ -31,6 +31,7 @@ _SIGNATURES = {
     "mg_extract_notes_gan_host": ([_vp, _ll, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_extract_notes_abs": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_extract_notes_abs_host": ([_vp, _ll, _i, _vp, _vp, _vp, _vp], _i),
+    "mg_ae_normalize": ([_vp, _vp, _ll, _i, _d, _d, _vp], _i),
     "mg_adam_step": ([_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _i, _f, _ll, _vp, _vp, _vp], _i),
     "mg_adam_step_clipped": ([_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _i, _f, _f, _vp, _ll, _vp, _vp, _vp], _i),
     "mg_launch_count": ([], _ll),

@@ -86,6 +86,19 @@ def extract_notes_abs(rolls, check=True):
     return out
 
 
+def ae_normalize(notes, max_start_beat=100.0, max_duration_beat=20.0, out=None):
+    """MIDIDataset.__getitem__ normalisation (reference src/ae/dataset.py:72-89,105) of a whole device-resident data set
+    at once: notes (R, T, 4) float32 CUDA tensor of raw rows (pitch, start, duration, velocity); -1 padding rows are kept."""
+    notes = _require_cuda_rolls(notes)
+    out = torch.empty_like(notes) if out is None else out
+    if not (out.is_cuda and out.dtype == torch.float32 and out.shape == notes.shape and out.is_contiguous()):
+        raise ValueError("out must be a contiguous float32 CUDA tensor shaped like notes")
+    with torch.cuda.device(notes.device):
+        _native.call("mg_ae_normalize", notes.data_ptr(), out.data_ptr(), notes.shape[0], notes.shape[1],
+                     float(max_start_beat), float(max_duration_beat), torch.cuda.current_stream(notes.device).cuda_stream)
+    return out
+
+
 def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 

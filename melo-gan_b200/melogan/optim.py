@@ -46,8 +46,14 @@ class FlatParams:
 
 
 class FusedAdam:
-    def __init__(self, flat: FlatParams, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+    def __init__(self, flat: FlatParams, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
+                 max_norm=None):
+        """decoupled=True is the AdamW form.  max_norm: torch.nn.utils.clip_grad_norm_(params, max_norm) over the whole
+        flat group fused in front of the update (reference src/ae/train_ae.py:121); the pre-clip norm of the last step
+        is left in self.grad_norm (device)."""
         self.flat = flat
+        self.max_norm = None if max_norm is None else float(max_norm)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat.data.device)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.weight_decay, self.decoupled = float(weight_decay), bool(decoupled)
         self.exp_avg = torch.zeros_like(flat.data)
@@ -62,7 +68,14 @@ class FusedAdam:
     def step(self, stream=None):
         f = self.flat
         s = (stream if stream is not None else torch.cuda.current_stream(f.data.device)).cuda_stream
+        bf = self.bf16_copy.data_ptr() if self.bf16_copy is not None else None
         with torch.cuda.device(f.data.device):
+            if self.max_norm is not None:
+                _native.call("mg_adam_step_clipped", f.data.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
+                             self.exp_avg_sq.data_ptr(), f.numel, self.lr, self.betas[0], self.betas[1], self.eps,
+                             self.weight_decay, int(self.decoupled), float(self.grad_scale), self.max_norm,
+                             self.grad_norm.data_ptr(), 0, self.step_dev.data_ptr(), bf, s)
+                return
             _native.call("mg_adam_step", f.data.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
                          self.exp_avg_sq.data_ptr(), f.numel, self.lr, self.betas[0], self.betas[1], self.eps,
                          self.weight_decay, int(self.decoupled), float(self.grad_scale), 0,

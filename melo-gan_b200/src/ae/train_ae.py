@@ -6,11 +6,13 @@
 Same flow as the reference's src/ae/train_ae.py (vae_loss, train, main): per batch forward -> vae_loss -> zero_grad ->
 backward -> clip_grad_norm_(1.0) -> AdamW, beta warm-up per epoch, ReduceLROnPlateau(factor 0.5, patience 5, min_lr 1e-6)
 on the validation loss, ae_best.pth {'epoch','model_state'} / ae_final.pth checkpoints, early stopping.  The model's
-forward and backward run in the native kernels (mg_vae_forward / mg_vae_backward); the loss arithmetic, gradient clipping
-and the optimizer are torch's, driven exactly as in the reference.
-Data: the reference's MIDIDataset reads per-file .npz archives with augmentation (not built); this CLI reads
-the pre-saved <SPLITS_DIR>/<split>/notes.npy arrays of the GAN fast path.  TensorBoard and reconstruction MIDI dumps of the
-reference loop are not part of the hot path and are left out.
+whole iteration runs natively (melogan.aux_trainers.VaeTrainer): mg_vae_loss_step (forward + vae_loss + backward) and
+mg_adam_step_clipped (gradient-norm clip + AdamW) over flat buffers, replayed as one CUDA graph per step.  `vae_loss` below
+is the reference's function, kept for callers that drive the drop-in module themselves.
+Data: the reference's MIDIDataset reads per-file .npz archives; this CLI reads the pre-saved <SPLITS_DIR>/<split>/notes.npy
+arrays, keeps them on the device and (NORMALIZE_RAW: true) applies the dataset's normalisation there (mg_ae_normalize).  The
+probabilistic augmentations are switched off by config/ae_config.yaml (all amplitudes 0) and are not built; TensorBoard and
+reconstruction MIDI dumps of the reference loop are not part of the hot path and are left out.
 """
 import argparse
 import os
@@ -30,63 +32,64 @@ def vae_loss(recon, target, mu, log_var, beta):
     return recon_loss + beta * kld_loss, recon_loss, kld_loss
 
 
-def _batches(notes, bs, shuffle, gen, drop_last):
-    n = len(notes)
-    idx = torch.randperm(n, generator=gen) if shuffle else torch.arange(n)
-    stop = n - bs + 1 if drop_last else n
-    for i in range(0, max(stop, 0), bs):
-        yield notes[idx[i:i + bs]]
+def load_rolls(cfg, split, device):
+    """<SPLITS_DIR>/<split>/notes.npy as a device-resident float32 tensor.  cfg['NORMALIZE_RAW'] (default false: the GAN
+    fast path's arrays are already in model units) applies MIDIDataset.__getitem__'s normalisation of raw rolls
+    (reference src/ae/dataset.py:72-89,105) on the device, the whole split in one launch."""
+    from melogan import notes as N
+    from melogan.aux_trainers import find_split_dir
+    x = torch.from_numpy(np.load(os.path.join(find_split_dir(cfg['SPLITS_DIR'], split), "notes.npy")).astype(np.float32))
+    x = x.to(device)
+    if cfg.get('NORMALIZE_RAW', False):
+        x = N.ae_normalize(x, cfg.get('MAX_START_BEAT', 100.0), cfg.get('MAX_DURATION_BEAT', 20.0))
+    return x
 
 
 def train(cfg):
+    """train_ae.py:54-199 of the reference on the fast path: melogan.aux_trainers.VaeTrainer (one CUDA graph per step:
+    device RNG, fused forward + vae_loss + backward, fused clip_grad_norm_ + AdamW, device loss accumulation)."""
+    from melogan.aux_trainers import ReduceOnPlateau, VaeTrainer
     if not torch.cuda.is_available():
         raise SystemExit("train_ae: a CUDA (sm_100a) device is required; this implementation has no CPU fallback")
     device = torch.device("cuda")
     model_dir = cfg.get('CHECKPOINT_DIR', 'models/ae')
     os.makedirs(model_dir, exist_ok=True)
-    load = lambda split: torch.from_numpy(np.load(os.path.join(cfg['SPLITS_DIR'], split, "notes.npy")).astype(np.float32))
-    train_x, val_x = load("train"), load("val")
+    train_x, val_x = load_rolls(cfg, "train", device), load_rolls(cfg, "val", device)      # resident on the device
     print(f"Train rolls: {len(train_x)}   Val rolls: {len(val_x)}")
 
-    model = VAE(cfg).to(device)
-    with torch.no_grad():
-        model.encoder(torch.zeros(1, cfg['MAX_NOTES'], 4, device=device))       # materialise encoder._linear
-    optimizer = torch.optim.AdamW(model.parameters(), lr=float(cfg.get('LR', 0.0001)),
-                                  weight_decay=float(cfg.get('WEIGHT_DECAY', 0.00001)))
-    scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=0.5, patience=5, min_lr=1e-6)
+    bs = cfg['BATCH_SIZE']
+    tr = VaeTrainer(cfg, batch=bs, precision=os.environ.get("MELOGAN_PRECISION", "fp32"), device=device, max_norm=1.0)
+    model = tr.model
+    scheduler = ReduceOnPlateau(tr.opt, factor=0.5, patience=5, min_lr=1e-6)
     best_val, no_improve = float('inf'), 0
     patience = cfg.get('EARLY_STOP_PATIENCE', 10)
     warm, final_beta = cfg.get('KLD_WARMUP_EPOCHS', 25), float(cfg.get('BETA', 1.0))
     gen = torch.Generator().manual_seed(int(cfg.get('SEED', 0)))
-    bs = cfg['BATCH_SIZE']
+    use_graph = os.environ.get("MELOGAN_NO_GRAPH") is None
+    captured_for, s_x = None, None
 
     for epoch in range(1, cfg['EPOCHS'] + 1):
-        model.train()
         beta = final_beta if epoch >= warm else min(final_beta, (epoch / warm) * final_beta)
-        tot = np.zeros(3)
-        nb = 0
-        for notes in _batches(train_x, bs, True, gen, drop_last=True):
-            notes = notes.to(device)
-            recon, z, mu, log_var = model(notes)
-            loss, recon_loss, kld_loss = vae_loss(recon, notes, mu, log_var, beta)
-            optimizer.zero_grad()
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
-            optimizer.step()
-            tot += [loss.item(), recon_loss.item(), kld_loss.item()]
-            nb += 1
-        tot /= max(1, nb)
+        tr.beta = beta
+        perm = torch.randperm(len(train_x), generator=gen).to(device)                   # shuffle=True, drop_last=True
+        for i in range(0, len(train_x) - bs + 1, bs):
+            idx = perm[i:i + bs]
+            if use_graph and captured_for == (beta, tr.opt.lr):
+                torch.index_select(train_x, 0, idx, out=s_x)
+                tr.replay()
+            else:
+                tr.step(train_x[idx].contiguous())                                      # eager (also the warm-up of a capture)
+                if use_graph:
+                    s_x = tr.capture()                                                   # beta and lr are baked into the graph
+                    captured_for = (beta, tr.opt.lr)
+        tot = tr.epoch_means()
 
-        model.eval()
-        val = np.zeros(3)
+        val = torch.zeros(3, device=device)
         vb = 0
-        with torch.no_grad():
-            for notes in _batches(val_x, bs, False, gen, drop_last=False):
-                notes = notes.to(device)
-                recon, z, mu, log_var = model(notes)
-                val += [t.item() for t in vae_loss(recon, notes, mu, log_var, beta=1.0)]
-                vb += 1
-        val /= max(1, vb)
+        for i in range(0, len(val_x), bs):                                               # drop_last=False: the tail batch counts
+            val += tr.evaluate(val_x[i:i + bs].contiguous())
+            vb += 1
+        val = (val / max(1, vb)).tolist()
         scheduler.step(val[0])
         print(f"[Epoch {epoch}] Train: {tot[0]:.6f} (Recon: {tot[1]:.6f}, KLD: {tot[2]:.6f}) | "
               f"Val: {val[0]:.6f} (Recon: {val[1]:.6f}, KLD: {val[2]:.6f})  beta={beta:.2f}")

@@ -79,6 +79,7 @@ def load_split_npz(cfg, split_csv):
     if not notes:
         raise FileNotFoundError(f"no processed .npz resolved from {split_csv} under {processed_dir}")
     labels = np.array([emotion_to_index(m) for m in moods], dtype=np.int64)
+    check_labels(labels, str(split_csv))
     return np.stack(notes), np.stack(numeric), labels
 
 
@@ -96,7 +97,30 @@ def load_split_arrays(cfg, split_csv):
     if not (len(notes) == len(emotions) == len(numeric)):
         raise ValueError("NPY file length mismatch (notes, emotions, numeric_features)")
     labels = np.array([emotion_to_index(e) for e in emotions], dtype=np.int64)
+    check_labels(labels, name)
     return notes.astype(np.float32), numeric.astype(np.float32), labels
+
+
+def check_labels(labels, what, n_classes=4):
+    """The generator step feeds these to the fused cross-entropy; nn.CrossEntropyLoss (reference train_gan.py:231) raises
+    on a target outside [0, n_classes) -- emotion_to_index gives -1 for an unknown or missing mood -- so do we, once, here."""
+    bad = np.nonzero((labels < 0) | (labels >= n_classes))[0]
+    if len(bad):
+        raise IndexError(f"{what}: Target {int(labels[bad[0]])} is out of bounds (row {int(bad[0])}; {len(bad)} such rows): "
+                         f"emotion labels must map to [0, {n_classes})")
+
+
+def load_encoder_feats(path, n, latent_dim):
+    """`latent_feats` of the reference's prepare_dataset / GANDataset (train_gan.py:50-51, dataset.py:47-54,169-171): the
+    array at cfg['ENCODER_FEATS_TRAIN'] when it exists and has one row per sample, else (warning) zero latents."""
+    if path and os.path.exists(path):
+        feats = np.load(path).astype(np.float32)
+        if feats.shape[0] == n and feats.ndim == 2 and feats.shape[1] == latent_dim:
+            return feats
+        print(f"[WARN] latent_feats shape mismatch {feats.shape} vs ({n}, {latent_dim}). Ignoring latent_feats.")
+    else:
+        print(f"[WARN] latent_feats not found at {path}; using zero latents.")
+    return np.zeros((n, latent_dim), dtype=np.float32)
 
 
 def main(argv=None):
@@ -137,10 +161,7 @@ def main(argv=None):
     d_notes, d_numeric, d_labels = (torch.from_numpy(a).to(device) for a in (notes, numeric, labels))   # 7 MB: resident
     d_cond = None
     if tr.cond_dim:                             # INTEGRATION_MODE 'conditioning': AE latents from src/ae/encode.py
-        feats = os.path.join(cfg.get('SPLITS_DIR', 'data/splits'), Path(cfg['TRAIN_SPLIT']).stem, "encoder_feats.npy")
-        d_cond = torch.from_numpy(np.load(feats).astype(np.float32)).to(device)
-        if d_cond.shape != (len(notes), tr.cond_dim):
-            raise ValueError(f"{feats}: expected shape {(len(notes), tr.cond_dim)}, got {tuple(d_cond.shape)}")
+        d_cond = torch.from_numpy(load_encoder_feats(cfg.get('ENCODER_FEATS_TRAIN'), len(notes), tr.cond_dim)).to(device)
     start_epoch = 1
     if args.resume:
         ck = torch.load(args.resume, map_location=device)
@@ -161,17 +182,49 @@ def main(argv=None):
     gen = torch.Generator(device="cpu").manual_seed(int(cfg.get("SEED", 42)))
     print("Starting WGAN-GP Training with Emotion Guidance...")
     steps = len(notes) // B                       # drop_last=True
+    # Every CRITIC_ITERS consecutive batches (train_gan.py:168-251: a critic step each, a generator step on the last) are
+    # ONE CUDA-graph replay over static input buffers -- at the reference's batch 32 the cycle is ~700 launches of a few
+    # microseconds each, i.e. launch-bound when issued eagerly.  The first cycle runs eagerly (allocates scratch), then the
+    # cycle is captured; the batches left over at the end of an epoch are critic steps only, as in the reference loop.
+    use_graph, captured = os.environ.get("MELOGAN_NO_GRAPH") is None, False
+
+    def batch_index(perm, b):
+        return perm[b * B:(b + 1) * B].view(world, -1)[rank]
+
+    def eager_batch(perm, b, with_g):
+        idx = batch_index(perm, b)
+        real, num = d_notes[idx].contiguous(), d_numeric[idx].contiguous()
+        cond = d_cond[idx].contiguous() if d_cond is not None else None
+        tr.critic_step(real, num, cond=cond)
+        if with_g:
+            tr.generator_step(num, d_labels[idx].contiguous(), cond=cond)
+
     for epoch in range(1, cfg['EPOCHS'] + 1):
         perm = torch.randperm(len(notes), generator=gen).to(device)          # shuffle=True, same order on every rank
         if epoch < start_epoch:
             continue                                                          # replay the shuffle stream up to the resume point
-        for batch_idx in range(steps):
-            idx = perm[batch_idx * B:(batch_idx + 1) * B].view(world, -1)[rank]
-            real, num, lab = d_notes[idx].contiguous(), d_numeric[idx].contiguous(), d_labels[idx].contiguous()
-            cond = d_cond[idx].contiguous() if d_cond is not None else None
-            tr.critic_step(real, num, cond=cond)
-            if (batch_idx + 1) % critic_iters == 0:
-                tr.generator_step(num, lab, cond=cond)
+        b = 0
+        while b < steps:
+            if b + critic_iters > steps:                                      # tail of the epoch: critic steps only
+                eager_batch(perm, b, False)
+                b += 1
+                continue
+            if captured:
+                for i in range(critic_iters):
+                    idx = batch_index(perm, b + i)
+                    torch.index_select(d_notes, 0, idx, out=tr.s_reals[i])
+                    torch.index_select(d_numeric, 0, idx, out=tr.s_numerics[i])
+                    if d_cond is not None:
+                        torch.index_select(d_cond, 0, idx, out=tr.s_conds[i])
+                torch.index_select(d_labels, 0, idx, out=tr.s_labels)
+                tr.replay_cycle()
+            else:
+                for i in range(critic_iters):
+                    eager_batch(perm, b + i, i == critic_iters - 1)
+                if use_graph:
+                    tr.capture_cycle()
+                    captured = True
+            b += critic_iters
         d_loss, g_adv, g_emo = tr.epoch_means()
         if rank == 0:
             print(f"Epoch {epoch}/{cfg['EPOCHS']} | D_loss: {d_loss:.4f} | G_adv: {g_adv:.4f} | G_emo: {g_emo:.4f}")

@@ -88,3 +88,17 @@ def digest(counts, pitch, vel, start, end):
         h.update(np.ascontiguousarray(start[r, :c], np.float64).tobytes())
         h.update(np.ascontiguousarray(end[r, :c], np.float64).tobytes())
     return h.hexdigest()
+
+
+def ae_normalize(notes, max_start_beat=100.0, max_duration_beat=20.0):
+    """numpy restatement of MIDIDataset.__getitem__ without augmentation (reference src/ae/dataset.py:68-89,105-106);
+    notes (..., T, 4) raw rows (pitch, start, duration, velocity), float32 arithmetic as numpy does it there."""
+    notes = np.array(notes, dtype=np.float32, copy=True)
+    flat = notes.reshape(-1, 4)
+    mask = flat[:, 0] != -1
+    flat[mask, 0] = (flat[mask, 0] / 128.0) * 2.0 - 1.0
+    flat[mask, 3] = np.clip(flat[mask, 3], 0, 127)
+    flat[mask, 3] = (flat[mask, 3] / 128.0) * 2.0 - 1.0
+    flat[mask, 1] = flat[mask, 1] / max_start_beat
+    flat[mask, 2] = flat[mask, 2] / max_duration_beat
+    return np.nan_to_num(flat, nan=0.0, posinf=0.0, neginf=0.0).astype(np.float32).reshape(notes.shape)

@@ -58,3 +58,47 @@ def test_fast_path_is_preferred_and_falls_back(tmp_path):
     (tmp_path / "splits" / "bad.csv").write_text("x,y\n1,2\n")
     with pytest.raises(KeyError):
         load_split_npz(cfg, str(tmp_path / "splits" / "bad.csv"))
+
+
+def test_labels_outside_the_classes_raise_like_cross_entropy():
+    """emotion_to_index returns -1 for unknown moods; nn.CrossEntropyLoss raises on such targets."""
+    import pytest
+    from src.gan import train_gan as T
+    T.check_labels(np.array([0, 1, 2, 3]), "ok")
+    with pytest.raises(IndexError):
+        T.check_labels(np.array([0, -1, 2]), "bad")
+    with pytest.raises(IndexError):
+        T.check_labels(np.array([0, 4]), "bad")
+
+
+def test_encoder_feats_follow_the_config_key_and_fall_back_to_zeros(tmp_path):
+    """cfg['ENCODER_FEATS_TRAIN'] like the reference's prepare_dataset; missing file / length mismatch ->
+    zero latents with a warning (dataset.py:47-54,169-171)."""
+    from src.gan import train_gan as T
+    f = tmp_path / "encoder_feats.npy"
+    np.save(f, np.arange(12, dtype=np.float32).reshape(3, 4))
+    assert np.array_equal(T.load_encoder_feats(str(f), 3, 4), np.arange(12, dtype=np.float32).reshape(3, 4))
+    assert not T.load_encoder_feats(str(f), 5, 4).any() and T.load_encoder_feats(str(f), 5, 4).shape == (5, 4)
+    assert not T.load_encoder_feats(str(tmp_path / "missing.npy"), 2, 4).any()
+    assert not T.load_encoder_feats(None, 2, 4).any()
+
+
+def test_split_directory_convention_and_plateau_scheduler(tmp_path):
+    import torch
+    from melogan.aux_trainers import ReduceOnPlateau, find_split_dir
+    (tmp_path / "train_split").mkdir()
+    (tmp_path / "val").mkdir()
+    assert find_split_dir(str(tmp_path), "train").endswith("train_split")
+    assert find_split_dir(str(tmp_path), "train_split").endswith("train_split")
+    assert find_split_dir(str(tmp_path), "val_split").endswith("val")
+
+    class Opt:
+        lr = 1e-3
+    o = Opt()
+    mine = ReduceOnPlateau(o, factor=0.5, patience=2, threshold=1e-4, min_lr=1e-4)
+    p = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.SGD([p], lr=1e-3)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(topt, factor=0.5, patience=2, threshold=1e-4, min_lr=1e-4)
+    for m in [1.0, 0.9, 0.95, 0.95, 0.95, 0.95, 0.8, 0.81, 0.82, 0.83, 0.84, 0.85, 0.86, 0.87, 0.88, 0.89, 0.9, 0.91]:
+        mine.step(m); ref.step(m)
+        assert abs(o.lr - topt.param_groups[0]["lr"]) < 1e-12, (m, o.lr, topt.param_groups[0]["lr"])
