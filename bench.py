@@ -193,6 +193,72 @@ def notes_records(L, dev, peak_gbs, R=262144):
             rec("extract_notes_abs_kernel (N-2)", ms2, b2, "8192 B read + 9216 B written per roll")]
 
 
+def aux_records(dev, steps=30):
+    """BASELINE configs #2 / #3 through their fast-path trainers (melogan/aux_trainers.py): one step = forward + loss +
+    backward + (clip) + AdamW, replayed as ONE CUDA graph over a static batch that is refreshed from a rotating set of
+    resident batches before every replay; device RNG for eps / dropout.  Reference loops: src/ae/train_ae.py:100-122,
+    src/emotion_discriminator/train_ed.py:61-74.  Returns one record per (config, precision, batch)."""
+    import contextlib
+    import torch
+    import yaml
+    from melogan.aux_trainers import EdTrainer, VaeTrainer
+
+    with open(os.path.join(PKG, "config", "ae_config.yaml")) as f:
+        ae_cfg = yaml.safe_load(f)
+    with open(os.path.join(PKG, "config", "ed_config.yaml")) as f:
+        ed_cfg = yaml.safe_load(f)
+    out = []
+
+    def timed(fn, n):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(5 + i)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+
+    g = torch.Generator(device=dev).manual_seed(11)
+    for precision in ("fp32", "bf16"):
+        for B in (int(ae_cfg.get("BATCH_SIZE", 32)), 1024):
+            with contextlib.redirect_stdout(sys.stderr):
+                tr = VaeTrainer(dict(ae_cfg), batch=B, precision=precision, device=dev)
+            xs = [torch.rand((B, tr.T, 4), generator=g, device=dev) * 2 - 1 for _ in range(3)]
+            tr.step(xs[0])
+            sx = tr.capture()
+
+            def vstep(i):
+                sx.copy_(xs[i % 3]); tr.replay()
+            ms = timed(vstep, steps)
+            loss = tr.epoch_means()[0]
+            out.append({"config": "#2 VAE train step (ae_config.yaml)", "precision": precision, "batch": B, "ms_per_step": ms,
+                        "rolls_per_s": B / ms * 1e3, "cuda_graph": True, "loss_finite": bool(loss == loss and abs(loss) < 1e30)})
+            del tr, sx, xs
+            torch.cuda.empty_cache()
+        for B in (int(ed_cfg.get("batch_size", 64)), 1024):
+            with contextlib.redirect_stdout(sys.stderr):
+                tr = EdTrainer(dict(ed_cfg), batch=B, precision=precision, device=dev)
+            xs = [torch.rand((B, tr.T, 4), generator=g, device=dev) * 2 - 1 for _ in range(3)]
+            y = (torch.arange(B, device=dev) % tr.n_classes).to(torch.int64)
+            tr.step(xs[0], y)
+            sx, sy = tr.capture()
+            sy.copy_(y)
+
+            def estep(i):
+                sx.copy_(xs[i % 3]); tr.replay()
+            ms = timed(estep, steps)
+            loss = tr.epoch_means()[0]
+            out.append({"config": "#3 emotion-discriminator train step (ed_config.yaml)", "precision": precision, "batch": B,
+                        "ms_per_step": ms, "rolls_per_s": B / ms * 1e3, "cuda_graph": True,
+                        "loss_finite": bool(loss == loss and abs(loss) < 1e30)})
+            del tr, sx, sy, xs
+            torch.cuda.empty_cache()
+    return out
+
+
 def parity_check(tr, cfg, ed_cfg, reals, numerics, labels, dev):
     """One critic step and one generator step of the BENCHED configuration (bf16 mode, bench batch, trained-for-a-few-
     steps parameters) against this engine's own fp32 parity mode (CUDA-core kernels, pinned to the oracle at 1e-5 by
@@ -360,10 +426,14 @@ def main():
             tr.train_cycle(reals[i % NSETS], numerics[i % NSETS], labels)
 
     def e2e_step(i):
+        # The call a user makes (GanTrainer.prefetch / replay_cycle_prefetched): this step's inputs were put on the copy
+        # stream from pinned host memory while the previous step computed (the first one by the warm-up below); the
+        # step waits for them, replays the cycle, starts the H2D of the NEXT step's inputs and reads this step's losses
+        # on the host.  Every step's 337 MB H2D and its D2H are inside the timed region.
         if use_graph:
-            s_reals.copy_(h_reals[i % NSETS], non_blocking=True); s_numerics.copy_(h_numerics[i % NSETS], non_blocking=True)
-            s_labels.copy_(h_labels, non_blocking=True)
-            tr.replay_cycle()
+            tr.replay_cycle_prefetched()
+            j = (i + 1) % NSETS
+            tr.prefetch(h_reals[j], h_numerics[j], h_labels)
         else:
             r = h_reals[i % NSETS].to(dev, non_blocking=True); x = h_numerics[i % NSETS].to(dev, non_blocking=True)
             lb = h_labels.to(dev, non_blocking=True)
@@ -400,6 +470,8 @@ def main():
     ms_dev = timed(device_step, args.steps)
     if sampler:
         sampler.stop_flag.set(); sampler.join(timeout=3)
+    if use_graph:
+        tr.prefetch(h_reals[0], h_numerics[0], h_labels)  # inputs of the first (warm-up) step
     ms_e2e = timed(e2e_step, args.steps)
 
     # per-kernel roofline of the dominant kernel family, measured live with CUDA events (eager pass)
@@ -455,6 +527,10 @@ def main():
             extra["parity_check"] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
         del reals, numerics
         torch.cuda.empty_cache()
+        try:
+            extra["aux_configs"] = aux_records(dev)
+        except Exception as e:
+            extra["aux_configs"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_yardstick:
             try:
                 extra["stock_torch_eager_same_gpu"] = stock_torch_yardstick(dev, B)
@@ -477,7 +553,9 @@ def main():
                    "l2": f"{NSETS} rotating input sets; per-step activation working set {tr.engine.workspace_bytes() / 1e6:.0f} MB >> 126 MB L2",
                    "algorithmic_mflop_per_roll": MFLOP_PER_ROLL},
         "e2e": {"value": e2e_value, "unit": "rolls/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "pipeline": "H2D of step i+1 on a copy stream under the compute of step i (GanTrainer.prefetch), one D2D into the "
+                            "graph's static buffers per step, losses read on the host every step"},
         "gpu_launches": launches_per_cycle * args.steps,
         "clocks": sampler.summary() if sampler else None,
         "roofline": {"bound": "tensor", "kernel": {1: "tapgemm_kernel (CUDA-core fp32 implicit GEMM)",

@@ -11,6 +11,8 @@ Data parallelism: one process per GPU, batch-sharded; the only ex
 all-reduce of the flat gradient buffers over NCCL/NVLink (1.09 MB per D-step, 35.4 MB per G-step);
 BatchNorm statistics stay local to the rank ("local BN", what torch DDP would do to the reference).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -209,7 +211,9 @@ class GanTrainer:
         In 'conditioning' mode a fourth static buffer, self.s_conds (K, B, latent), holds the AE latents of the batches.
         Single GPU: the whole cycle is ONE graph.  Data parallel: NCCL all-reduces stay outside the graphs (capturing
         them deadlocked on this stack), so every step is two graphs -- [zero grads, draw, step body] and [Adam, loss
-        accumulation] -- with the eager all-reduce of the flat gradient buffer between them on the same stream."""
+        accumulation] -- with the eager all-reduce of the flat gradient buffer between them on the same stream.
+        (Round 2, two B200s: NCCL captured inside ONE cycle graph in thread-local capture mode replays correctly but is
+        no faster -- 53.70 vs 53.47 ms per cycle -- and the process group then hangs at teardown; not kept.)"""
         K, B, dev = self.critic_iters, self.B, self.device
         self.s_reals = torch.zeros((K, B, self.cfg['MAX_NOTES'], self.cfg['NOTE_DIM']), device=dev)
         self.s_numerics = torch.zeros((K, B, self.cfg.get('NUMERIC_INPUT_DIM', 6)), device=dev)
@@ -267,6 +271,52 @@ class GanTrainer:
             self._allreduce(self.flat_d if i < K else self.flat_g)
             self._g_post[i].replay()
 
+    # ---- host -> device input pipeline (double buffered) ----
+    def prefetch(self, h_reals, h_numerics, h_labels, h_conds=None):
+        """Starts the host->device copy of the NEXT cycle's inputs (pinned host tensors shaped like the static buffers of
+        capture_cycle) on a dedicated copy stream into a second set of device buffers, so that it runs under the cycle
+        the compute stream is working on.  replay_cycle_prefetched() then moves them into the static buffers with one
+        device-to-device copy (337 MB at HBM speed instead of PCIe speed on the critical path)."""
+        if self._graph is None:
+            raise RuntimeError("capture_cycle() first")
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stg = [torch.empty_like(t) for t in (self.s_reals, self.s_numerics, self.s_labels)]
+            self._stg_conds = torch.empty_like(self.s_conds) if self.s_conds is not None else None
+            self._staged, self._stg_free = torch.cuda.Event(), torch.cuda.Event()
+            self._stg_free.record(torch.cuda.current_stream(self.device))
+        cs = self._copy_stream
+        cs.wait_event(self._stg_free)                    # the previous contents have left the staging buffers
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stg, (h_reals, h_numerics, h_labels)):
+                dst.copy_(src, non_blocking=True)
+            if self._stg_conds is not None:
+                if h_conds is None:
+                    raise ValueError("INTEGRATION_MODE 'conditioning' needs the AE latents of the batches")
+                self._stg_conds.copy_(h_conds, non_blocking=True)
+            self._staged.record(cs)
+
+    def replay_cycle_prefetched(self):
+        """Replays the captured cycle on the inputs of the last prefetch()."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged)
+        self.s_reals.copy_(self._stg[0]); self.s_numerics.copy_(self._stg[1]); self.s_labels.copy_(self._stg[2])
+        if self._stg_conds is not None:
+            self.s_conds.copy_(self._stg_conds)
+        self._stg_free.record(cur)
+        self.replay_cycle()
+
+    def sync_bn_running_stats_(self):
+        """Data parallel: BatchNorm batch statistics are local to the rank (what torch DDP does to the reference), so
+        the running estimates drift apart.  Before a checkpoint / evaluation they are replaced by their mean over ranks
+        (the running mean of rank-local batch means IS the global-batch mean; for the variance the mean of the
+        rank-local unbiased variances, torch SyncBatchNorm's estimate minus the between-rank term)."""
+        if self.world > 1:
+            for bn in (self.G.decoder.deconv[1], self.G.decoder.deconv[4]):
+                for t in (bn.running_mean, bn.running_var):
+                    torch.distributed.all_reduce(t, group=self.pg)
+                    t.div_(self.world)
+
     def epoch_means(self):
         """(D_loss, G_adv, G_emo) accumulated since the last call, one host sync (train_gan.py:254-264 log line).
         Data parallel: every rank's loss is the mean over its shard, so the sums are all-reduced first -- the log line
@@ -279,7 +329,8 @@ class GanTrainer:
         return a[0].item() / nd, a[4].item() / ng, a[5].item() / ng
 
     def state_dict(self):
-        """Checkpoint layout of train_gan.py:269-276."""
+        """Checkpoint layout of train_gan.py:269-276 (collective in data-parallel mode: every rank calls it)."""
+        self.sync_bn_running_stats_()
         return {'G': self.G.state_dict(), 'D': self.D.state_dict(), 'E_num': self.E_num.state_dict(),
                 'opt_G': self.opt_G.state_dict(), 'opt_D': self.opt_D.state_dict(),
                 'rng_counter': self.rng_counter.clone()}

@@ -226,16 +226,19 @@ def main(argv=None):
                     captured = True
             b += critic_iters
         d_loss, g_adv, g_emo = tr.epoch_means()
+        saving = epoch % cfg.get('SAVE_FREQ', 5) == 0
+        ck_state = tr.state_dict() if saving else None        # collective: averages the BatchNorm running stats over ranks
         if rank == 0:
             print(f"Epoch {epoch}/{cfg['EPOCHS']} | D_loss: {d_loss:.4f} | G_adv: {g_adv:.4f} | G_emo: {g_emo:.4f}")
             if writer is not None:
                 writer.add_scalar("Loss/Critic", d_loss, epoch)
                 writer.add_scalar("Loss/Generator_Adv", g_adv, epoch)
                 writer.add_scalar("Loss/Generator_Emo", g_emo, epoch)
-            if epoch % cfg.get('SAVE_FREQ', 5) == 0:
+            if saving:
                 ck = {'epoch': epoch}
-                ck.update(tr.state_dict())
+                ck.update(ck_state)
                 torch.save(ck, os.path.join(cfg['CHECKPOINT_DIR'], f"gan_epoch{epoch:04d}.pth"))
+    tr.sync_bn_running_stats_()
     if rank == 0:
         torch.save({'G': tr.G.state_dict(), 'E_num': tr.E_num.state_dict()},
                    os.path.join(cfg['CHECKPOINT_DIR'], "gan_final.pth"))

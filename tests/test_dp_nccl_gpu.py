@@ -1,0 +1,136 @@
+"""Two-GPU test of the data-parallel CUDA path over NCCL (skips on a one-GPU box).
+
+Each rank runs GanTrainer.critic_step / generator_step on its shard with injected noise / alpha / dropout masks; the
+all-reduced flat gradient must equal the SUM of the gradients a single-GPU trainer computes for the two shards one after
+the other (local-BN semantics: G's BatchNorm sees the shard, as under torch DDP), and the parameters after the fused Adam
+(grad_scale = 1/world) must be identical on both ranks.  Then the captured cycle (two graphs per step with the eager
+all-reduce between them) must reproduce eager data-parallel steps, and the checkpoint's BatchNorm running statistics
+must be the same on every rank.
+"""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _inputs(seed, B, cfg):
+    g = torch.Generator().manual_seed(seed)
+    h = cfg.get('ENCODER_HIDDEN', [256, 128])
+    return dict(real=torch.rand((B, cfg['MAX_NOTES'], 4), generator=g) * 2 - 1,
+                numeric=torch.randn((B, cfg.get('NUMERIC_INPUT_DIM', 6)), generator=g),
+                noise=torch.randn((B, cfg['NOISE_DIM']), generator=g), alpha=torch.rand(B, generator=g),
+                mask1=(torch.rand((B, h[0]), generator=g) < 0.8).float(),
+                mask2=(torch.rand((B, h[1]), generator=g) < 0.8).float(),
+                labels=torch.randint(0, 4, (B,), generator=g))
+
+
+def _worker(rank, world, port, one_graph, out):
+    for p in (ROOT, os.path.join(ROOT, "melo-gan_b200"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import contextlib
+    import io
+    import yaml
+    from melogan.trainer import GanTrainer
+    cfgd = os.path.join(ROOT, "melo-gan_b200", "config")
+    cfg = yaml.safe_load(open(os.path.join(cfgd, "gan_config.yaml")))
+    ed_cfg = yaml.safe_load(open(os.path.join(cfgd, "ed_config.yaml")))
+    cfg["INTEGRATION_MODE"] = "numeric_only" if cfg.get("INTEGRATION_MODE") == "conditioning" else cfg.get("INTEGRATION_MODE")
+    Bl = 8                                   # per-rank shard
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = GanTrainer(cfg, ed_cfg, batch=Bl, precision="fp32", device=dev, process_group=dist.group.WORLD, seed_offset=rank)
+        ref = GanTrainer(cfg, ed_cfg, batch=Bl, precision="fp32", device=dev) if rank == 0 else None
+    res = {}
+    full = _inputs(5, Bl * world, cfg)
+    mine = {k: v[rank * Bl:(rank + 1) * Bl].to(dev) for k, v in full.items()}
+    # ---- critic step ----
+    tr.critic_step(mine["real"], mine["numeric"], noise=mine["noise"], alpha=mine["alpha"], mask1=mine["mask1"], mask2=mine["mask2"])
+    gd = tr.flat_d.grad.clone()
+    if rank == 0:
+        want = torch.zeros_like(gd)
+        for r in range(world):
+            sh = {k: v[r * Bl:(r + 1) * Bl].to(dev) for k, v in full.items()}
+            ref.opt_D.lr, lr0 = 0.0, ref.opt_D.lr           # keep the reference trainer's parameters fixed between the shards
+            ref.critic_step(sh["real"], sh["numeric"], noise=sh["noise"], alpha=sh["alpha"], mask1=sh["mask1"], mask2=sh["mask2"])
+            ref.opt_D.lr = lr0
+            want += ref.flat_d.grad
+        res["critic_grad_err"] = float((gd - want).abs().max() / want.abs().max())
+    # ---- generator step ----
+    tr.generator_step(mine["numeric"], mine["labels"], noise=mine["noise"], mask1=mine["mask1"], mask2=mine["mask2"])
+    gg = tr.flat_g.grad.clone()
+    # parameters identical on every rank after the fused Adam steps
+    for name, flat in (("d", tr.flat_d), ("g", tr.flat_g)):
+        mx, mn = flat.data.clone(), flat.data.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        res[f"param_spread_{name}"] = float((mx - mn).abs().max())
+    mx = gg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    res["g_grad_same_on_ranks"] = float((mx - gg).abs().max())
+    # ---- captured cycle == eager data-parallel cycle ----
+    K = tr.critic_iters
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    reals = torch.rand((K, Bl, cfg['MAX_NOTES'], 4), generator=g, device=dev) * 2 - 1
+    nums = torch.randn((K, Bl, cfg.get('NUMERIC_INPUT_DIM', 6)), generator=g, device=dev)
+    labels = (torch.arange(Bl, device=dev) % 4).to(torch.int64)
+    snap = (tr.flat_d.data.clone(), tr.flat_g.data.clone(), tr.rng_counter.clone(), tr.opt_D.state_dict(), tr.opt_G.state_dict())
+    import copy
+    snap = copy.deepcopy(snap)
+    tr.train_cycle(reals, nums, labels)                  # eager (also the warm-up the capture needs)
+    tr.train_cycle(reals, nums, labels)
+    eager_d, eager_g = tr.flat_d.data.clone(), tr.flat_g.data.clone()
+    tr.flat_d.data.copy_(snap[0]); tr.flat_g.data.copy_(snap[1]); tr.rng_counter.copy_(snap[2])
+    tr.opt_D.load_state_dict(snap[3]); tr.opt_G.load_state_dict(snap[4])
+    tr.engine.weight_cache(True)
+    s_reals, s_nums, s_labels = tr.capture_cycle()
+    s_reals.copy_(reals); s_nums.copy_(nums); s_labels.copy_(labels)
+    tr.replay_cycle(); tr.replay_cycle()
+    torch.cuda.synchronize(dev)
+    res["graph_vs_eager_d"] = float((tr.flat_d.data - eager_d).abs().max() / eager_d.abs().max())
+    res["graph_vs_eager_g"] = float((tr.flat_g.data - eager_g).abs().max() / eager_g.abs().max())
+    ck = tr.state_dict()                                 # collective: BatchNorm running stats averaged over ranks
+    rm = ck["G"]["decoder.deconv.1.running_mean"].clone()
+    mx = rm.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    res["bn_running_mean_spread"] = float((mx - rm).abs().max())
+    if rank == 0:
+        out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(one_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29700 + os.getpid() % 200 + (50 if one_graph else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, one_graph, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not alive, "data-parallel worker hung"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = out.get(timeout=10)
+    print(res)
+    assert res["critic_grad_err"] < 2e-5, res
+    assert res["param_spread_d"] == 0.0 and res["param_spread_g"] == 0.0 and res["g_grad_same_on_ranks"] == 0.0, res
+    assert res["graph_vs_eager_d"] < 2e-3 and res["graph_vs_eager_g"] < 2e-3, res     # fp32 atomics + Adam on near-zero g
+    assert res["bn_running_mean_spread"] == 0.0, res
+    return res
+
+
+@pytest.mark.timeout(600)
+def test_dp_two_gpus_gradients_and_captured_cycle():
+    _run(False)
