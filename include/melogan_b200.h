@@ -284,6 +284,25 @@ int mg_tc_enable(int on);
 int mg_gan_weight_cache(mg_gan* ctx, int on);
 int mg_weight_cache_invalidate(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone forms of the MLP-type inner blocks (fused inside mg_generator_* / mg_emotion_* on the hot path):
+ *   NoiseToLatent.forward          reference src/gan/models.py:20-29
+ *   GeneratorDecoder.pre           reference src/gan/models.py:46-51
+ *   MLPClassifier.forward          reference src/emotion_discriminator/ed_model.py:74-101
+ *   EmotionDiscriminator.forward with input_mode 'latent'   reference ed_model.py:128-136,156-160
+ * are chains of these four float32 operators (nn.Linear, then activation [+ nn.Dropout keep-mask]):
+ *   z  = x W^T + bias                         x (rows, K), W (N, K) row-major as nn.Linear.weight, z (rows, N)
+ *   h  = act(z) * (mask ? mask * scale : 1)   act: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 GELU (erf form); mask 0/1 floats
+ *   dz = dh * act'(z) * (mask ? mask * scale : 1)
+ *   dx = dz W (if dx), dW += dz^T x (if dW; caller zeroes), db += column sums of dz (if db)
+ * ---------------------------------------------------------------------------------------- */
+int mg_linear_forward(const float* x, const float* W, const float* bias, float* z, int rows, int K, int N, void* stream);
+int mg_linear_backward(const float* x, const float* W, const float* dz, float* dx, float* dW, float* db, int rows, int K,
+                       int N, void* stream);
+int mg_act_dropout_forward(const float* z, const float* mask, float scale, int act, float* h, long long n, void* stream);
+int mg_act_dropout_backward(const float* dh, const float* z, const float* mask, float scale, int act, float* dz,
+                            long long n, void* stream);
+
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
 
@@ -332,7 +351,8 @@ typedef struct mg_debug_layer {
 } mg_debug_layer;
 int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
 /* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",
- * "dbg" (ablation bits, -1 = off), "reverse" (-1 = alternate), "no_tma_store", "no_tma_mask", "no_reuse";
+ * "dbg" (ablation bits, -1 = off), "reverse" (-1 = alternate), "no_tma_store", "no_tma_mask", "no_reuse", "no_pair"
+ * (never the CTA-pair cta_group::2 kernel);
  * "reset" restores the product heuristics.  Returns MG_ERR_INVALID for an unknown key. */
 int mg_debug_set(const char* key, int value);
 /* One line describing the last tensor-core launch of this thread (kernel variant, grid, stages, ...); "" if the

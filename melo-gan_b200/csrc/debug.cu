@@ -99,6 +99,8 @@ extern "C" int mg_debug_set(const char* key, int value) {
     if (!strcmp(key, "staging_bufs")) { t.staging_bufs = value; return MG_OK; }
     if (!strcmp(key, "mask_bufs")) { t.mask_bufs = value; return MG_OK; }
     if (!strcmp(key, "no_ws")) { t.no_ws = value; return MG_OK; }
+    if (!strcmp(key, "no_pair")) { t.no_pair = value; return MG_OK; }
+    if (!strcmp(key, "force_pair")) { t.force_pair = value; return MG_OK; }
     if (!strcmp(key, "dbg")) { t.dbg = value; return MG_OK; }
     if (!strcmp(key, "reverse")) { t.reverse = value; return MG_OK; }
     if (!strcmp(key, "no_tma_store")) { t.no_tma_store = value; return MG_OK; }
@@ -117,8 +119,8 @@ extern "C" const char* mg_debug_last_launch(void) {
     else
         snprintf(g_line, sizeof(g_line),
                  "tc_tap rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%d ws=%d stages=%d act=%d mul=%d aux=%d "
-                 "tma_store=%d tma_mask=%d nsb=%d reverse=%d grid=%dx%d tf32=%d flops=%.6e bytes=%.6e",
+                 "tma_store=%d tma_mask=%d nsb=%d reverse=%d grid=%dx%d tf32=%d pair=%d flops=%.6e bytes=%.6e",
                  li.rows, li.N, li.K, li.taps, li.groups, li.halo, li.BN, li.out_bytes, li.ws, li.stages, li.act, li.mul, li.aux,
-                 li.tma_store, li.tma_mask, li.nsb, li.reverse, li.ctas_x, li.slabs, li.tf32, li.flops, li.bytes);
+                 li.tma_store, li.tma_mask, li.nsb, li.reverse, li.ctas_x, li.slabs, li.tf32, li.pair, li.flops, li.bytes);
     return g_line;
 }

@@ -104,6 +104,10 @@ bool ws_enabled() {
     }
     return v == 1;
 }
+bool pair_enabled() {
+    static const bool on = getenv("MELOGAN_DISABLE_PAIR") == nullptr;
+    return on;
+}
 bool mask_tma_enabled() {
     static const bool on = getenv("MELOGAN_DISABLE_TMA_MASK") == nullptr;
     return on;

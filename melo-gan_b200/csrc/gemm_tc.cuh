@@ -122,6 +122,62 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: two CTAs of one cluster (the two SMs of a TPC) run ONE 256-row MMA; each holds its own
+// 128 activation rows and HALF of the weight columns in its shared memory, and its own 128 accumulator lanes in its TMEM ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this kernel's layout) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a pair: data into THIS CTA's shared memory, complete_tx on a barrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {   // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -197,6 +253,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major, uint32_t fmt = 1) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+// the same for a CTA pair: M = 256 (128 rows in each CTA's TMEM), N = the pair's slab width
+__host__ __device__ constexpr uint32_t make_idesc_pair(int N, uint32_t fmt = 1) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -480,7 +540,8 @@ __device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&r
 //   * TMEM hand-back by one mbarrier arrive per WARP right after its tcgen05.ld (no CTA-wide barrier);
 //   * ONE named barrier per tile (staging tile complete -> TMA store); the staging slot is recycled by waiting, before
 //     that barrier, for the bulk store issued one tile earlier (it has had a whole tile of math to drain).
-template <int BN, int kEpi, int CPT, int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool SCL, typename TO, typename TMSK, typename HDR>
+template <int BN, int kEpi, int CPT, int ACT, int MUL, bool AFF, bool AUX, bool GEN, bool SCL, typename TO, typename TMSK, typename HDR,
+          bool PAIR = false>
 __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
                                                  const CUtensorMap* m_map, HDR& H, uint32_t tmem0, int n0, int mtiles,
                                                  unsigned char* staging0, unsigned char* maskbuf) {
@@ -539,7 +600,10 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&H.tmem_empty[acc]);          // this warp's lanes of the accumulator are free again
+        if (lane == 0) {                                         // this warp's lanes of the accumulator are free again
+            if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&H.tmem_empty[acc]), 0));   // the pair's MMA warp lives in CTA 0
+            else mbar_arrive(&H.tmem_empty[acc]);
+        }
         if (!ring2) {                                            // single staging slot: the previous store must have left it
             if (et == 0) bulk_wait_read0();
             asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
@@ -886,6 +950,178 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// weight-stationary persistent tap-GEMM on CTA PAIRS (tcgen05 cta_group::2)
+// ---------------------------------------------------------------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) work on adjacent 128-row tiles with ONE tcgen05.mma of M = 256, N = 128: each
+// CTA streams its own activation tiles, keeps only HALF of the slab's weight columns (64) resident and drains its own 128
+// accumulator lanes.  Against the one-CTA kernel this halves (a) the resident weight bytes per SM -- 256-channel layers whose
+// 128-wide slab did not fit next to a pipeline (K = 3 x 256, 5 x 128, 2 x 256) keep BN = 128, deeper activation rings, double
+// staging and TMA mask tiles -- and (b) the shared-memory operand bytes the tensor core reads per FLOP (A 4 KB + B 2 KB per
+// CTA and 64 clocks instead of A 4 KB + B 4 KB).  Roles as in tc_tapgemm_ws_kernel; differences: only CTA 0's warp 1 issues
+// MMAs; every `full` / `wfull` barrier that gates them lives in CTA 0 and counts the bytes of BOTH CTAs' TMA loads (the
+// peer's loads name CTA 0's barrier, cta_group::2 form); tcgen05.commit multicasts its arrive to the barrier at the same
+// offset in both CTAs (each producer's `empty`, each epilogue's `tmem_full`); both epilogues hand their TMEM lanes back
+// to CTA 0's `tmem_empty`.  Epilogue: the TMA-store staging form only (ws_epilogue_loop, PAIR = true).
+template <typename TO, typename TMSK>
+__global__ void __launch_bounds__(WsCfg<128>::kThreads) tc_tapgemm_ws2_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                            const __grid_constant__ CUtensorMap b_map,
+                                                            const __grid_constant__ CUtensorMap o_map,
+                                                            const __grid_constant__ CUtensorMap x_map,
+                                                            const __grid_constant__ CUtensorMap m_map, const TcTapArgs P,
+                                                            int mtiles, int nstages) {
+    constexpr int BN = 128, BH = 64;                  // the pair's slab width, this CTA's resident half
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    WsHeader<BN>& H = *reinterpret_cast<WsHeader<BN>*>(base);
+    const int nkb = P.ntaps * P.kblocks;
+    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(base + kWsHeaderBytes);             // [nkb][BH][64]
+    unsigned char* asm_ = reinterpret_cast<unsigned char*>(wsm + (size_t)nkb * BH * kTileK);  // [nstages][128 + halo][64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BN;
+    constexpr uint32_t kWBytes = BH * kTileK * 2;
+    const uint32_t a_tx = (uint32_t)(kTileM + P.halo * P.il) * kTileK * 2;
+    const uint32_t a_stage = (a_tx + 1023u) & ~1023u;
+    unsigned char* staging = asm_ + (size_t)nstages * a_stage;
+    unsigned char* maskbuf = staging + (size_t)P.nsb * 128 * BN * sizeof(TO);
+    const int n0 = blockIdx.y * BN;
+    const uint32_t rank = cluster_ctarank();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstages; ++s) { mbar_init(&H.full[s], 1); mbar_init(&H.empty[s], 1); }
+        mbar_init(&H.wfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&H.tmem_full[a], 1);
+            mbar_init(&H.tmem_empty[a], 2u * (uint32_t)(WsCfg<BN>::kEpiThreads / 32));    // every epilogue warp of both CTAs
+        }
+        mbar_init(&H.mask_full[0], 1); mbar_init(&H.mask_full[1], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc_pair(&H.tmem_base, kTmemCols);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&a_map); tma_prefetch_desc(&b_map); }
+    const int npt = P.ngroups * P.kblocks;
+    if (threadIdx.x == 64) {
+        int i = 0;
+        for (int g = 0; g < P.ngroups; ++g)
+            for (int kc = 0; kc < P.kblocks; ++kc) {
+                H.ldtab[g * P.kblocks + kc] = make_int4(kc * P.ktile, P.g_p[g], P.g_dmin[g], 0);
+                for (int j = 0; j < P.g_count[g]; ++j, ++i) {
+                    const int t = P.g_tap[P.g_first[g] + j];
+                    H.mmatab[i] = make_int4((P.a_dm[t] - P.g_dmin[g]) * P.il * 128, (t * P.kblocks + kc) * (int)kWBytes,
+                                            j == P.g_count[g] - 1, 0);
+                }
+            }
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // barriers of BOTH CTAs initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem0 = H.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t wfull0 = mapa_u32(smem_u32(&H.wfull), 0);
+            if (rank == 0) mbar_expect_tx(&H.wfull, 2u * (uint32_t)nkb * kWBytes);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
+                tma_load_2d_pair(&b_map, wfull0, wsm + (size_t)kb * BH * kTileK, kc * P.ktile, P.b_row[t] + n0 + (int)rank * BH);
+            }
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
+                const int row0 = (P.reverse ? mtiles - 1 - tile : tile) * kTileM;
+                const int b0 = row0 >> P.mper_shift, m0 = row0 & (P.Mper - 1);
+                for (int j = 0; j < npt; ++j) {
+                    mbar_wait(&H.empty[s], ph ^ 1);
+                    const int4 L = H.ldtab[j];
+                    if (rank == 0) mbar_expect_tx(&H.full[s], 2u * a_tx);
+                    const uint32_t full0 = mapa_u32(smem_u32(&H.full[s]), 0);
+                    if (P.il > 1) tma_load_4d_pair(&a_map, full0, asm_ + (size_t)s * a_stage, L.x, b0, L.y, m0 + L.z);
+                    else tma_load_4d_pair(&a_map, full0, asm_ + (size_t)s * a_stage, L.x, L.y, m0 + L.z, b0);
+                    if (++s == nstages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_pair(BN);
+            mbar_wait(&H.wfull, 0);
+            int s = 0, tcount = 0;
+            uint32_t ph = 0;
+            const uint64_t dbase = make_smem_desc(0, 16, 1024);
+            const uint32_t a_base = smem_u32(asm_), w_base = smem_u32(wsm);
+            for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                mbar_wait(&H.tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem0 + (uint32_t)(acc * BN);
+                uint32_t started = 0;
+                int i = 0;
+                for (int j = 0; j < npt; ++j) {
+                    mbar_wait(&H.full[s], ph);
+                    tc_fence_after();
+                    const uint32_t stage_addr = a_base + (uint32_t)s * a_stage;
+                    int last;
+                    do {
+                        const int4 M = H.mmatab[i++];
+                        const uint64_t ad = dbase | (uint64_t)(((stage_addr + (uint32_t)M.x) >> 4) & 0x3FFF);
+                        const uint64_t bd = dbase | (uint64_t)(((w_base + (uint32_t)M.y) >> 4) & 0x3FFF);
+                        if (!(P.dbg & 2) && elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < kTileK / 16; ++k) umma_f16_pair(tacc, ad + 2u * k, bd + 2u * k, idesc, k ? 1u : started);
+                        }
+                        started = 1;
+                        last = M.z;
+                    } while (!last);
+                    if (elect_one()) {
+                        umma_commit_pair(&H.empty[s]);
+                        if (j == npt - 1) umma_commit_pair(&H.tmem_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++s == nstages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int et = threadIdx.x - 64;
+        constexpr int kEpi = WsCfg<BN>::kEpiThreads;
+        for (int i = et; i < BN; i += kEpi) {
+            H.bias[i] = P.bias ? __ldg(P.bias + perm_index(n0 + i, P.n_perm_q, P.n_perm_p)) : 0.0f;
+            H.scale[i] = (P.col_scale ? __ldg(P.col_scale + n0 + i) : 1.0f) * P.alpha;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+        const bool scaled = P.col_scale != nullptr || P.alpha != 1.0f;
+        const bool affine = P.bias != nullptr || scaled;
+        int variant = 0;
+        if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;
+        else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
+        else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
+#define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
+    ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK, WsHeader<BN>, true>(   \
+        P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, staging, maskbuf)
+        switch (variant) {
+            case 1: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, true); break;
+            case 2: MG_LOOP(ACT_RELU, MUL_NONE, true, false, false, true); break;
+            case 3: MG_LOOP(ACT_LRELU, MUL_NONE, true, false, false, true); break;
+            case 4: MG_LOOP(ACT_GELU, MUL_NONE, true, true, false, true); break;
+            case 5: MG_LOOP(ACT_NONE, MUL_LRELU_SIGN, false, false, false, true); break;
+            case 6: MG_LOOP(ACT_NONE, MUL_RELU_SIGN, false, false, false, true); break;
+            case 7: MG_LOOP(ACT_NONE, MUL_VALUE, false, false, false, true); break;
+            case 8: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, false); break;
+            case 9: MG_LOOP(ACT_RELU, MUL_NONE, true, false, false, false); break;
+            case 10: MG_LOOP(ACT_LRELU, MUL_NONE, true, false, false, false); break;
+            default: MG_LOOP(ACT_NONE, MUL_NONE, true, true, true, true); break;
+        }
+#undef MG_LOOP
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // nobody leaves while the peer may still signal it or read its operands
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem0, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad
 // ---------------------------------------------------------------------------------------------
 struct TcWgradArgs {
@@ -1096,6 +1332,30 @@ int launch_tc_tap_ws(const CUtensorMap& am, const CUtensorMap& bm, const CUtenso
     return MG_OK;
 }
 
+// CTA-pair form: cluster (2, 1, 1), even grid.x
+template <typename TO, typename TMSK>
+int launch_tc_tap_ws2(const CUtensorMap& am, const CUtensorMap& bm, const CUtensorMap& om, const CUtensorMap& xm,
+                      const CUtensorMap& mm, const TcTapArgs& a, int mtiles, int nstages, int ctas_x, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        MG_CUDA_OK(cudaFuncSetAttribute(tc_tapgemm_ws2_kernel<TO, TMSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas_x, a.N / 128);
+    cfg.blockDim = dim3(WsCfg<128>::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MG_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm_ws2_kernel<TO, TMSK>, am, bm, om, xm, mm, a, mtiles, nstages));
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
 template <int BNK>
 int launch_tc_wgrad(const CUtensorMap& gm, const CUtensorMap& am, const TcWgradArgs& a, int splits, cudaStream_t st) {
     static bool attr_done = false;
@@ -1138,6 +1398,7 @@ inline void build_tap_groups(TcTapArgs& a, int halo_max) {
 }
 
 bool reuse_enabled();        // MELOGAN_DISABLE_TAP_REUSE=1: one activation tile per tap (A/B profiling)
+bool pair_enabled();         // MELOGAN_DISABLE_PAIR=1: never the CTA-pair (cta_group::2) kernel (A/B profiling)
 
 // Kernel-selection overrides for the per-layer harness (mg_debug_set, csrc/debug.cu); all zero = the product heuristics.
 struct Tuning {
@@ -1149,6 +1410,8 @@ struct Tuning {
     int dbg = -1;            // MELOGAN_TC_DEBUG ablation bits (-1 = environment)
     int reverse = -1;        // fixed tile order (-1 = alternate)
     int no_tma_store = 0, no_tma_mask = 0, no_reuse = 0;
+    int no_pair = 0;         // 1 = never the CTA-pair (cta_group::2) kernel
+    int force_pair = 0;      // 1 = CTA pairs also for short tiles (taps x K < 512)
 };
 Tuning& tuning();
 // What the last tensor-core launch on this thread looked like (tests assert that the variant they mean to pin ran).
@@ -1156,7 +1419,7 @@ struct LaunchInfo {
     int kind = 0;            // 0 none, 1 tap-GEMM, 2 wgrad
     long long rows = 0;
     int N = 0, K = 0, taps = 0, groups = 0, halo = 0, BN = 0, out_bytes = 0, ws = 0, stages = 0, act = 0, mul = 0, aux = 0;
-    int tma_store = 0, tma_mask = 0, nsb = 0, reverse = 0, ctas_x = 0, slabs = 0, tf32 = 0, splits = 0;
+    int tma_store = 0, tma_mask = 0, nsb = 0, reverse = 0, ctas_x = 0, slabs = 0, tf32 = 0, splits = 0, pair = 0;
     double flops = 0, bytes = 0;
 };
 LaunchInfo& last_launch();
@@ -1166,7 +1429,7 @@ LaunchInfo& last_launch();
 // am_halo (optional): the same activation view with boxes of 128 + a.halo rows, a.ngroups/g_* describing the tap groups.
 template <typename TO, typename TMSK, bool TF32 = false>
 int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN, int K, cudaStream_t st,
-               const CUtensorMap* am_halo = nullptr) {
+               const CUtensorMap* am_halo = nullptr, const CUtensorMap* bm_half = nullptr) {
     a.ktile = TF32 ? 32 : 64;
     if (!is_pow2(a.Mper) || !is_pow2(a.mpt) || a.mpt * a.bpt != kTileM || (a.Mper > kTileM && a.Mper % kTileM)) {
         set_error("run_tc_tap: Mper=%d mpt=%d bpt=%d is not a power-of-two tiling", a.Mper, a.mpt, a.bpt);
@@ -1183,13 +1446,31 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
                      (double)rows * (K * 2.0 + a.N * sizeof(TO) * (a.aux ? 2.0 : 1.0) +
                                      (a.mul_mode != MUL_NONE ? a.N * (double)sizeof(TMSK) : 0.0)), st);
     const int nslabs = a.N / BN;
-    const size_t wbytes = (size_t)a.ntaps * (K / a.ktile) * BN * 128;
+    const Tuning& tn = tuning();
+    if (!am_halo) build_tap_groups(a, 0);
     const size_t avail = (size_t)227 * 1024 - 1024 - kWsHeaderBytes;
+    const size_t a_stage = (((size_t)(128 + a.halo * a.il) * 128) + 1023) / 1024 * 1024;
+    // tiles can leave through a staging tile + TMA bulk stores: output rows uniformly strided (conv outputs [b][m][n], and
+    // Linears: one row per sample), 16-byte aligned
+    const long long row_stride = a.Mper == 1 ? a.o_bstride : a.o_mstride;
+    const int per_tile = a.aux ? 2 : 1;                            // staging slots one tile needs (result + derivative tile)
+    const size_t staging = (size_t)128 * BN * sizeof(TO) * per_tile;
+    const bool tma_ok = tma_store_enabled() && !tn.no_tma_store && !a.accumulate &&
+                        (a.Mper == 1 || a.o_bstride == (long long)a.Mper * a.o_mstride) && (row_stride * sizeof(TO)) % 16 == 0 &&
+                        ((uintptr_t)((TO*)a.Out + a.o_off)) % 16 == 0 && (!a.aux || sizeof(TO) == 2);
+    // CTA pairs (tc_tapgemm_ws2_kernel): bf16 operands, 128-wide slabs, an even number of tiles, the TMA-store epilogue, each
+    // CTA keeps half of the slab's weights
+    const size_t wbytes_pair = (size_t)a.ntaps * (K / a.ktile) * 64 * 128;
+    // ... and only where a tile carries >= 32 MMAs (taps x K >= 512): measured per layer at the bench shapes, the pair's
+    // cross-CTA hand-offs cost more than they save on the short K = 64 / 128 tiles (critic conv.2 forward 276 -> 477 us)
+    // and win 10-25 % from taps x K = 512 up (critic conv.4 forward 616 -> 469 us)
+    const bool pair = !TF32 && BN == 128 && bm_half && pair_enabled() && !tn.no_pair && (mtiles % 2 == 0) && num_sms() / nslabs >= 2 &&
+                      tma_ok && wbytes_pair + 3 * a_stage + staging <= avail && (a.ntaps * K >= 512 || tn.force_pair);
+    const size_t wbytes = pair ? wbytes_pair : (size_t)a.ntaps * (K / a.ktile) * BN * 128;
     int ctas_x = num_sms() / nslabs;
+    if (pair) ctas_x &= ~1;
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
-    if (!am_halo) build_tap_groups(a, 0);
-    const Tuning& tn = tuning();
     {   // Consecutive layers are 0.4-0.8 GB producer -> consumer hand-offs through a 126 MB L2: the consumer starts where
         // the producer stopped (its last tiles are still resident) if successive launches walk the rows in opposite order.
         static const bool snake = getenv("MELOGAN_NO_SNAKE") == nullptr;
@@ -1198,7 +1479,6 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         if (tn.reverse >= 0) a.reverse = tn.reverse;
     }
     { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = tn.dbg >= 0 ? tn.dbg : dbg; }
-    const size_t a_stage = (((size_t)(128 + a.halo * a.il) * 128) + 1023) / 1024 * 1024;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
     const bool ws = ws_enabled() && !tn.no_ws && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x &&
                     a.ntaps * (K / a.ktile) <= kWsMaxLoads;
@@ -1218,16 +1498,9 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     if (ws) {
         // tiles leave through a staging tile + TMA bulk stores when the output rows are uniformly strided and the staging
         // tile fits next to >= 3 activation stages
-        const int per_tile = a.aux ? 2 : 1;                        // staging slots one tile needs (result + derivative tile)
-        const size_t staging = (size_t)128 * BN * sizeof(TO) * per_tile;
         CUtensorMap om = am, xm = am;
         a.tma_store = 0; a.nsb = per_tile;
-        // output rows uniformly strided: conv outputs [b][m][n], and Linears (one row per sample)
-        const long long row_stride = a.Mper == 1 ? a.o_bstride : a.o_mstride;
-        if (tma_store_enabled() && !tn.no_tma_store && !a.accumulate &&
-            (a.Mper == 1 || a.o_bstride == (long long)a.Mper * a.o_mstride) &&
-            wbytes + 3 * a_stage + staging <= avail && (row_stride * sizeof(TO)) % 16 == 0 &&
-            ((uintptr_t)((TO*)a.Out + a.o_off)) % 16 == 0 && (!a.aux || sizeof(TO) == 2)) {
+        if (tma_ok && wbytes + 3 * a_stage + staging <= avail) {
             int rc = make_out_map(&om, (TO*)a.Out + a.o_off, (int)sizeof(TO), a.N, rows, row_stride);
             if (rc != MG_OK) return rc;
             if (a.aux) {
@@ -1260,9 +1533,10 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
-        li.stages = nstages; li.tma_store = a.tma_store; li.tma_mask = a.tma_mask; li.nsb = a.nsb;
+        li.stages = nstages; li.tma_store = a.tma_store; li.tma_mask = a.tma_mask; li.nsb = a.nsb; li.pair = pair;
         const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage + extra;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
+        if (pair) return launch_tc_tap_ws2<TO, TMSK>(amap, *bm_half, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
                            : launch_tc_tap_ws<64, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
@@ -1338,7 +1612,11 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
         const size_t w128 = (size_t)P.ntaps * (P.K / KT) * 128 * 128;
         const long long mt = ((long long)P.B * P.Mper + 127) / 128;
         static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;
-        if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64))) BN = 64;
+        // ... unless a CTA pair can take the 128-wide slab (half of it per CTA)
+        const bool pair_fits = !TF32 && pair_enabled() && !tuning().no_pair && mt % 2 == 0 && !P.accumulate && tma_store_enabled() &&
+                               (P.ntaps * P.K >= 512 || tuning().force_pair) &&
+                               !tuning().no_tma_store && w128 / 2 + (size_t)128 * 128 * sizeof(TO) * (P.aux ? 2 : 1) <= avail;
+        if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64)) && !pair_fits) BN = 64;
     }
     if (tuning().force_bn == 64 || (tuning().force_bn == 128 && P.N % 128 == 0)) BN = tuning().force_bn;
     int rc = make_act_map(&am, P.A, P.K, P.Mper == 1 ? 1 : LA, P.B, stride, a.mpt, a.bpt, EB);
@@ -1360,7 +1638,14 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
             build_tap_groups(a, 0);
         }
     }
-    rc = run_tc_tap<TO, TMSK, TF32>(am, bm, a, BN, P.K, st, halo_map);
+    CUtensorMap bmh;
+    const CUtensorMap* half_map = nullptr;
+    if (BN == 128 && !TF32 && pair_enabled()) {          // boxes of 64 weight rows: each CTA of a pair keeps half a slab
+        rc = make_weight_map(&bmh, wp, P.K, (long long)P.ntaps * P.N, 64, EB);
+        if (rc != MG_OK) return rc;
+        half_map = &bmh;
+    }
+    rc = run_tc_tap<TO, TMSK, TF32>(am, bm, a, BN, P.K, st, halo_map, half_map);
     return rc == MG_OK ? 1 : rc;
 }
 

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "mg_vae_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_vae_buffer": ([_vp, ctypes.c_char_p, _vp, _vp], _i),
     "mg_vae_loss_step": ([_vp, _vp, _vp, _d, _vp, _vp], _i),
+    "mg_linear_forward": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "mg_linear_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "mg_act_dropout_forward": ([_vp, _vp, _f, _i, _vp, _ll, _vp], _i),
+    "mg_act_dropout_backward": ([_vp, _vp, _vp, _f, _i, _vp, _ll, _vp], _i),
     # per-layer harness (tests/tc_layers.py owns the mg_debug_layer struct)
     "mg_debug_layer_run": ([_vp, _vp], _i),
     "mg_debug_set": ([ctypes.c_char_p, _i], _i),

@@ -1,0 +1,130 @@
+"""Stand-alone forms of the reference's MLP-type inner blocks, as autograd Functions over the C ABI.
+
+On the hot path NoiseToLatent (src/gan/models.py:20-29), GeneratorDecoder.pre (models.py:46-51) and MLPClassifier
+(src/emotion_discriminator/ed_model.py:74-101) run fused inside mg_generator_* / mg_emotion_*.  A caller that invokes the
+inner module directly -- or builds the emotion discriminator with input_mode 'latent' (ed_model.py:128-136), which is the
+MLPClassifier alone -- gets the same arithmetic as a chain of mg_linear_forward / mg_act_dropout_forward launches, float32,
+with a full backward (input, weight and bias gradients).  CUDA tensors only; there is no CPU path.
+"""
+import torch
+import torch.nn as nn
+
+from . import _native
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU = 0, 1, 2, 3
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: CUDA tensors only (the B200 path has no CPU fallback)")
+
+
+class _LinearFn(torch.autograd.Function):
+    """z = x W^T + b"""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _need_cuda(x, "linear")
+        x2 = x.detach().to(torch.float32).reshape(-1, x.shape[-1]).contiguous()
+        Wc = W.detach().to(torch.float32).contiguous()
+        bc = b.detach().to(torch.float32).contiguous() if b is not None else None
+        rows, K, N = x2.shape[0], x2.shape[1], Wc.shape[0]
+        z = torch.empty((rows, N), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _native.call("mg_linear_forward", x2.data_ptr(), Wc.data_ptr(), bc.data_ptr() if bc is not None else None,
+                         z.data_ptr(), rows, K, N, _stream(x))
+        ctx.save_for_backward(x2, Wc)
+        ctx.has_bias, ctx.x_shape = b is not None, x.shape
+        return z.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x2, Wc = ctx.saved_tensors
+        rows, K, N = x2.shape[0], x2.shape[1], Wc.shape[0]
+        dz2 = dz.detach().to(torch.float32).reshape(rows, N).contiguous()
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dW = torch.zeros_like(Wc) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(N, device=x2.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(x2.device):
+            _native.call("mg_linear_backward", x2.data_ptr(), Wc.data_ptr(), dz2.data_ptr(), ptr(dx), ptr(dW), ptr(db),
+                         rows, K, N, _stream(x2))
+        return (dx.reshape(ctx.x_shape) if dx is not None else None), dW, db
+
+
+class _ActDropoutFn(torch.autograd.Function):
+    """h = act(z) * mask * scale   (mask None: no dropout)"""
+
+    @staticmethod
+    def forward(ctx, z, mask, scale, act):
+        _need_cuda(z, "activation")
+        zc = z.detach().to(torch.float32).contiguous()
+        mc = mask.detach().to(torch.float32).contiguous() if mask is not None else None
+        h = torch.empty_like(zc)
+        with torch.cuda.device(z.device):
+            _native.call("mg_act_dropout_forward", zc.data_ptr(), mc.data_ptr() if mc is not None else None, float(scale),
+                         int(act), h.data_ptr(), zc.numel(), _stream(z))
+        ctx.save_for_backward(zc, mc)
+        ctx.scale, ctx.act = float(scale), int(act)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        zc, mc = ctx.saved_tensors
+        dhc = dh.detach().to(torch.float32).contiguous()
+        dz = torch.empty_like(zc)
+        with torch.cuda.device(zc.device):
+            _native.call("mg_act_dropout_backward", dhc.data_ptr(), zc.data_ptr(), mc.data_ptr() if mc is not None else None,
+                         ctx.scale, ctx.act, dz.data_ptr(), zc.numel(), _stream(zc))
+        return dz, None, None, None
+
+
+def linear(x, W, b=None):
+    return _LinearFn.apply(x, W, b)
+
+
+def act_dropout(z, act, mask=None, scale=1.0):
+    return _ActDropoutFn.apply(z, mask, scale, act)
+
+
+_ACT_OF = {nn.ReLU: ACT_RELU, nn.GELU: ACT_GELU, nn.LeakyReLU: ACT_LRELU}
+
+
+def run_mlp(seq, x, training, masks=None):
+    """Runs an nn.Sequential of Linear / ReLU / GELU / LeakyReLU(0.2) / Dropout children (the reference's MLP blocks) on the
+    native operators.  An activation and the nn.Dropout that follows it are ONE launch.  masks: optional list of injected
+    0/1 keep-masks, one per nn.Dropout (tests); default: torch.bernoulli draws, as nn.Dropout would make them."""
+    mods = list(seq)
+    i, drop_i = 0, 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            x = linear(x, m.weight, m.bias)
+            i += 1
+            continue
+        act = ACT_NONE
+        if type(m) in _ACT_OF:
+            if isinstance(m, nn.LeakyReLU) and abs(m.negative_slope - 0.2) > 1e-12:
+                raise NotImplementedError("LeakyReLU slope other than 0.2")
+            if isinstance(m, nn.GELU) and getattr(m, "approximate", "none") != "none":
+                raise NotImplementedError("tanh-approximated GELU")
+            act = _ACT_OF[type(m)]
+            i += 1
+            m = mods[i] if i < len(mods) else None
+        mask, scale = None, 1.0
+        if isinstance(m, nn.Dropout):
+            if training and m.p > 0.0:
+                keep = 1.0 - m.p
+                mask = masks[drop_i] if masks is not None else torch.bernoulli(torch.full_like(x, keep))
+                scale = 1.0 / keep
+            drop_i += 1
+            i += 1
+        elif act == ACT_NONE:
+            raise NotImplementedError(f"no native operator for {type(m).__name__} in a stand-alone MLP block")
+        if act != ACT_NONE or mask is not None:
+            x = act_dropout(x, act, mask, scale)
+    return x

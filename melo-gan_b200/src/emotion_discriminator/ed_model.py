@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from melogan import blocks as B_
 from melogan import engine as E
 from melogan import runtime as R
 
@@ -58,8 +59,10 @@ class MLPClassifier(nn.Module):
         self.net = nn.Sequential(*stack)
         self.head = nn.Linear(width, n_classes)
 
-    def forward(self, x):
-        raise NotImplementedError("MLPClassifier runs fused inside EmotionDiscriminator.forward on the CUDA path")
+    def forward(self, x, masks=None):
+        """Stand-alone call, and the whole model when input_mode is 'latent' (ed_model.py:128-136): Linear -> GELU ->
+        Dropout per hidden layer, then the head, on the native operators of melogan.blocks with full backward."""
+        return B_.linear(B_.run_mlp(self.net, x, self.training, masks), self.head.weight, self.head.bias)
 
 
 class _EmotionFn(torch.autograd.Function):
@@ -152,7 +155,7 @@ class EmotionDiscriminator(nn.Module):
         if self.input_mode == 'latent':
             if x.dim() != 2:
                 raise ValueError(f"Expected latent input shape (B, latent_dim), got {x.shape}")
-            raise NotImplementedError("input_mode 'latent' is off the hot path (ed_config.yaml: input_mode notes)")
+            return self.classifier(x, masks)          # 'latent' mode IS the MLP classifier (ed_model.py:156-160)
         if x.dim() != 3:
             raise ValueError(f"Expected notes input shape (B, T, note_dim), got {x.shape}")
         if self.training:

@@ -10,6 +10,7 @@ mg_discriminator_* entry points, in channels-last layout (the permutes at models
 import torch
 import torch.nn as nn
 
+from melogan import blocks as B_
 from melogan import engine as E
 from melogan import runtime as R
 
@@ -22,8 +23,9 @@ class NoiseToLatent(nn.Module):
         self.net = nn.Sequential(nn.Linear(noise_dim, hidden), nn.ReLU(True), nn.Linear(hidden, out_dim))
 
     def forward(self, z):
-        raise NotImplementedError("NoiseToLatent runs fused inside Generator.forward on the CUDA path; "
-                                  "call the Generator")
+        """Stand-alone call (the Generator runs this block fused): Linear -> ReLU -> Linear on the native operators of
+        melogan.blocks, with full backward."""
+        return B_.run_mlp(self.net, z, self.training)
 
 
 class GeneratorDecoder(nn.Module):
@@ -42,9 +44,14 @@ class GeneratorDecoder(nn.Module):
                                     nn.ConvTranspose1d(128, 64, **up), nn.BatchNorm1d(64), nn.ReLU(True),
                                     nn.ConvTranspose1d(64, out_channels, **up))
 
+    def pre_forward(self, latent):
+        """The Linear stack in front of the transposed convs (models.py:46-51,66-69), stand-alone: (B, latent) ->
+        (B, 256, reduced_len) on the native operators of melogan.blocks."""
+        return B_.run_mlp(self.pre, latent, self.training).view(-1, 256, self.reduced_len)
+
     def forward(self, latent):
-        raise NotImplementedError("GeneratorDecoder runs fused inside Generator.forward on the CUDA path; "
-                                  "call the Generator")
+        raise NotImplementedError("GeneratorDecoder's transposed-conv stack runs fused inside Generator.forward on the "
+                                  "CUDA path (pre_forward gives the Linear stack alone); call the Generator")
 
 
 class _GeneratorFn(torch.autograd.Function):

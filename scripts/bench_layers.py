@@ -18,7 +18,9 @@ for p in (ROOT, os.path.join(ROOT, "melo-gan_b200"), os.path.join(ROOT, "tests")
 import torch  # noqa: E402
 import tc_layers as TL  # noqa: E402
 
-VARIANTS = [("base", {}), ("1 staging tile", {"staging_bufs": 1}), ("1 mask tile", {"mask_bufs": 1}), ("BN=64", {"force_bn": 64}), ("BN=128", {"force_bn": 128}),
+VARIANTS = [("base", {}), ("no pair", {"no_pair": 1}), ("pair", {"force_pair": 1}), ("pair, no stores", {"force_pair": 1, "dbg": 1}),
+            ("pair, no MMA", {"force_pair": 1, "dbg": 2}), ("pair, 3 stages", {"force_pair": 1, "max_stages": 3}),
+            ("pair, 1 staging", {"force_pair": 1, "staging_bufs": 1}), ("1 staging tile", {"staging_bufs": 1}), ("1 mask tile", {"mask_bufs": 1}), ("BN=64", {"force_bn": 64}), ("BN=128", {"force_bn": 128}),
             ("no stores", {"dbg": 1}), ("no MMA", {"dbg": 2}), ("no loads", {"dbg": 4}), ("no MMA, no loads", {"dbg": 6}),
             ("no mask loads", {"dbg": 8})]
 
