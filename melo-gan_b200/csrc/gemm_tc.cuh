@@ -139,8 +139,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
+// Remote arrive with the default (.release.cta) semantics: what is handed over is TMEM, ordered by tcgen05.wait::ld +
+// tcgen05.fence, not generic memory.  The .release.cluster form compiles to MEMBAR.ALL.GPU + CCTL.IVALL (an L1 invalidate)
+// per arrive -- with it every epilogue warp stalled once per tile and the pair kernel lost 1.7x on short tiles.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a pair: data into THIS CTA's shared memory, complete_tx on a barrier of either CTA of the pair
 __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
@@ -1411,7 +1414,6 @@ struct Tuning {
     int reverse = -1;        // fixed tile order (-1 = alternate)
     int no_tma_store = 0, no_tma_mask = 0, no_reuse = 0;
     int no_pair = 0;         // 1 = never the CTA-pair (cta_group::2) kernel
-    int force_pair = 0;      // 1 = CTA pairs also for short tiles (taps x K < 512)
 };
 Tuning& tuning();
 // What the last tensor-core launch on this thread looked like (tests assert that the variant they mean to pin ran).
@@ -1461,11 +1463,10 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     // CTA pairs (tc_tapgemm_ws2_kernel): bf16 operands, 128-wide slabs, an even number of tiles, the TMA-store epilogue, each
     // CTA keeps half of the slab's weights
     const size_t wbytes_pair = (size_t)a.ntaps * (K / a.ktile) * 64 * 128;
-    // ... and only where a tile carries >= 32 MMAs (taps x K >= 512): measured per layer at the bench shapes, the pair's
-    // cross-CTA hand-offs cost more than they save on the short K = 64 / 128 tiles (critic conv.2 forward 276 -> 477 us)
-    // and win 10-25 % from taps x K = 512 up (critic conv.4 forward 616 -> 469 us)
+    // (measured per layer at the bench shapes, gpurun_out/r02o_*: never slower than one CTA per tile row, 5-35 % faster from
+    // taps x K = 192 up -- critic conv.4 forward 616 -> 440 us, ED conv.1 forward 718 -> 490 us, ED conv.3 dgrad 2287 -> 1547 us)
     const bool pair = !TF32 && BN == 128 && bm_half && pair_enabled() && !tn.no_pair && (mtiles % 2 == 0) && num_sms() / nslabs >= 2 &&
-                      tma_ok && wbytes_pair + 3 * a_stage + staging <= avail && (a.ntaps * K >= 512 || tn.force_pair);
+                      tma_ok && wbytes_pair + 3 * a_stage + staging <= avail;
     const size_t wbytes = pair ? wbytes_pair : (size_t)a.ntaps * (K / a.ktile) * BN * 128;
     int ctas_x = num_sms() / nslabs;
     if (pair) ctas_x &= ~1;
@@ -1614,7 +1615,6 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
         static const bool narrow = getenv("MELOGAN_WS_NO_NARROW") == nullptr;
         // ... unless a CTA pair can take the 128-wide slab (half of it per CTA)
         const bool pair_fits = !TF32 && pair_enabled() && !tuning().no_pair && mt % 2 == 0 && !P.accumulate && tma_store_enabled() &&
-                               (P.ntaps * P.K >= 512 || tuning().force_pair) &&
                                !tuning().no_tma_store && w128 / 2 + (size_t)128 * 128 * sizeof(TO) * (P.aux ? 2 : 1) <= avail;
         if (narrow && w128 > avail && w128 / 2 <= avail && mt >= 4LL * (num_sms() / (P.N / 64)) && !pair_fits) BN = 64;
     }

@@ -18,9 +18,7 @@ for p in (ROOT, os.path.join(ROOT, "melo-gan_b200"), os.path.join(ROOT, "tests")
 import torch  # noqa: E402
 import tc_layers as TL  # noqa: E402
 
-VARIANTS = [("base", {}), ("no pair", {"no_pair": 1}), ("pair", {"force_pair": 1}), ("pair, no stores", {"force_pair": 1, "dbg": 1}),
-            ("pair, no MMA", {"force_pair": 1, "dbg": 2}), ("pair, 3 stages", {"force_pair": 1, "max_stages": 3}),
-            ("pair, 1 staging", {"force_pair": 1, "staging_bufs": 1}), ("1 staging tile", {"staging_bufs": 1}), ("1 mask tile", {"mask_bufs": 1}), ("BN=64", {"force_bn": 64}), ("BN=128", {"force_bn": 128}),
+VARIANTS = [("base", {}), ("no pair", {"no_pair": 1}), ("1 staging tile", {"staging_bufs": 1}), ("1 mask tile", {"mask_bufs": 1}), ("BN=64", {"force_bn": 64}), ("BN=128", {"force_bn": 128}),
             ("no stores", {"dbg": 1}), ("no MMA", {"dbg": 2}), ("no loads", {"dbg": 4}), ("no MMA, no loads", {"dbg": 6}),
             ("no mask loads", {"dbg": 8})]
 
@@ -32,6 +30,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--json", default="")
+    ap.add_argument("--knob", action="append", default=[], help="k=v tuning knob (mg_debug_set) applied to every run")
     a = ap.parse_args()
     peaks = {"bf16_tflops_sustained": 1379.6, "hbm_gbs": 6546.6}
     try:
@@ -50,6 +49,8 @@ def main():
             if spec["op"] >= 5 and vname != "base":
                 continue
             TL.debug_set("reset", 0)
+            for kv_ in a.knob:
+                TL.debug_set(kv_.split("=")[0], int(kv_.split("=")[1]))
             for k, v in knobs.items():
                 TL.debug_set(k, v)
 

@@ -71,7 +71,7 @@ def test_layer_matches_float64(spec):
     # one CTA per tile row where the heuristics now take CTA pairs (cta_group::2), and pairs with thin rings
     ("D.conv4.fwd", {"no_pair": 1}), ("ED.conv3.fwd", {"no_pair": 1}), ("D.conv4.dgrad", {"no_pair": 1}),
     ("G.pre2.fwd", {"no_pair": 1}), ("ED.conv2.fwd", {"max_stages": 2}), ("D.conv2.fwd", {"mask_bufs": 1, "staging_bufs": 1}),
-    ("D.conv2.fwd", {"force_pair": 1}), ("ED.conv1.fwd", {"force_pair": 1}), ("D.conv2.adjoint", {"force_pair": 1}),
+    ("D.conv2.fwd", {"no_pair": 1}), ("ED.conv1.fwd", {"no_pair": 1}), ("D.conv2.adjoint", {"no_pair": 1}),
 ])
 def test_kernel_variants_match_float64(name, knobs):
     """The other kernel variants the heuristics can pick at other batch sizes (narrow slabs, single staging tile, one
