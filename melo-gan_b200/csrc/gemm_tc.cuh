@@ -295,8 +295,19 @@ struct TcTapArgs {
     int nmb;                            // TMA mask tiles: ring of nmb (1 or 2) buffers; with 2 the tile after next is in flight
                                         // while this one is drained (a single buffer exposes one L2/HBM latency per tile)
     int reverse;                        // walk the M tiles from the last to the first (see run_tc_tap)
+    int rot_step;                       // weight-stationary kernels: slab y starts its walk y * rot_step tiles further (see ws_row_tile)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
+
+// Row tile a CTA works on at step `tile` of its grid-strided walk: optionally from the last tile to the first (snake
+// order between successive launches), and rotated by rot_step tiles per output slab -- when many slabs stream the SAME
+// activation (decoder.pre.2: 128 slabs over 64 row tiles) a common order has every SM asking the same few L2 slices for the
+// same lines at the same time (measured: 6500 clocks per tile pair against 2048 of MMA); staggered starts spread them.
+__device__ __forceinline__ int ws_row_tile(const TcTapArgs& P, int tile, int mtiles) {
+    int t = P.reverse ? mtiles - 1 - tile : tile;
+    if (P.rot_step) { t += (int)blockIdx.y * P.rot_step; t %= mtiles; }
+    return t;
+}
 
 __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -568,7 +579,7 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
     const int gstep = (int)gridDim.x;
     int sbuf = 0, tcount = 0;
     auto load_mask = [&](int tile, int buf) {        // one thread: the mask tile of `tile` -> ring slot buf
-        const int mrow0 = (P.reverse ? mtiles - 1 - tile : tile) * 128;
+        const int mrow0 = ws_row_tile(P, tile, mtiles) * 128;
         mbar_expect_tx(&H.mask_full[buf], kMaskTile);
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx)
@@ -583,7 +594,7 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < mtiles; tile += gstep, ++tcount) {
         const int acc = tcount & 1;
-        const int row0 = (P.reverse ? mtiles - 1 - tile : tile) * 128;
+        const int row0 = ws_row_tile(P, tile, mtiles) * 128;
         const int bb = (row0 >> P.mper_shift) + rdiv;
         const bool row_ok = bb < P.B;
         uint4 mreg[CPT / 8] = {};
@@ -826,7 +837,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
     const uint32_t tmem0 = H.tmem_base;
 
     auto tile_coords = [&](int tile, int& b0, int& m0) {      // tile -> first sample, first row inside it (powers of two)
-        if (P.reverse) tile = mtiles - 1 - tile;
+        tile = ws_row_tile(P, tile, mtiles);
         const int row0 = tile * kTileM;
         b0 = row0 >> P.mper_shift;
         m0 = row0 & (P.Mper - 1);
@@ -1031,7 +1042,7 @@ __global__ void __launch_bounds__(WsCfg<128>::kThreads) tc_tapgemm_ws2_kernel(co
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
-                const int row0 = (P.reverse ? mtiles - 1 - tile : tile) * kTileM;
+                const int row0 = ws_row_tile(P, tile, mtiles) * kTileM;
                 const int b0 = row0 >> P.mper_shift, m0 = row0 & (P.Mper - 1);
                 for (int j = 0; j < npt; ++j) {
                     mbar_wait(&H.empty[s], ph ^ 1);
@@ -1414,6 +1425,7 @@ struct Tuning {
     int reverse = -1;        // fixed tile order (-1 = alternate)
     int no_tma_store = 0, no_tma_mask = 0, no_reuse = 0;
     int no_pair = 0;         // 1 = never the CTA-pair (cta_group::2) kernel
+    int no_rot = 0;          // 1 = every slab walks the row tiles in the same order
 };
 Tuning& tuning();
 // What the last tensor-core launch on this thread looked like (tests assert that the variant they mean to pin ran).
@@ -1465,11 +1477,13 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
     const size_t wbytes_pair = (size_t)a.ntaps * (K / a.ktile) * 64 * 128;
     // (measured per layer at the bench shapes, gpurun_out/r02o_*: never slower than one CTA per tile row, 5-35 % faster from
     // taps x K = 192 up -- critic conv.4 forward 616 -> 440 us, ED conv.1 forward 718 -> 490 us, ED conv.3 dgrad 2287 -> 1547 us)
-    const bool pair = !TF32 && BN == 128 && bm_half && pair_enabled() && !tn.no_pair && (mtiles % 2 == 0) && num_sms() / nslabs >= 2 &&
-                      tma_ok && wbytes_pair + 3 * a_stage + staging <= avail;
+    // More slabs than SM pairs (decoder.pre.2: 128 slabs, 64 row tiles): one pair per slab, in two waves of clusters -- half
+    // the resident weights buy an 8-deep activation ring where the single CTA had 3 stages and sat on TMA latency.
+    const bool pair = !TF32 && BN == 128 && bm_half && pair_enabled() && !tn.no_pair && (mtiles % 2 == 0) &&
+                      (num_sms() / nslabs >= 2 || mtiles >= 8) && tma_ok && wbytes_pair + 3 * a_stage + staging <= avail;
     const size_t wbytes = pair ? wbytes_pair : (size_t)a.ntaps * (K / a.ktile) * BN * 128;
     int ctas_x = num_sms() / nslabs;
-    if (pair) ctas_x &= ~1;
+    if (pair) ctas_x = ctas_x < 2 ? 2 : (ctas_x & ~1);
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > mtiles) ctas_x = mtiles;
     {   // Consecutive layers are 0.4-0.8 GB producer -> consumer hand-offs through a 126 MB L2: the consumer starts where
@@ -1480,6 +1494,8 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         if (tn.reverse >= 0) a.reverse = tn.reverse;
     }
     { static const int dbg = getenv("MELOGAN_TC_DEBUG") ? atoi(getenv("MELOGAN_TC_DEBUG")) : 0; a.dbg = tn.dbg >= 0 ? tn.dbg : dbg; }
+    // staggered walks when more than two slabs stream the same activation (an even step keeps a pair's tiles adjacent)
+    a.rot_step = (nslabs > 2 && mtiles >= 8 && !tn.no_rot) ? 2 : 0;
     static const bool trace = getenv("MELOGAN_TRACE") != nullptr;
     const bool ws = ws_enabled() && !tn.no_ws && wbytes + 3 * a_stage <= avail && mtiles >= 4 * ctas_x &&
                     a.ntaps * (K / a.ktile) <= kWsMaxLoads;

@@ -18,7 +18,7 @@ for p in (ROOT, os.path.join(ROOT, "melo-gan_b200"), os.path.join(ROOT, "tests")
 import torch  # noqa: E402
 import tc_layers as TL  # noqa: E402
 
-VARIANTS = [("base", {}), ("no pair", {"no_pair": 1}), ("1 staging tile", {"staging_bufs": 1}), ("1 mask tile", {"mask_bufs": 1}), ("BN=64", {"force_bn": 64}), ("BN=128", {"force_bn": 128}),
+VARIANTS = [("base", {}), ("no pair", {"no_pair": 1}), ("no rotation", {"no_rot": 1}), ("1 staging tile", {"staging_bufs": 1}), ("1 mask tile", {"mask_bufs": 1}), ("BN=64", {"force_bn": 64}), ("BN=128", {"force_bn": 128}),
             ("no stores", {"dbg": 1}), ("no MMA", {"dbg": 2}), ("no loads", {"dbg": 4}), ("no MMA, no loads", {"dbg": 6}),
             ("no mask loads", {"dbg": 8})]
 
