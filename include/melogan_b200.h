@@ -348,6 +348,9 @@ typedef struct mg_debug_layer {
     int n_perm_q, n_perm_p;
     const void* in; const void* in2; void* out; void* aux; const void* mul_src;
     const float* W; const float* bias; const float* col_scale; float* dW;
+    /* op 0 only, optional: fused AdaptiveAvgPool1d(1) -- pool_out[r, n] = pool_scale * sum_l out[r, l, n]; *pool_done = 1 if
+     * the kernel that ran produced it (weight-stationary tensor-core kernels), left untouched otherwise */
+    float* pool_out; float pool_scale; int* pool_done;
 } mg_debug_layer;
 int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
 /* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",

@@ -19,7 +19,8 @@ int run_tap(const mg_debug_layer& L, cudaStream_t st) {
     switch (L.op) {
         case 0:
             return conv_fwd<TA, TO, TMSK>(in, out, L.W, L.bias, L.R, L.Lin, L.Cin, L.Cout, L.ks, L.stride, L.pad, L.act,
-                                          L.col_scale, L.aux, L.mul_src, L.mul_mode, st, L.w_nstride, L.w_kstride);
+                                          L.col_scale, L.aux, L.mul_src, L.mul_mode, st, L.w_nstride, L.w_kstride, L.pool_out,
+                                          L.pool_scale, L.pool_done);
         case 1:
             return conv_s1_dgrad<TA, TO, TMSK>(in, out, L.W, L.R, L.Lin, L.Cin, L.Cout, L.ks, L.pad, L.col_scale, L.mul_src,
                                                L.mul_mode, L.accumulate, st);
@@ -119,8 +120,8 @@ extern "C" const char* mg_debug_last_launch(void) {
     else
         snprintf(g_line, sizeof(g_line),
                  "tc_tap rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%d ws=%d stages=%d act=%d mul=%d aux=%d "
-                 "tma_store=%d tma_mask=%d nsb=%d reverse=%d grid=%dx%d tf32=%d pair=%d flops=%.6e bytes=%.6e",
+                 "tma_store=%d tma_mask=%d nsb=%d reverse=%d grid=%dx%d tf32=%d pair=%d pool=%d flops=%.6e bytes=%.6e",
                  li.rows, li.N, li.K, li.taps, li.groups, li.halo, li.BN, li.out_bytes, li.ws, li.stages, li.act, li.mul, li.aux,
-                 li.tma_store, li.tma_mask, li.nsb, li.reverse, li.ctas_x, li.slabs, li.tf32, li.pair, li.flops, li.bytes);
+                 li.tma_store, li.tma_mask, li.nsb, li.reverse, li.ctas_x, li.slabs, li.tf32, li.pair, li.pool, li.flops, li.bytes);
     return g_line;
 }

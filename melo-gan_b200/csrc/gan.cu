@@ -360,9 +360,10 @@ int disc_forward(mg_gan* c, const float* notes, const float* emb, int R, float* 
     }
     MG_TRY((conv_fwd<T, T>((const T*)c->d_h1, (T*)c->d_h2, c->D.c2_w, c->D.c2_b, R, 4 * L0, 64, 128, 5, 2, 2, ACT_LRELU,
                            nullptr, nullptr, nullptr, MUL_NONE, st)));
+    int pooled = 0;       // the weight-stationary tensor-core kernels pool from their staging tile (ws_pool_*)
     MG_TRY((conv_fwd<T, T>((const T*)c->d_h2, (T*)c->d_h3, c->D.c4_w, c->D.c4_b, R, 2 * L0, 128, 256, 5, 2, 2, ACT_LRELU,
-                           nullptr, nullptr, nullptr, MUL_NONE, st)));
-    {
+                           nullptr, nullptr, nullptr, MUL_NONE, st, -1, -1, c->d_pool, 1.0f / (float)L0, &pooled)));
+    if (!pooled) {
         ProbeScope probe(PROBE_ELEM, 0.0, (double)R * L0 * 256 * sizeof(T), st);
         pool_rows_kernel<T, float><<<R, 256, 0, st>>>((const T*)c->d_h3, c->d_pool, R, L0, 256, 1.0f / (float)L0);
         MG_LAUNCH_OK();
@@ -491,11 +492,12 @@ int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const 
     }
     MG_TRY((conv_fwd<T, T>(h1x, h2x, c->D.c2_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE, nullptr, nullptr, h2x,
                            MUL_LRELU_SIGN, st)));
-    MG_TRY((conv_fwd<T, T>(h2x, h3x, c->D.c4_w, nullptr, B, 2 * L0, 128, 256, 5, 2, 2, ACT_NONE, nullptr, nullptr, h3x,
-                           MUL_LRELU_SIGN, st)));
     float* poolx = c->d_pool + (size_t)2 * B * 256;
     float* hfx = c->d_hf + (size_t)2 * B * 256;
-    {
+    int pooled = 0;
+    MG_TRY((conv_fwd<T, T>(h2x, h3x, c->D.c4_w, nullptr, B, 2 * L0, 128, 256, 5, 2, 2, ACT_NONE, nullptr, nullptr, h3x,
+                           MUL_LRELU_SIGN, st, -1, -1, poolx, 1.0f / (float)L0, &pooled)));
+    if (!pooled) {
         ProbeScope probe(PROBE_ELEM, 0.0, (double)B * L0 * 256 * sizeof(T), st);
         pool_rows_kernel<T, float><<<B, 256, 0, st>>>(h3x, poolx, B, L0, 256, 1.0f / (float)L0);
         MG_LAUNCH_OK();
@@ -540,10 +542,12 @@ int ed_forward(mg_gan* c, const float* notes, float* logits_out, cudaStream_t st
                                    c->ed_scale[0], c->ed_g[0], nullptr, MUL_NONE, st)));
     }
     const int ci[4] = {4, 64, 128, 256}, co[4] = {64, 128, 256, 256};
+    int pooled = 0;       // conv.3's epilogue also pools (atomics: a sample spans T4 / 128 tiles)
     for (int i = 1; i < 4; ++i)
         MG_TRY((conv_fwd<T, T>((const T*)c->ed_h[i - 1], (T*)c->ed_h[i], c->ED.conv[i].w, c->ed_shift[i], B, T4, ci[i],
-                               co[i], 3, 1, 1, ACT_GELU, c->ed_scale[i], c->ed_g[i], nullptr, MUL_NONE, st)));
-    {
+                               co[i], 3, 1, 1, ACT_GELU, c->ed_scale[i], c->ed_g[i], nullptr, MUL_NONE, st, -1, -1,
+                               i == 3 ? c->ed_pool : nullptr, 1.0f / (float)T4, i == 3 ? &pooled : nullptr)));
+    if (!pooled) {
         ProbeScope probe(PROBE_ELEM, 0.0, (double)B * T4 * 256 * sizeof(T), st);
         pool_rows_kernel<T, float><<<B, 256, 0, st>>>((const T*)c->ed_h[3], c->ed_pool, B, T4, 256, 1.0f / (float)T4);
         MG_LAUNCH_OK();

@@ -44,6 +44,10 @@ struct TapGemmArgs {
     const float* row_scale;       // optional per-row (b*Mper+m) multiplier applied before everything else
     float alpha;
     int accumulate;               // Out += result (float outputs only)
+    // optional fused AdaptiveAvgPool1d(1): pool_out[b, n] = pool_scale * sum_m Out[b, m, n] (sums of the STORED values).  Only
+    // the weight-stationary tensor-core kernels do it (from their staging tile); *pool_done is set to 1 when they did, else the
+    // caller runs pool_rows_kernel over Out as before.
+    float* pool_out; float pool_scale; int* pool_done;
 };
 
 struct WgradArgs {

@@ -295,6 +295,9 @@ struct TcTapArgs {
     int nmb;                            // TMA mask tiles: ring of nmb (1 or 2) buffers; with 2 the tile after next is in flight
                                         // while this one is drained (a single buffer exposes one L2/HBM latency per tile)
     int reverse;                        // walk the M tiles from the last to the first (see run_tc_tap)
+    float* pool_out; float pool_scale;  // fused mean over the rows of a sample (see ws_pool_*): pool_out[b * N + n]
+    int pool_atomic;                    // a sample spans several tiles (Mper > 128): atomicAdd into a zeroed pool_out
+    int* pool_done;                     // host only
     int rot_step;                       // weight-stationary kernels: slab y starts its walk y * rot_step tiles further (see ws_row_tile)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
@@ -546,6 +549,38 @@ __device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&r
     }
 }
 
+// Fused AdaptiveAvgPool1d(1) of the weight-stationary kernels (bf16 outputs, 128-wide slabs, 1 or 2 samples per tile): the
+// finished staging tile [128 rows][128 columns] is summed column-wise by the 512 epilogue threads -- thread = (column pair,
+// group of 16 rows), conflict-free 4-byte reads of the swizzled rows -- into a double-buffered [8 row groups][128] float
+// buffer; the partials of tile t are combined and written out after the barrier of tile t + 1 (no extra barrier per tile).
+// The sums are sums of the STORED bf16 values, in float32, like pool_rows_kernel's.
+__device__ __forceinline__ void ws_pool_partial(const unsigned char* stage_out, float* poolbuf, int buf, int et) {
+    const int cp = et & 63, rg = et >> 6;
+    const unsigned char* col = stage_out + (cp >> 5) * 16384 + (cp & 3) * 4;
+    const int pidx = (cp & 31) >> 2;
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = rg * 16 + rr;
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(col + r * 128 + ((pidx ^ (r & 7)) << 4));
+        s0 += __uint_as_float(w << 16);
+        s1 += __uint_as_float(w & 0xFFFF0000u);
+    }
+    *reinterpret_cast<float2*>(poolbuf + (buf * 8 + rg) * 128 + 2 * cp) = make_float2(s0, s1);
+}
+__device__ __forceinline__ void ws_pool_flush(const TcTapArgs& P, const float* poolbuf, int buf, int row0, int n0, int et) {
+    const int j = et >> 7, col = et & 127;                    // sample inside the tile, column of the slab
+    if (j >= P.bpt) return;
+    const int per = 8 / P.bpt;                                // row groups per sample
+    float s = 0.0f;
+    for (int g = j * per; g < (j + 1) * per; ++g) s += poolbuf[(buf * 8 + g) * 128 + col];
+    const int b = (row0 >> P.mper_shift) + j;
+    if (b >= P.B) return;
+    float* dst = P.pool_out + (long long)b * P.N + n0 + col;
+    if (P.pool_atomic) atomicAdd(dst, s * P.pool_scale);
+    else *dst = s * P.pool_scale;
+}
+
 // The whole epilogue of the weight-stationary kernel for one compile-time epilogue variant: the tile loop lives INSIDE
 // the variant (ncu, round 2: with the variant switch, three integer divisions for the tile coordinates and two
 // 512-thread barriers per tile the drain executed ~470 instructions per warp and tile of which ~150 were the epilogue
@@ -558,7 +593,7 @@ template <int BN, int kEpi, int CPT, int ACT, int MUL, bool AFF, bool AUX, bool 
           bool PAIR = false>
 __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUtensorMap* o_map, const CUtensorMap* x_map,
                                                  const CUtensorMap* m_map, HDR& H, uint32_t tmem0, int n0, int mtiles,
-                                                 unsigned char* staging0, unsigned char* maskbuf) {
+                                                 unsigned char* staging0, unsigned char* maskbuf, float* poolbuf = nullptr) {
     constexpr int EPB = 128 / (int)sizeof(TO);       // elements per staging box row
     constexpr size_t kStageTile = (size_t)128 * BN * sizeof(TO);
     const int et = threadIdx.x - 64, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -577,7 +612,7 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
     const uint32_t tmem_lane = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)c_begin;
     constexpr uint32_t kMaskTile = (uint32_t)(BN / 64) * 16384u;
     const int gstep = (int)gridDim.x;
-    int sbuf = 0, tcount = 0;
+    int sbuf = 0, tcount = 0, pool_row0 = 0;
     auto load_mask = [&](int tile, int buf) {        // one thread: the mask tile of `tile` -> ring slot buf
         const int mrow0 = ws_row_tile(P, tile, mtiles) * 128;
         mbar_expect_tx(&H.mask_full[buf], kMaskTile);
@@ -647,9 +682,18 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
             // every thread has read this tile's mask: its ring slot takes the tile nmb steps ahead
             if (tma_mask && tile + P.nmb * gstep < mtiles) load_mask(tile + P.nmb * gstep, mbuf);
         }
+        if (BN == 128 && sizeof(TO) == 2 && poolbuf) {           // fused mean over the rows of a sample (ws_pool_*)
+            if (tcount > 0) ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
+            ws_pool_partial(stage_out, poolbuf, tcount & 1, et);
+            pool_row0 = row0;
+        }
         if (++mbuf >= P.nmb) { mbuf = 0; mpar ^= 1u; }
         sbuf += per_tile;
         if (sbuf >= P.nsb) sbuf = 0;
+    }
+    if (BN == 128 && sizeof(TO) == 2 && poolbuf && tcount > 0) { // the last tile's partials
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+        ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
     }
     if (et == 0) bulk_wait0();                                   // all bulk stores complete before the CTA retires
 }
@@ -923,9 +967,10 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;     // 1..3 / 8..10
             else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
             else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
+            float* poolbuf = P.pool_out ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
     ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK>(P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, \
-                                                                             staging, maskbuf)
+                                                                             staging, maskbuf, poolbuf)
             switch (variant) {
                 case 1: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, true); break;
                 case 2: MG_LOOP(ACT_RELU, MUL_NONE, true, false, false, true); break;
@@ -1109,9 +1154,10 @@ __global__ void __launch_bounds__(WsCfg<128>::kThreads) tc_tapgemm_ws2_kernel(co
         if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;
         else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
         else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
+        float* poolbuf = P.pool_out ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
     ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK, WsHeader<BN>, true>(   \
-        P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, staging, maskbuf)
+        P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, staging, maskbuf, poolbuf)
         switch (variant) {
             case 1: MG_LOOP(ACT_NONE, MUL_NONE, true, false, false, true); break;
             case 2: MG_LOOP(ACT_RELU, MUL_NONE, true, false, false, true); break;
@@ -1433,7 +1479,7 @@ struct LaunchInfo {
     int kind = 0;            // 0 none, 1 tap-GEMM, 2 wgrad
     long long rows = 0;
     int N = 0, K = 0, taps = 0, groups = 0, halo = 0, BN = 0, out_bytes = 0, ws = 0, stages = 0, act = 0, mul = 0, aux = 0;
-    int tma_store = 0, tma_mask = 0, nsb = 0, reverse = 0, ctas_x = 0, slabs = 0, tf32 = 0, splits = 0, pair = 0;
+    int tma_store = 0, tma_mask = 0, nsb = 0, reverse = 0, ctas_x = 0, slabs = 0, tf32 = 0, splits = 0, pair = 0, pool = 0;
     double flops = 0, bytes = 0;
 };
 LaunchInfo& last_launch();
@@ -1546,18 +1592,31 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         if (a.tma_mask && tn.mask_bufs != 1 &&
             wbytes + 4 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + 2 * maskbytes <= avail)
             a.nmb = 2;
-        const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes * a.nmb : 0);
+        // fused pooling (ws_pool_*): bf16 staging tile of a 128-wide slab, 1 or 2 samples per tile, 8 KB of partial sums
+        const size_t poolbytes = 2 * 8 * 128 * sizeof(float);
+        const bool pool = a.pool_out && a.tma_store && BN == 128 && sizeof(TO) == 2 && a.bpt <= 2 && !a.accumulate &&
+                          wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
+        if (!pool) a.pool_out = nullptr;
+        a.pool_atomic = a.Mper > 128;
+        const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes * a.nmb : 0) +
+                             (pool ? poolbytes : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
         li.stages = nstages; li.tma_store = a.tma_store; li.tma_mask = a.tma_mask; li.nsb = a.nsb; li.pair = pair;
         const size_t smem = 1024 + kWsHeaderBytes + wbytes + (size_t)nstages * a_stage + extra;
         const CUtensorMap& amap = am_halo ? *am_halo : am;
+        if (pool) {
+            if (a.pool_atomic) MG_CUDA_OK(cudaMemsetAsync(a.pool_out, 0, (size_t)a.B * a.N * sizeof(float), st));
+            if (a.pool_done) *a.pool_done = 1;
+        }
+        li.pool = pool;
         if (pair) return launch_tc_tap_ws2<TO, TMSK>(amap, *bm_half, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
                            : launch_tc_tap_ws<64, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
     a.il = 1; a.il_shift = 0;                            // one tile per CTA: plain boxes, accumulator lane = tile row
+    a.pool_out = nullptr;                                // no fused pooling here: the caller runs pool_rows_kernel
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK, TF32>(am, bm, a, mtiles, st)
                        : launch_tc_tap<64, TO, TMSK, TF32>(am, bm, a, mtiles, st);
 }
@@ -1597,6 +1656,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     a.bias = P.bias; a.col_scale = P.col_scale; a.act = P.act; a.mul_src = P.mul_src; a.mul_mode = P.mul_mode;
     a.aux = P.aux; a.alpha = P.alpha; a.accumulate = P.accumulate;
     a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
+    a.pool_out = P.pool_out; a.pool_scale = P.pool_scale; a.pool_done = P.pool_done;
 
     // pack the weight taps [ntaps][N][K] (bf16, or fp32 for the TF32 path): into the packed-weight cache when the host has
     // promised that weights only change through mg_adam_step (melogan.trainer), else into the next scratch slot

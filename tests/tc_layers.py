@@ -24,7 +24,8 @@ class DebugLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("op", "in_bf16", "out_bf16", "mask_bf16", "tf32", "R", "Lin", "Cin", "Cout", "ks", "stride", "pad", "act",
                  "mul_mode", "accumulate", "w_nstride", "w_kstride", "n_perm_q", "n_perm_p")] + \
-               [(n, ctypes.c_void_p) for n in ("inp", "in2", "out", "aux", "mul_src", "W", "bias", "col_scale", "dW")]
+               [(n, ctypes.c_void_p) for n in ("inp", "in2", "out", "aux", "mul_src", "W", "bias", "col_scale", "dW")] + \
+               [("pool_out", ctypes.c_void_p), ("pool_scale", ctypes.c_float), ("pool_done", ctypes.c_void_p)]
 
 
 def _lib():
@@ -183,7 +184,17 @@ class Layer:
         d.n_perm_q, d.n_perm_p = s["perm"]
         d.inp, d.in2, d.out, d.aux, d.mul_src = p(self.x), p(getattr(self, "x2", None)), p(self.out), p(self.aux), p(self.mask)
         d.W, d.bias, d.col_scale, d.dW = p(getattr(self, "W", None)), p(self.bias), p(self.scale), p(self.dW)
+        if getattr(self, "pool", None) is not None:      # fused AdaptiveAvgPool1d(1) of conv forward layers (op 0)
+            d.pool_out, d.pool_scale = p(self.pool), 1.0 / float(self.oshape[1])
+            d.pool_done = ctypes.c_void_p(self.pool_done.ctypes.data)
         return d
+
+    def enable_pool(self):
+        """Asks the layer (op 0, bf16 out) for the mean over positions as a second output; self.pool_done[0] tells whether
+        the kernel that ran produced it."""
+        import numpy as np
+        self.pool = torch.full((self.oshape[0], self.oshape[2]), float("nan"), device=self.out.device)
+        self.pool_done = np.zeros(1, dtype=np.int32)
 
     def run(self):
         if self.s["inplace_mask"]:

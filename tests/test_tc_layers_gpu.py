@@ -89,3 +89,35 @@ def test_kernel_variants_match_float64(name, knobs):
         print(f"{name:18s} {knobs} rel={rel:.2e} ulp={ulp:.2f}  {info}")
     finally:
         TL.debug_set("reset", 0)
+
+
+@pytest.mark.parametrize("name", ["D.conv4.fwd", "D.conv4.adjoint", "ED.conv3.fwd", "D.conv4.fwd.B"])
+def test_fused_pooling_matches_mean_of_stored_output(name):
+    """The weight-stationary kernels also emit AdaptiveAvgPool1d(1) of the tile they store (ws_pool_*: column sums of the
+    staging tile; complete per tile for the critic's 64-row samples, atomics over the 4 tiles of an ED sample): it must
+    equal the float64 mean of the bf16 values the same launch stored, to float32 summation noise, in both tile orders and on
+    CTA pairs as well as single CTAs."""
+    spec = dict(next(s for s in SPECS if s["name"] == name))
+    for knobs in ({}, {"no_pair": 1}):
+        TL.debug_set("reset", 0)
+        for k, v in knobs.items():
+            TL.debug_set(k, v)
+        try:
+            layer = TL.Layer(spec, seed=13)
+            layer.enable_pool()
+            for reverse in (0, 1):
+                TL.debug_set("reverse", reverse)
+                layer.pool.fill_(float("nan"))
+                layer.pool_done[0] = 0
+                info = layer.run()
+                torch.cuda.synchronize()
+                if knobs and "pool=0" in info:           # a single CTA has no room for conv.4's staging tile / takes 64-wide
+                    assert layer.pool_done[0] == 0, info  # slabs for ED conv.3: no fused pooling, the caller is told so and
+                    continue                              # runs pool_rows_kernel
+                assert "ws=1" in info and "pool=1" in info and layer.pool_done[0] == 1, info
+                want = layer.out.double().mean(dim=1)
+                err = ((layer.pool.double() - want).abs().max() / want.abs().max()).item()
+                assert err < 2e-6, f"{name} {knobs} reverse={reverse}: fused pooling off by {err:.2e} ({info})"
+                _check(layer, info)                      # and the stored tile itself is unchanged
+        finally:
+            TL.debug_set("reset", 0)
