@@ -351,6 +351,9 @@ typedef struct mg_debug_layer {
     /* op 0 only, optional: fused AdaptiveAvgPool1d(1) -- pool_out[r, n] = pool_scale * sum_l out[r, l, n]; *pool_done = 1 if
      * the kernel that ran produced it (weight-stationary tensor-core kernels), left untouched otherwise */
     float* pool_out; float pool_scale; int* pool_done;
+    /* op 2 only, optional: fused column sums (bias gradient of the layer below) -- colsum_out[n] += sum of the stored
+     * out[r, l, n] over the samples r < colsum_samples; *colsum_done = 1 if the kernels that ran produced it */
+    float* colsum_out; int colsum_samples; int* colsum_done;
 } mg_debug_layer;
 int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
 /* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",

@@ -381,7 +381,8 @@ int disc_forward(mg_gan* c, const float* notes, const float* emb, int R, float* 
 
 // dgrad chain for all R rows from per-row seeds; optionally continues to d(notes) for rows [x0, x0+xn)
 template <typename T>
-int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int xn, int accumulate, cudaStream_t st) {
+int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int xn, int accumulate, cudaStream_t st,
+               int Rb_bias = 0) {   // > 0: a disc_wgrad(.., Rb = Rb_bias) follows -- the dgrad epilogues may already sum its bias gradients
     const int L0 = c->L0;
     const size_t per = (size_t)L0 * 256;
     {
@@ -398,10 +399,18 @@ int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int x
         MG_LAUNCH_OK();
     }
     // conv.4 dgrad: k = conv_out 256, n = conv_in 128;  W [256][128][5]
+    // conv.2 / conv.0 bias gradients = column sums of dz2 / dz1 over the first Rb_bias samples: fused into the epilogues that
+    // store those tensors where the weight-stationary kernels run (ws_colsum_*); disc_wgrad reduces them itself otherwise
+    int f2 = 0, f0 = 0;
+    const bool fuse = Rb_bias > 0 && c->gD.c2_b && c->gD.c0_b;
     MG_TRY((upsample2_fwd<T, T>((const T*)c->d_dz3, (T*)c->d_dz2, c->D.c4_w, nullptr, R, L0, 256, 128, 5, 128 * 5,
-                                ACT_NONE, c->d_h2, MUL_LRELU_SIGN, 0, st)));
+                                ACT_NONE, c->d_h2, MUL_LRELU_SIGN, 0, st, fuse ? c->gD.c2_b : nullptr,
+                                (long long)Rb_bias * L0, &f2)));
     MG_TRY((upsample2_fwd<T, T>((const T*)c->d_dz2, (T*)c->d_dz1, c->D.c2_w, nullptr, R, 2 * L0, 128, 64, 5, 64 * 5,
-                                ACT_NONE, c->d_h1, MUL_LRELU_SIGN, 0, st)));
+                                ACT_NONE, c->d_h1, MUL_LRELU_SIGN, 0, st, fuse ? c->gD.c0_b : nullptr,
+                                (long long)Rb_bias * 2 * L0, &f0)));
+    MG_REQUIRE(f2 >= 0 && f0 >= 0, "disc_dgrad: the two sub-pixel phases of a dgrad took different kernels");
+    c->bias_fused_c2 = f2 > 0; c->bias_fused_c0 = f0 > 0;
     if (dnotes && xn > 0) {
         const T* dz1 = (const T*)c->d_dz1 + (size_t)x0 * per;
         if (use_banded<T>(c)) {
@@ -440,15 +449,18 @@ int disc_wgrad(mg_gan* c, const float* x_in, const float* seed, int R, int Rb, c
                                   (long long)Rb * L0, 256, c->gD.c4_b, 0, 0, 0, 1.0f, 1, st)));
     MG_TRY((conv_wgrad<T, T>((const T*)c->d_dz2, (const T*)c->d_h1, c->gD.c2_w, 0, (long long)R * 2 * L0, 4 * L0, 64, 128,
                              5, 2, 2, st)));
-    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz2, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
-                                  (long long)Rb * 2 * L0, 128, c->gD.c2_b, 0, 0, 0, 1.0f, 1, st)));
+    if (!c->bias_fused_c2)
+        MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz2, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                      (long long)Rb * 2 * L0, 128, c->gD.c2_b, 0, 0, 0, 1.0f, 1, st)));
     if (use_banded<T>(c)) {   // d_xp holds the padded bf16 copy of x_in (written by the forward / the adjoint pass)
         MG_TRY(banded::conv_k_wgrad(c->band, BF(c->d_dz1), c->d_xp, R, T4, 2, c->gD.c0_w, 20, 5, 1, st));
     } else {
         MG_TRY((conv_wgrad<T, float>((const T*)c->d_dz1, x_in, c->gD.c0_w, 0, (long long)R * 4 * L0, T4, 4, 64, 5, 2, 2, st)));
     }
-    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz1, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
-                                  (long long)Rb * 4 * L0, 64, c->gD.c0_b, 0, 0, 0, 1.0f, 1, st)));
+    if (!c->bias_fused_c0)
+        MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz1, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                      (long long)Rb * 4 * L0, 64, c->gD.c0_b, 0, 0, 0, 1.0f, 1, st)));
+    c->bias_fused_c2 = c->bias_fused_c0 = false;
     return MG_OK;
 }
 
@@ -469,7 +481,7 @@ int critic_loss_backward(mg_gan* c, const float* real, const float* fake, const 
     critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->d_seed, B, w_real, w_fake);
     MG_LAUNCH_OK();
     // one dgrad chain for all 3B rows; the x_hat rows continue to grad_x
-    MG_TRY((disc_dgrad<T>(c, c->d_seed, 3 * B, c->d_gx, 2 * B, B, 0, st)));
+    MG_TRY((disc_dgrad<T>(c, c->d_seed, 3 * B, c->d_gx, 2 * B, B, 0, st, 2 * B)));
     // penalty and u = dL/d(grad_x), written over the x_hat rows of X3
     float* u = c->d_x3 + (size_t)2 * B * pern;
     gp_norm_kernel<<<B, 256, 0, st>>>(c->d_gx, u, (int)pern, lambda / (float)B, c->d_gp_ps, nullptr);
@@ -955,7 +967,7 @@ template <typename T>
 int disc_backward_api(mg_gan* c, const float* dscore, int param_grads, float* dnotes_out, float* demb_out,
                       const float* notes_in, cudaStream_t st) {
     const int R = c->d_rows, E = c->cfg.embed_dim;
-    MG_TRY((disc_dgrad<T>(c, dscore, R, dnotes_out, 0, dnotes_out ? R : 0, 0, st)));
+    MG_TRY((disc_dgrad<T>(c, dscore, R, dnotes_out, 0, dnotes_out ? R : 0, 0, st, param_grads ? R : 0)));
     if (param_grads) MG_TRY((disc_wgrad<T>(c, notes_in, dscore, R, R, st)));
     if (demb_out && c->d_emb) {
         MG_REQUIRE(R <= c->B, "discriminator_backward: demb_out needs nsamples <= batch");

@@ -13,6 +13,7 @@ struct mg_gan {
     // derived sizes
     int B, T, L0, zin;             // batch, max_notes, max_notes/8, noise+embed
     bool bf16;
+    bool bias_fused_c2 = false, bias_fused_c0 = false;   // disc_dgrad's epilogues already summed these bias gradients
 
     // ---- bound parameters / gradients (caller-owned device memory) ----
     struct EP { float *ln_w, *ln_b, *w1, *b1, *w2, *b2, *w3, *b3; } E{}, gE{};
@@ -163,9 +164,13 @@ int conv_s1_dgrad(const TA* dOut, TO* dIn, const float* W, int R, int L, int Cin
 template <typename TA, typename TO, typename TMSK = TO>
 int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int K, int N,
                   int w_nstride, int w_kstride, int act, const void* mul_src, int mul_mode, int accumulate,
-                  cudaStream_t st) {
+                  cudaStream_t st, float* colsum_out = nullptr, long long colsum_rows = 0, int* colsum_done = nullptr) {
+    // fused column sums of the output (bias gradient of the layer below): both phases add into colsum_out; the caller's
+    // fallback reduction runs unless BOTH phases did it
+    int done[2] = {0, 0};
     for (int ph = 0; ph < 2; ++ph) {
         TapGemmArgs a = tap_defaults();
+        if (colsum_out && (ph == 0 || done[0])) { a.colsum_out = colsum_out; a.colsum_rows = colsum_rows; a.colsum_done = &done[ph]; }
         a.A = in; a.a_bstride = (long long)Lin * K; a.a_mstride = K; a.a_valid = Lin * K; a.K = K;
         a.ntaps = 0;
         for (int t = ph; t < 5; t += 2) {
@@ -180,6 +185,7 @@ int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int 
         int rc = launch_tapgemm<TA, TO, TMSK>(a, st);
         if (rc != MG_OK) return rc;
     }
+    if (colsum_done) *colsum_done = (done[0] && done[1]) ? 1 : (done[0] ? -1 : 0);   // -1: half done (cannot happen: same shape)
     return MG_OK;
 }
 

@@ -298,6 +298,7 @@ struct TcTapArgs {
     float* pool_out; float pool_scale;  // fused mean over the rows of a sample (see ws_pool_*): pool_out[b * N + n]
     int pool_atomic;                    // a sample spans several tiles (Mper > 128): atomicAdd into a zeroed pool_out
     int* pool_done;                     // host only
+    float* colsum_out; int colsum_tiles; int* colsum_done;   // fused column sums over the row tiles < colsum_tiles (bias gradients)
     int rot_step;                       // weight-stationary kernels: slab y starts its walk y * rot_step tiles further (see ws_row_tile)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
@@ -554,19 +555,30 @@ __device__ __forceinline__ void epi_row32(const TcTapArgs& P, const uint32_t (&r
 // group of 16 rows), conflict-free 4-byte reads of the swizzled rows -- into a double-buffered [8 row groups][128] float
 // buffer; the partials of tile t are combined and written out after the barrier of tile t + 1 (no extra barrier per tile).
 // The sums are sums of the STORED bf16 values, in float32, like pool_rows_kernel's.
+template <int BN>
 __device__ __forceinline__ void ws_pool_partial(const unsigned char* stage_out, float* poolbuf, int buf, int et) {
-    const int cp = et & 63, rg = et >> 6;
+    constexpr int CP = BN / 2, RG = 512 / CP, ROWS = 128 / RG;     // column pairs, row groups, rows per group (512 threads)
+    const int cp = et % CP, rg = et / CP;
     const unsigned char* col = stage_out + (cp >> 5) * 16384 + (cp & 3) * 4;
     const int pidx = (cp & 31) >> 2;
     float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-        const int r = rg * 16 + rr;
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const int r = rg * ROWS + rr;
         const uint32_t w = *reinterpret_cast<const uint32_t*>(col + r * 128 + ((pidx ^ (r & 7)) << 4));
         s0 += __uint_as_float(w << 16);
         s1 += __uint_as_float(w & 0xFFFF0000u);
     }
-    *reinterpret_cast<float2*>(poolbuf + (buf * 8 + rg) * 128 + 2 * cp) = make_float2(s0, s1);
+    *reinterpret_cast<float2*>(poolbuf + (buf * RG + rg) * BN + 2 * cp) = make_float2(s0, s1);
+}
+// column sums over ALL rows (bias gradients): each thread et < BN keeps a running sum of its column over this CTA's tiles
+template <int BN>
+__device__ __forceinline__ float ws_colsum_take(const float* poolbuf, int buf, int et) {
+    constexpr int RG = 512 / (BN / 2);
+    float s = 0.0f;
+#pragma unroll
+    for (int g = 0; g < RG; ++g) s += poolbuf[(buf * RG + g) * BN + et];
+    return s;
 }
 __device__ __forceinline__ void ws_pool_flush(const TcTapArgs& P, const float* poolbuf, int buf, int row0, int n0, int et) {
     const int j = et >> 7, col = et & 127;                    // sample inside the tile, column of the slab
@@ -613,6 +625,7 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
     constexpr uint32_t kMaskTile = (uint32_t)(BN / 64) * 16384u;
     const int gstep = (int)gridDim.x;
     int sbuf = 0, tcount = 0, pool_row0 = 0;
+    float colsum_acc = 0.0f;
     auto load_mask = [&](int tile, int buf) {        // one thread: the mask tile of `tile` -> ring slot buf
         const int mrow0 = ws_row_tile(P, tile, mtiles) * 128;
         mbar_expect_tx(&H.mask_full[buf], kMaskTile);
@@ -682,18 +695,28 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
             // every thread has read this tile's mask: its ring slot takes the tile nmb steps ahead
             if (tma_mask && tile + P.nmb * gstep < mtiles) load_mask(tile + P.nmb * gstep, mbuf);
         }
-        if (BN == 128 && sizeof(TO) == 2 && poolbuf) {           // fused mean over the rows of a sample (ws_pool_*)
-            if (tcount > 0) ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
-            ws_pool_partial(stage_out, poolbuf, tcount & 1, et);
-            pool_row0 = row0;
+        if (sizeof(TO) == 2 && poolbuf) {
+            if (BN == 128 && P.pool_out) {                       // fused mean over the rows of a sample (ws_pool_*)
+                if (tcount > 0) ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
+                ws_pool_partial<BN>(stage_out, poolbuf, tcount & 1, et);
+                pool_row0 = row0;
+            } else if (P.colsum_out) {                           // fused column sums over the first colsum_tiles row tiles
+                if (tcount > 0 && pool_row0 && et < BN) colsum_acc += ws_colsum_take<BN>(poolbuf, (tcount - 1) & 1, et);
+                pool_row0 = (row0 >> 7) < P.colsum_tiles;        // (reused as "the previous tile contributed")
+                if (pool_row0) ws_pool_partial<BN>(stage_out, poolbuf, tcount & 1, et);
+            }
         }
         if (++mbuf >= P.nmb) { mbuf = 0; mpar ^= 1u; }
         sbuf += per_tile;
         if (sbuf >= P.nsb) sbuf = 0;
     }
-    if (BN == 128 && sizeof(TO) == 2 && poolbuf && tcount > 0) { // the last tile's partials
+    if (sizeof(TO) == 2 && poolbuf && tcount > 0) {              // the last tile's partials
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-        ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
+        if (BN == 128 && P.pool_out) ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
+        else if (P.colsum_out && et < BN) {
+            if (pool_row0) colsum_acc += ws_colsum_take<BN>(poolbuf, (tcount - 1) & 1, et);
+            atomicAdd(P.colsum_out + n0 + et, colsum_acc);
+        }
     }
     if (et == 0) bulk_wait0();                                   // all bulk stores complete before the CTA retires
 }
@@ -967,7 +990,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;     // 1..3 / 8..10
             else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
             else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
-            float* poolbuf = P.pool_out ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
+            float* poolbuf = (P.pool_out || P.colsum_out) ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
     ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK>(P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, \
                                                                              staging, maskbuf, poolbuf)
@@ -1154,7 +1177,7 @@ __global__ void __launch_bounds__(WsCfg<128>::kThreads) tc_tapgemm_ws2_kernel(co
         if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;
         else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
         else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
-        float* poolbuf = P.pool_out ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
+        float* poolbuf = (P.pool_out || P.colsum_out) ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
     ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK, WsHeader<BN>, true>(   \
         P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, staging, maskbuf, poolbuf)
@@ -1598,8 +1621,12 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
                           wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
         if (!pool) a.pool_out = nullptr;
         a.pool_atomic = a.Mper > 128;
+        // fused column sums (bias gradients): any bf16 staging tile; whole tiles only
+        const bool colsum = a.colsum_out && !pool && a.tma_store && sizeof(TO) == 2 && !a.accumulate && rows % 128 == 0 &&
+                            wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
+        if (!colsum) a.colsum_out = nullptr;
         const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes * a.nmb : 0) +
-                             (pool ? poolbytes : 0);
+                             (pool || colsum ? poolbytes : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
@@ -1610,13 +1637,14 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
             if (a.pool_atomic) MG_CUDA_OK(cudaMemsetAsync(a.pool_out, 0, (size_t)a.B * a.N * sizeof(float), st));
             if (a.pool_done) *a.pool_done = 1;
         }
-        li.pool = pool;
+        if (colsum && a.colsum_done) *a.colsum_done = 1;
+        li.pool = pool ? 1 : (colsum ? 2 : 0);
         if (pair) return launch_tc_tap_ws2<TO, TMSK>(amap, *bm_half, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
                            : launch_tc_tap_ws<64, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
     a.il = 1; a.il_shift = 0;                            // one tile per CTA: plain boxes, accumulator lane = tile row
-    a.pool_out = nullptr;                                // no fused pooling here: the caller runs pool_rows_kernel
+    a.pool_out = nullptr; a.colsum_out = nullptr;        // no fused pooling / column sums here: the caller runs its own kernels
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK, TF32>(am, bm, a, mtiles, st)
                        : launch_tc_tap<64, TO, TMSK, TF32>(am, bm, a, mtiles, st);
 }
@@ -1657,6 +1685,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     a.aux = P.aux; a.alpha = P.alpha; a.accumulate = P.accumulate;
     a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
     a.pool_out = P.pool_out; a.pool_scale = P.pool_scale; a.pool_done = P.pool_done;
+    a.colsum_out = P.colsum_out; a.colsum_tiles = (int)(P.colsum_rows / 128); a.colsum_done = P.colsum_done;
 
     // pack the weight taps [ntaps][N][K] (bf16, or fp32 for the TF32 path): into the packed-weight cache when the host has
     // promised that weights only change through mg_adam_step (melogan.trainer), else into the next scratch slot

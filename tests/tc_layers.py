@@ -25,7 +25,8 @@ class DebugLayer(ctypes.Structure):
                 ("op", "in_bf16", "out_bf16", "mask_bf16", "tf32", "R", "Lin", "Cin", "Cout", "ks", "stride", "pad", "act",
                  "mul_mode", "accumulate", "w_nstride", "w_kstride", "n_perm_q", "n_perm_p")] + \
                [(n, ctypes.c_void_p) for n in ("inp", "in2", "out", "aux", "mul_src", "W", "bias", "col_scale", "dW")] + \
-               [("pool_out", ctypes.c_void_p), ("pool_scale", ctypes.c_float), ("pool_done", ctypes.c_void_p)]
+               [("pool_out", ctypes.c_void_p), ("pool_scale", ctypes.c_float), ("pool_done", ctypes.c_void_p),
+                ("colsum_out", ctypes.c_void_p), ("colsum_samples", ctypes.c_int), ("colsum_done", ctypes.c_void_p)]
 
 
 def _lib():
@@ -187,7 +188,18 @@ class Layer:
         if getattr(self, "pool", None) is not None:      # fused AdaptiveAvgPool1d(1) of conv forward layers (op 0)
             d.pool_out, d.pool_scale = p(self.pool), 1.0 / float(self.oshape[1])
             d.pool_done = ctypes.c_void_p(self.pool_done.ctypes.data)
+        if getattr(self, "colsum", None) is not None:    # fused column sums of up-sampling dgrads (op 2)
+            d.colsum_out, d.colsum_samples = p(self.colsum), int(self.colsum_samples)
+            d.colsum_done = ctypes.c_void_p(self.colsum_done.ctypes.data)
         return d
+
+    def enable_colsum(self, samples):
+        """Asks the layer (op 2, bf16 out) to add the column sums of its output over the first `samples` samples to
+        self.colsum; self.colsum_done[0] tells whether the kernels that ran did."""
+        import numpy as np
+        self.colsum = torch.zeros(self.oshape[2], device=self.out.device)
+        self.colsum_samples = samples
+        self.colsum_done = np.zeros(1, dtype=np.int32)
 
     def enable_pool(self):
         """Asks the layer (op 0, bf16 out) for the mean over positions as a second output; self.pool_done[0] tells whether

@@ -121,3 +121,31 @@ def test_fused_pooling_matches_mean_of_stored_output(name):
                 _check(layer, info)                      # and the stored tile itself is unchanged
         finally:
             TL.debug_set("reset", 0)
+
+
+@pytest.mark.parametrize("name", ["D.conv4.dgrad", "D.conv2.dgrad"])
+def test_fused_bias_gradient_column_sums(name):
+    """The dgrad epilogues also add the column sums of the tensor they store, over the first Rb samples, into the bias
+    gradient of the layer below (ws_colsum_*: per-CTA running sums of the staging tiles, one atomicAdd per column and CTA
+    at the end; the 128-wide pair kernel and the 64-wide single-CTA kernel).  Against the float64 sum of the stored bf16
+    values; accumulates (+=) like the colreduce it replaces."""
+    spec = dict(next(s for s in SPECS if s["name"] == name))
+    TL.debug_set("reset", 0)
+    try:
+        layer = TL.Layer(spec, seed=17)
+        R = spec["R"]
+        Rb = (2 * R) // 3                              # the critic step: real + fake rows of the 3B-row batch
+        layer.enable_colsum(Rb)
+        for reverse in (0, 1):
+            TL.debug_set("reverse", reverse)
+            layer.colsum.fill_(1.5)                    # += semantics
+            layer.colsum_done[0] = 0
+            info = layer.run()
+            torch.cuda.synchronize()
+            assert "ws=1" in info and "pool=2" in info and layer.colsum_done[0] == 1, info
+            want = layer.out[:Rb].double().sum(dim=(0, 1)) + 1.5
+            err = ((layer.colsum.double() - want).abs().max() / want.abs().max()).item()
+            assert err < 5e-6, f"{name} reverse={reverse}: fused column sums off by {err:.2e} ({info})"
+            _check(layer, info)
+    finally:
+        TL.debug_set("reset", 0)
