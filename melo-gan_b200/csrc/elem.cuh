@@ -237,6 +237,33 @@ static __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const TX* __r
                                                             const float* __restrict__ beta) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sizeof(TX) == 4 && sizeof(T) == 2 && (n4 & 1) == 0 && (stride * 8) % C == 0 && C % 8 == 0) {
+        // float32 in, bf16 out: two 16-byte loads and ONE 16-byte store per step (8 channels, constant per thread)
+        const int c = (int)((i0 * 8) % C);
+        float sc[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            sc[e] = invstd[c + e] * gamma[c + e];
+            sh[e] = fmaf(-mean[c + e], sc[e], beta[c + e]);
+        }
+        const long long n8 = n4 >> 1;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        uint4* y4 = reinterpret_cast<uint4*>(y);
+#pragma unroll 4
+        for (long long i = i0; i < n8; i += stride) {
+            const float4 a = __ldcs(x4 + 2 * i), b = __ldcs(x4 + 2 * i + 1);
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(fmaf(v[2 * e], sc[2 * e], sh[2 * e]), 0.0f),
+                                                               fmaxf(fmaf(v[2 * e + 1], sc[2 * e + 1], sh[2 * e + 1]), 0.0f));
+                w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            y4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return;
+    }
     if ((stride * 4) % C == 0) {      // this thread's 4 channels never change: fold the statistics once
         const int c = (int)((i0 * 4) % C);
         float sc[4], sh[4];
@@ -300,6 +327,27 @@ static __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TX* __re
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ sums) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    if ((stride * 4) % C == 0) {      // this thread's 4 channels never change: dx = A*dy + Bx*x + Cc with folded coefficients
+        const int c = (int)((((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4) % C);
+        float A[4], Bx[4], Cc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float is = invstd[c + e], gi = gamma[c + e] * is, s2 = sums[C + c + e] * invR;
+            A[e] = gi;
+            Bx[e] = -gi * is * s2;
+            Cc[e] = -gi * sums[c + e] * invR - Bx[e] * mean[c + e];
+        }
+#pragma unroll 4
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float xv[4], dv[4], o[4];
+            ld4(x + i * 4, xv);
+            ld4(dy + i * 4, dv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = fmaf(A[e], dv[e], fmaf(Bx[e], xv[e], Cc[e]));
+            st4(dx + i * 4, o);
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int c = (int)((i * 4) % C);
         float xv[4], dv[4], o[4];
@@ -362,6 +410,32 @@ static __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __
     const T* r0 = ref + (long long)s * L * C;
     TOUT* o0 = out + (long long)s * L * C;
     const TS* sp = src + (long long)s * C;
+    if (sizeof(T) == 2 && sizeof(TOUT) == 2 && (n4 & 1) == 0 && C % 8 == 0 && (gridDim.x * 2048) % C == 0) {
+        // bf16 in, bf16 out: one 16-byte load and one 16-byte store per step (8 channels, constant per thread)
+        const int c = ((blockIdx.x * 256 + threadIdx.x) * 8) % C;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = ld_as_float(sp + c + e) * (scale * (colscale ? colscale[c + e] : 1.0f));
+        const uint4* r4 = reinterpret_cast<const uint4*>(r0);
+        uint4* o4 = reinterpret_cast<uint4*>(o0);
+        const int n8 = n4 >> 1;
+#pragma unroll 4
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < n8; i += gridDim.x * 256) {
+            const uint4 q = __ldcs(r4 + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float r_lo = __uint_as_float(w[e] << 16), r_hi = __uint_as_float(w[e] & 0xFFFF0000u);
+                const float d_lo = (mode == MUL_LRELU_SIGN) ? (r_lo > 0.f ? 1.f : 0.2f) : (mode == MUL_RELU_SIGN) ? (r_lo > 0.f ? 1.f : 0.f) : r_lo;
+                const float d_hi = (mode == MUL_LRELU_SIGN) ? (r_hi > 0.f ? 1.f : 0.2f) : (mode == MUL_RELU_SIGN) ? (r_hi > 0.f ? 1.f : 0.f) : r_hi;
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e] * d_lo, f[2 * e + 1] * d_hi);
+                o[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     if ((gridDim.x * 1024) % C == 0) {      // this thread's 4 channels never change: fold the row factor once
         const int c = ((blockIdx.x * 256 + threadIdx.x) * 4) % C;
         float f[4];
