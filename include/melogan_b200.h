@@ -354,6 +354,9 @@ typedef struct mg_debug_layer {
     /* op 2 only, optional: fused column sums (bias gradient of the layer below) -- colsum_out[n] += sum of the stored
      * out[r, l, n] over the samples r < colsum_samples; *colsum_done = 1 if the kernels that ran produced it */
     float* colsum_out; int colsum_samples; int* colsum_done;
+    /* op 2 only, optional (float32 out): fused BatchNorm statistics -- stats_out[n] += sum out[., ., n], stats_out[Cout + n] +=
+     * sum out[., ., n]^2 (caller zeroes); *stats_done = 1 if the kernels that ran produced them */
+    float* stats_out; int* stats_done;
 } mg_debug_layer;
 int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
 /* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",

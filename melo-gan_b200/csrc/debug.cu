@@ -27,7 +27,7 @@ int run_tap(const mg_debug_layer& L, cudaStream_t st) {
         case 2:
             return upsample2_fwd<TA, TO, TMSK>(in, out, L.W, L.bias, L.R, L.Lin, L.Cin, L.Cout, L.w_nstride, L.w_kstride, L.act,
                                                L.mul_src, L.mul_mode, L.accumulate, st, L.colsum_out,
-                                               (long long)L.colsum_samples * L.Lin, L.colsum_done);
+                                               (long long)L.colsum_samples * L.Lin, L.colsum_done, L.stats_out, L.stats_done);
         case 3:
             return linear_fwd<TA, TO>(in, out, L.W, L.bias, L.R, L.Cin, L.Cout, L.act, L.aux, st, L.n_perm_q, L.n_perm_p);
         case 4:

@@ -251,15 +251,21 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
     MG_TRY((linear_fwd<T, T>((const T*)c->g_hb, (T*)c->g_y0, c->G.p2_w, c->G.p2_b, B, 512, 256 * L0, ACT_RELU, nullptr, st,
                              256, L0)));
     // deconv.0 -> BN -> ReLU
+    // (train mode: the deconv epilogues also sum x and x^2 per channel for the BatchNorm that follows, ws_stats_*)
+    int s1 = 0, s2 = 0;
+    if (train) MG_CUDA_OK(cudaMemsetAsync(c->g_bn1_stats, 0, 2 * 128 * sizeof(float), st));
     MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y0, c->g_x1, c->G.d0_w, c->G.d0_b, B, L0, 256, 128, 5, 128 * 5,
-                                    ACT_NONE, nullptr, MUL_NONE, 0, st)));
+                                    ACT_NONE, nullptr, MUL_NONE, 0, st, nullptr, 0, nullptr, train ? c->g_bn1_stats : nullptr, &s1)));
+    MG_REQUIRE(s1 >= 0, "gen_forward: the two sub-pixel phases of deconv.0 took different kernels");
     MG_TRY((bn_train_or_eval<T>(c, c->g_x1, (T*)c->g_y1, (long long)B * 2 * L0, 128, c->g_bn1_stats,
-                                c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->G.bn1_b, c->G.bn1_rm, c->G.bn1_rv, train, st)));
+                                c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->G.bn1_b, c->G.bn1_rm, c->G.bn1_rv, train, st, s1 > 0)));
     // deconv.3 -> BN -> ReLU
+    if (train) MG_CUDA_OK(cudaMemsetAsync(c->g_bn2_stats, 0, 2 * 64 * sizeof(float), st));
     MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y1, c->g_x2, c->G.d3_w, c->G.d3_b, B, 2 * L0, 128, 64, 5, 64 * 5,
-                                    ACT_NONE, nullptr, MUL_NONE, 0, st)));
+                                    ACT_NONE, nullptr, MUL_NONE, 0, st, nullptr, 0, nullptr, train ? c->g_bn2_stats : nullptr, &s2)));
+    MG_REQUIRE(s2 >= 0, "gen_forward: the two sub-pixel phases of deconv.3 took different kernels");
     MG_TRY((bn_train_or_eval<T>(c, c->g_x2, (T*)c->g_y2, (long long)B * 4 * L0, 64, c->g_bn2_stats,
-                                c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st)));
+                                c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st, s2 > 0)));
     // deconv.6 -> notes (B, T, 4) float32, already in the reference's permuted (B, notes, 4) order
     float* notes = notes_out ? notes_out : c->g_notes;
     if (use_banded<T>(c)) {

@@ -164,12 +164,14 @@ int conv_s1_dgrad(const TA* dOut, TO* dIn, const float* W, int R, int L, int Cin
 template <typename TA, typename TO, typename TMSK = TO>
 int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int K, int N,
                   int w_nstride, int w_kstride, int act, const void* mul_src, int mul_mode, int accumulate,
-                  cudaStream_t st, float* colsum_out = nullptr, long long colsum_rows = 0, int* colsum_done = nullptr) {
+                  cudaStream_t st, float* colsum_out = nullptr, long long colsum_rows = 0, int* colsum_done = nullptr,
+                  float* stats_out = nullptr, int* stats_done = nullptr) {
     // fused column sums of the output (bias gradient of the layer below): both phases add into colsum_out; the caller's
     // fallback reduction runs unless BOTH phases did it
-    int done[2] = {0, 0};
+    int done[2] = {0, 0}, sdone[2] = {0, 0};
     for (int ph = 0; ph < 2; ++ph) {
         TapGemmArgs a = tap_defaults();
+        if (stats_out && (ph == 0 || sdone[0])) { a.stats_out = stats_out; a.stats_done = &sdone[ph]; }
         if (colsum_out && (ph == 0 || done[0])) { a.colsum_out = colsum_out; a.colsum_rows = colsum_rows; a.colsum_done = &done[ph]; }
         a.A = in; a.a_bstride = (long long)Lin * K; a.a_mstride = K; a.a_valid = Lin * K; a.K = K;
         a.ntaps = 0;
@@ -186,6 +188,7 @@ int upsample2_fwd(const TA* in, TO* out, const float* W, const float* bias, int 
         if (rc != MG_OK) return rc;
     }
     if (colsum_done) *colsum_done = (done[0] && done[1]) ? 1 : (done[0] ? -1 : 0);   // -1: half done (cannot happen: same shape)
+    if (stats_done) *stats_done = (sdone[0] && sdone[1]) ? 1 : (sdone[0] ? -1 : 0);
     return MG_OK;
 }
 
@@ -276,10 +279,12 @@ inline int grid_for(long long n, int threads = 256, int max_per_sm = 8) {
 // ---- BatchNorm1d + ReLU over a float32 pre-activation [rows, C] (train: batch statistics + running update) ----
 template <typename T>
 int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
-                     const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st) {
+                     const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st,
+                     bool stats_ready = false) {   // the producing epilogue already summed x and x^2 into `stats`
     if (train) {
-        MG_TRY((colreduce<float, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
-                                         1.0f, 0, st)));
+        if (!stats_ready)
+            MG_TRY((colreduce<float, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
+                                             1.0f, 0, st)));
         bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows, (float)c->cfg.bn_eps,
                                                             (float)c->cfg.bn_momentum, mean, invstd, rm, rv, 1);
     } else {

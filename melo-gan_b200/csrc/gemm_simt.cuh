@@ -51,6 +51,9 @@ struct TapGemmArgs {
     // optional fused column sums (bias gradients): colsum_out[n] += sum of the STORED Out[b, m, n] over the flattened rows
     // r = b * Mper + m < colsum_rows (a multiple of 128), by atomicAdd; same contract as pool_done for *colsum_done
     float* colsum_out; long long colsum_rows; int* colsum_done;
+    // optional fused BatchNorm batch statistics of a float32 output: stats_out[n] += sum Out[., ., n], stats_out[N + n] += sum
+    // Out[., ., n]^2 over all rows, by atomicAdd into a zeroed [2][N] buffer; same contract for *stats_done
+    float* stats_out; int* stats_done;
 };
 
 struct WgradArgs {

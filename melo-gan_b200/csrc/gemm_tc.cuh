@@ -299,6 +299,7 @@ struct TcTapArgs {
     int pool_atomic;                    // a sample spans several tiles (Mper > 128): atomicAdd into a zeroed pool_out
     int* pool_done;                     // host only
     float* colsum_out; int colsum_tiles; int* colsum_done;   // fused column sums over the row tiles < colsum_tiles (bias gradients)
+    float* stats_out; int* stats_done;  // fused BatchNorm statistics of a float32 output: [sum | sum of squares][N]
     int rot_step;                       // weight-stationary kernels: slab y starts its walk y * rot_step tiles further (see ws_row_tile)
     int dbg;                            // MELOGAN_TC_DEBUG bits (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A loads
 };
@@ -571,6 +572,33 @@ __device__ __forceinline__ void ws_pool_partial(const unsigned char* stage_out, 
     }
     *reinterpret_cast<float2*>(poolbuf + (buf * RG + rg) * BN + 2 * cp) = make_float2(s0, s1);
 }
+// BatchNorm batch statistics of a float32 staging tile [BN / 32 boxes][128 rows][32 floats]: thread = (column, group of rows),
+// sum and sum of squares; partials [buf][row group][2][BN]
+template <int BN>
+__device__ __forceinline__ void ws_stats_partial(const unsigned char* stage_out, float* poolbuf, int buf, int et) {
+    constexpr int RG = 512 / BN, ROWS = 128 / RG;
+    const int col = et % BN, rg = et / BN;
+    const unsigned char* p = stage_out + (col >> 5) * 16384 + (col & 3) * 4;
+    const int pidx = (col & 31) >> 2;
+    float s = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const int r = rg * ROWS + rr;
+        const float v = *reinterpret_cast<const float*>(p + r * 128 + ((pidx ^ (r & 7)) << 4));
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    poolbuf[(buf * RG + rg) * 2 * BN + col] = s;
+    poolbuf[(buf * RG + rg) * 2 * BN + BN + col] = q;
+}
+template <int BN>
+__device__ __forceinline__ float ws_stats_take(const float* poolbuf, int buf, int et) {      // et < 2 * BN: (statistic, column)
+    constexpr int RG = 512 / BN;
+    float s = 0.0f;
+#pragma unroll
+    for (int g = 0; g < RG; ++g) s += poolbuf[(buf * RG + g) * 2 * BN + et];
+    return s;
+}
 // column sums over ALL rows (bias gradients): each thread et < BN keeps a running sum of its column over this CTA's tiles
 template <int BN>
 __device__ __forceinline__ float ws_colsum_take(const float* poolbuf, int buf, int et) {
@@ -626,6 +654,7 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
     const int gstep = (int)gridDim.x;
     int sbuf = 0, tcount = 0, pool_row0 = 0;
     float colsum_acc = 0.0f;
+    double stats_acc = 0.0;
     auto load_mask = [&](int tile, int buf) {        // one thread: the mask tile of `tile` -> ring slot buf
         const int mrow0 = ws_row_tile(P, tile, mtiles) * 128;
         mbar_expect_tx(&H.mask_full[buf], kMaskTile);
@@ -695,6 +724,10 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
             // every thread has read this tile's mask: its ring slot takes the tile nmb steps ahead
             if (tma_mask && tile + P.nmb * gstep < mtiles) load_mask(tile + P.nmb * gstep, mbuf);
         }
+        if (sizeof(TO) == 4 && poolbuf && P.stats_out) {         // fused BatchNorm statistics (float32 staging tile)
+            if (tcount > 0 && et < 2 * BN) stats_acc += (double)ws_stats_take<BN>(poolbuf, (tcount - 1) & 1, et);
+            ws_stats_partial<BN>(stage_out, poolbuf, tcount & 1, et);
+        }
         if (sizeof(TO) == 2 && poolbuf) {
             if (BN == 128 && P.pool_out) {                       // fused mean over the rows of a sample (ws_pool_*)
                 if (tcount > 0) ws_pool_flush(P, poolbuf, (tcount - 1) & 1, pool_row0, n0, et);
@@ -709,6 +742,13 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
         if (++mbuf >= P.nmb) { mbuf = 0; mpar ^= 1u; }
         sbuf += per_tile;
         if (sbuf >= P.nsb) sbuf = 0;
+    }
+    if (sizeof(TO) == 4 && poolbuf && P.stats_out && tcount > 0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+        if (et < 2 * BN) {
+            stats_acc += (double)ws_stats_take<BN>(poolbuf, (tcount - 1) & 1, et);
+            atomicAdd(P.stats_out + (et / BN) * P.N + n0 + (et % BN), (float)stats_acc);
+        }
     }
     if (sizeof(TO) == 2 && poolbuf && tcount > 0) {              // the last tile's partials
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
@@ -990,7 +1030,7 @@ __global__ void __launch_bounds__(WsCfg<BN>::kThreads) tc_tapgemm_ws_kernel(cons
             if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;     // 1..3 / 8..10
             else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
             else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
-            float* poolbuf = (P.pool_out || P.colsum_out) ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
+            float* poolbuf = (P.pool_out || P.colsum_out || P.stats_out) ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
     ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK>(P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, \
                                                                              staging, maskbuf, poolbuf)
@@ -1177,7 +1217,7 @@ __global__ void __launch_bounds__(WsCfg<128>::kThreads) tc_tapgemm_ws2_kernel(co
         if (P.mul_mode == MUL_NONE && !P.aux && P.act != ACT_GELU) variant = (scaled ? 1 : 8) + P.act;
         else if (P.mul_mode == MUL_NONE && P.aux && P.act == ACT_GELU) variant = 4;
         else if (P.act == ACT_NONE && !P.aux && !affine && P.mul_mode != MUL_NONE) variant = 4 + P.mul_mode;
-        float* poolbuf = (P.pool_out || P.colsum_out) ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
+        float* poolbuf = (P.pool_out || P.colsum_out || P.stats_out) ? reinterpret_cast<float*>(maskbuf + (P.tma_mask ? (size_t)P.nmb * (BN / 64) * 16384 : 0)) : nullptr;
 #define MG_LOOP(ACT_, MUL_, AFF_, AUX_, GEN_, SCL_)                                                                  \
     ws_epilogue_loop<BN, kEpi, WsCfg<BN>::kCpt, ACT_, MUL_, AFF_, AUX_, GEN_, SCL_, TO, TMSK, WsHeader<BN>, true>(   \
         P, &o_map, &x_map, &m_map, H, tmem0, n0, mtiles, staging, maskbuf, poolbuf)
@@ -1625,8 +1665,12 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         const bool colsum = a.colsum_out && !pool && a.tma_store && sizeof(TO) == 2 && !a.accumulate && rows % 128 == 0 &&
                             wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
         if (!colsum) a.colsum_out = nullptr;
+        // fused BatchNorm statistics: float32 staging tile, whole tiles only
+        const bool stats = a.stats_out && !pool && !colsum && a.tma_store && sizeof(TO) == 4 && !a.accumulate && rows % 128 == 0 &&
+                           wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
+        if (!stats) a.stats_out = nullptr;
         const size_t extra = (a.tma_store ? (size_t)128 * BN * sizeof(TO) * a.nsb : 0) + (a.tma_mask ? maskbytes * a.nmb : 0) +
-                             (pool || colsum ? poolbytes : 0);
+                             (pool || colsum || stats ? poolbytes : 0);
         int nstages = (int)((avail - wbytes - extra) / a_stage);
         if (nstages > kWsMaxStages) nstages = kWsMaxStages;
         if (tn.max_stages > 0 && nstages > tn.max_stages) nstages = tn.max_stages < 2 ? 2 : tn.max_stages;
@@ -1638,13 +1682,14 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
             if (a.pool_done) *a.pool_done = 1;
         }
         if (colsum && a.colsum_done) *a.colsum_done = 1;
-        li.pool = pool ? 1 : (colsum ? 2 : 0);
+        if (stats && a.stats_done) *a.stats_done = 1;
+        li.pool = pool ? 1 : (colsum ? 2 : (stats ? 3 : 0));
         if (pair) return launch_tc_tap_ws2<TO, TMSK>(amap, *bm_half, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
         return (BN == 128) ? launch_tc_tap_ws<128, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st)
                            : launch_tc_tap_ws<64, TO, TMSK, TF32>(amap, bm, om, xm, mm, a, mtiles, nstages, ctas_x, smem, st);
     }
     a.il = 1; a.il_shift = 0;                            // one tile per CTA: plain boxes, accumulator lane = tile row
-    a.pool_out = nullptr; a.colsum_out = nullptr;        // no fused pooling / column sums here: the caller runs its own kernels
+    a.pool_out = nullptr; a.colsum_out = nullptr; a.stats_out = nullptr;   // nothing fused here: the caller runs its own kernels
     return (BN == 128) ? launch_tc_tap<128, TO, TMSK, TF32>(am, bm, a, mtiles, st)
                        : launch_tc_tap<64, TO, TMSK, TF32>(am, bm, a, mtiles, st);
 }
@@ -1686,6 +1731,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
     a.pool_out = P.pool_out; a.pool_scale = P.pool_scale; a.pool_done = P.pool_done;
     a.colsum_out = P.colsum_out; a.colsum_tiles = (int)(P.colsum_rows / 128); a.colsum_done = P.colsum_done;
+    a.stats_out = P.stats_out; a.stats_done = P.stats_done;
 
     // pack the weight taps [ntaps][N][K] (bf16, or fp32 for the TF32 path): into the packed-weight cache when the host has
     // promised that weights only change through mg_adam_step (melogan.trainer), else into the next scratch slot

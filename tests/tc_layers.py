@@ -26,7 +26,8 @@ class DebugLayer(ctypes.Structure):
                  "mul_mode", "accumulate", "w_nstride", "w_kstride", "n_perm_q", "n_perm_p")] + \
                [(n, ctypes.c_void_p) for n in ("inp", "in2", "out", "aux", "mul_src", "W", "bias", "col_scale", "dW")] + \
                [("pool_out", ctypes.c_void_p), ("pool_scale", ctypes.c_float), ("pool_done", ctypes.c_void_p),
-                ("colsum_out", ctypes.c_void_p), ("colsum_samples", ctypes.c_int), ("colsum_done", ctypes.c_void_p)]
+                ("colsum_out", ctypes.c_void_p), ("colsum_samples", ctypes.c_int), ("colsum_done", ctypes.c_void_p),
+                ("stats_out", ctypes.c_void_p), ("stats_done", ctypes.c_void_p)]
 
 
 def _lib():
@@ -191,7 +192,15 @@ class Layer:
         if getattr(self, "colsum", None) is not None:    # fused column sums of up-sampling dgrads (op 2)
             d.colsum_out, d.colsum_samples = p(self.colsum), int(self.colsum_samples)
             d.colsum_done = ctypes.c_void_p(self.colsum_done.ctypes.data)
+        if getattr(self, "stats", None) is not None:     # fused BatchNorm statistics of up-sampling layers with float32 out
+            d.stats_out = p(self.stats)
+            d.stats_done = ctypes.c_void_p(self.stats_done.ctypes.data)
         return d
+
+    def enable_stats(self):
+        import numpy as np
+        self.stats = torch.zeros(2 * self.oshape[2], device=self.out.device)
+        self.stats_done = np.zeros(1, dtype=np.int32)
 
     def enable_colsum(self, samples):
         """Asks the layer (op 2, bf16 out) to add the column sums of its output over the first `samples` samples to

@@ -149,3 +149,31 @@ def test_fused_bias_gradient_column_sums(name):
             _check(layer, info)
     finally:
         TL.debug_set("reset", 0)
+
+
+@pytest.mark.parametrize("name", ["G.deconv0.fwd", "G.deconv3.fwd"])
+def test_fused_batchnorm_statistics(name):
+    """The generator's transposed-conv epilogues also sum x and x^2 per channel of the float32 tile they store (ws_stats_*)
+    for the train-mode BatchNorm that follows: against float64 sums of the stored values (what colreduce COL_SUM_SQ gave)."""
+    spec = dict(next(s for s in SPECS if s["name"] == name))
+    TL.debug_set("reset", 0)
+    try:
+        layer = TL.Layer(spec, seed=19)
+        layer.enable_stats()
+        for reverse in (0, 1):
+            TL.debug_set("reverse", reverse)
+            layer.stats.zero_()
+            layer.stats_done[0] = 0
+            info = layer.run()
+            torch.cuda.synchronize()
+            assert "ws=1" in info and "pool=3" in info and layer.stats_done[0] == 1, info
+            x = layer.out.double()
+            want = torch.cat([x.sum(dim=(0, 1)), (x * x).sum(dim=(0, 1))])
+            C = x.shape[2]
+            got = layer.stats.double()
+            e1 = ((got[:C] - want[:C]).abs().max() / want[:C].abs().max().clamp_min(1e-30)).item()
+            e2 = ((got[C:] - want[C:]).abs().max() / want[C:].abs().max()).item()
+            assert e2 < 2e-6 and e1 < 1e-4, f"{name} reverse={reverse}: fused statistics off by {e1:.2e} / {e2:.2e} ({info})"
+            _check(layer, info)
+    finally:
+        TL.debug_set("reset", 0)
