@@ -14,7 +14,12 @@
  *   - tensors are contiguous row-major; a "roll" is (T<=512 rows, 4) float32 with
  *     columns (pitch, velocity, duration, step) -- config/gan_config.yaml:43-44;
  *   - every function returns MG_OK (0) or a negative mg_status; nothing falls back
- *     to the CPU: without a usable sm_100 device the calls fail with MG_ERR_CUDA.
+ *     to the CPU: without a usable sm_100 device the calls fail with MG_ERR_CUDA;
+ *   - ONE device and ONE calling thread per process (the deployment model is one process per
+ *     GPU): kernel-selection switches, the packed-weight scratch ring, the launch counter and
+ *     the probe state are process-global; contexts created on different devices of the same
+ *     process, or calls from concurrent host threads, are not supported.  Streams: calls that
+ *     share a context must be issued on one stream (or be ordered by the caller).
  */
 #ifndef MELOGAN_B200_H
 #define MELOGAN_B200_H
