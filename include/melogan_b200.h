@@ -366,7 +366,8 @@ typedef struct mg_debug_layer {
 int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
 /* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",
  * "dbg" (ablation bits, -1 = off), "reverse" (-1 = alternate), "no_tma_store", "no_tma_mask", "no_reuse", "no_pair"
- * (never the CTA-pair cta_group::2 kernel);
+ * (never the CTA-pair cta_group::2 kernel), "no_rot", "no_fuse" (bits: 1 no pooling, 2 no column sums, 4 no BatchNorm statistics in
+ * the epilogues);
  * "reset" restores the product heuristics.  Returns MG_ERR_INVALID for an unknown key. */
 int mg_debug_set(const char* key, int value);
 /* One line describing the last tensor-core launch of this thread (kernel variant, grid, stages, ...); "" if the

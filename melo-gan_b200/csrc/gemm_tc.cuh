@@ -1535,6 +1535,8 @@ struct Tuning {
     int no_tma_store = 0, no_tma_mask = 0, no_reuse = 0;
     int no_pair = 0;         // 1 = never the CTA-pair (cta_group::2) kernel
     int no_rot = 0;          // 1 = every slab walks the row tiles in the same order
+    int no_fuse = 0;         // bits: 1 = no pooling, 2 = no column sums, 4 = no BatchNorm statistics in the epilogues (the callers
+                             // then run their own passes)
 };
 Tuning& tuning();
 // What the last tensor-core launch on this thread looked like (tests assert that the variant they mean to pin ran).
@@ -1657,6 +1659,9 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
             a.nmb = 2;
         // fused pooling (ws_pool_*): bf16 staging tile of a 128-wide slab, 1 or 2 samples per tile, 8 KB of partial sums
         const size_t poolbytes = 2 * 8 * 128 * sizeof(float);
+        if (tn.no_fuse & 1) a.pool_out = nullptr;
+        if (tn.no_fuse & 2) a.colsum_out = nullptr;
+        if (tn.no_fuse & 4) a.stats_out = nullptr;
         const bool pool = a.pool_out && a.tma_store && BN == 128 && sizeof(TO) == 2 && a.bpt <= 2 && !a.accumulate &&
                           wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
         if (!pool) a.pool_out = nullptr;
