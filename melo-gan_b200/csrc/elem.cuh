@@ -470,6 +470,60 @@ static __global__ void __launch_bounds__(256) bcast_rows_mul_kernel(const TS* __
     }
 }
 
+// The same for bf16 tensors as a persistent kernel: a CTA walks whole samples (grid-strided), 16-byte loads and stores, the
+// thread's 8 channels and their row factors fixed per sample (2048 % C == 0).  Optionally adds the column sums of the STORED
+// values over the samples s < colsum_samples to colsum_out (the bias gradient of the layer whose output gradient this is):
+// per-thread running sums, one shared-memory pass and one atomicAdd per channel and CTA at the end.
+// (stand-alone at the critic's shape, scripts/probes/elem_probe.cu: 317 us for the (chunks, samples) grid above, 295 us here)
+template <typename TS>
+static __global__ void __launch_bounds__(256) bcast_rows_mul_bf16_kernel(const TS* __restrict__ src, const __nv_bfloat16* __restrict__ ref,
+                                                                   __nv_bfloat16* __restrict__ out, int S, int L, int C, float scale,
+                                                                   const float* __restrict__ colscale, int mode,
+                                                                   float* __restrict__ colsum_out, int colsum_samples) {
+    __shared__ float red[256][8 + 1];
+    const int per8 = L * C / 8;
+    const int c = (threadIdx.x * 8) % C;
+    float cs[8], acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { cs[e] = scale * (colscale ? colscale[c + e] : 1.0f); acc[e] = 0.0f; }
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(ref + (long long)s * L * C);
+        uint4* o4 = reinterpret_cast<uint4*>(out + (long long)s * L * C);
+        const bool summed = colsum_out != nullptr && s < colsum_samples;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = ld_as_float(src + (long long)s * C + c + e) * cs[e];
+#pragma unroll 4
+        for (int i = threadIdx.x; i < per8; i += 256) {
+            const uint4 q = __ldcs(r4 + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
+                const float dl = (mode == MUL_LRELU_SIGN) ? (lo > 0.f ? 1.f : 0.2f) : (mode == MUL_RELU_SIGN) ? (lo > 0.f ? 1.f : 0.f) : lo;
+                const float dh = (mode == MUL_LRELU_SIGN) ? (hi > 0.f ? 1.f : 0.2f) : (mode == MUL_RELU_SIGN) ? (hi > 0.f ? 1.f : 0.f) : hi;
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e] * dl, f[2 * e + 1] * dh);
+                o[e] = *reinterpret_cast<const uint32_t*>(&h);
+                if (summed) { acc[2 * e] += __low2float(h); acc[2 * e + 1] += __high2float(h); }
+            }
+            o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (colsum_out) {                             // threads t and t + C/8 (mod 256) hold the same channels
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+        __syncthreads();
+        const int groups = C / 8;                 // distinct channel groups among the 256 threads
+        for (int i = threadIdx.x; i < C; i += 256) {
+            const int g = i >> 3, e = i & 7;
+            float t = 0.0f;
+            for (int j = g; j < 256; j += groups) t += red[j][e];
+            atomicAdd(colsum_out + i, t);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FeatureEncoder pieces (tiny tensors, float only)          reference feature_encoder.py:17-41
 // ---------------------------------------------------------------------------------------------

@@ -400,8 +400,16 @@ int disc_dgrad(mg_gan* c, const float* seed, int R, float* dnotes, int x0, int x
     {
         const int chunks = (int)((per / 4 + 1023) / 1024);
         ProbeScope probe(PROBE_ELEM, 0.0, (double)R * per * 2 * sizeof(T), st);
-        bcast_rows_mul_kernel<float, T><<<dim3(chunks, R), 256, 0, st>>>(c->d_dp, (const T*)c->d_h3, (T*)c->d_dz3, L0, 256,
-                                                                        1.0f / (float)L0, nullptr, MUL_LRELU_SIGN);
+        if (sizeof(T) == 2) {   // persistent bf16 form; with a disc_wgrad to follow it also sums conv.4's bias gradient
+            const bool fuse4 = Rb_bias > 0 && c->gD.c4_b != nullptr;
+            bcast_rows_mul_bf16_kernel<float><<<grid_for((long long)R * 256, 256, 16), 256, 0, st>>>(
+                c->d_dp, (const __nv_bfloat16*)c->d_h3, (__nv_bfloat16*)c->d_dz3, R, L0, 256, 1.0f / (float)L0, nullptr,
+                MUL_LRELU_SIGN, fuse4 ? c->gD.c4_b : nullptr, Rb_bias);
+            c->bias_fused_c4 = fuse4;
+        } else {
+            bcast_rows_mul_kernel<float, T><<<dim3(chunks, R), 256, 0, st>>>(c->d_dp, (const T*)c->d_h3, (T*)c->d_dz3, L0, 256,
+                                                                            1.0f / (float)L0, nullptr, MUL_LRELU_SIGN);
+        }
         MG_LAUNCH_OK();
     }
     // conv.4 dgrad: k = conv_out 256, n = conv_in 128;  W [256][128][5]
@@ -451,8 +459,9 @@ int disc_wgrad(mg_gan* c, const float* x_in, const float* seed, int R, int Rb, c
     // conv.4 / conv.2 / conv.0
     MG_TRY((conv_wgrad<T, T>((const T*)c->d_dz3, (const T*)c->d_h2, c->gD.c4_w, 0, (long long)R * L0, 2 * L0, 128, 256, 5,
                              2, 2, st)));
-    MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz3, 256, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
-                                  (long long)Rb * L0, 256, c->gD.c4_b, 0, 0, 0, 1.0f, 1, st)));
+    if (!c->bias_fused_c4)
+        MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz3, 256, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
+                                      (long long)Rb * L0, 256, c->gD.c4_b, 0, 0, 0, 1.0f, 1, st)));
     MG_TRY((conv_wgrad<T, T>((const T*)c->d_dz2, (const T*)c->d_h1, c->gD.c2_w, 0, (long long)R * 2 * L0, 4 * L0, 64, 128,
                              5, 2, 2, st)));
     if (!c->bias_fused_c2)
@@ -466,7 +475,7 @@ int disc_wgrad(mg_gan* c, const float* x_in, const float* seed, int R, int Rb, c
     if (!c->bias_fused_c0)
         MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->d_dz1, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
                                       (long long)Rb * 4 * L0, 64, c->gD.c0_b, 0, 0, 0, 1.0f, 1, st)));
-    c->bias_fused_c2 = c->bias_fused_c0 = false;
+    c->bias_fused_c2 = c->bias_fused_c0 = c->bias_fused_c4 = false;
     return MG_OK;
 }
 
@@ -590,8 +599,13 @@ int ed_backward_input(mg_gan* c, const float* dlogits, float* dnotes, int accumu
     {
         const int chunks = (T4 * 256 / 4 + 1023) / 1024;
         ProbeScope probe(PROBE_ELEM, 0.0, (double)B * T4 * 256 * 2 * sizeof(T), st);
-        bcast_rows_mul_kernel<float, T><<<dim3(chunks, B), 256, 0, st>>>(c->ed_d256a, (const T*)c->ed_g[3], (T*)c->ed_dzA, T4,
-                                                                        256, 1.0f / (float)T4, c->ed_scale[3], MUL_VALUE);
+        if (sizeof(T) == 2)
+            bcast_rows_mul_bf16_kernel<float><<<grid_for((long long)B * 256, 256, 16), 256, 0, st>>>(
+                c->ed_d256a, (const __nv_bfloat16*)c->ed_g[3], (__nv_bfloat16*)c->ed_dzA, B, T4, 256, 1.0f / (float)T4,
+                c->ed_scale[3], MUL_VALUE, nullptr, 0);
+        else
+            bcast_rows_mul_kernel<float, T><<<dim3(chunks, B), 256, 0, st>>>(c->ed_d256a, (const T*)c->ed_g[3], (T*)c->ed_dzA, T4,
+                                                                            256, 1.0f / (float)T4, c->ed_scale[3], MUL_VALUE);
         MG_LAUNCH_OK();
     }
     // conv3 dgrad -> dz of conv2 output (x gelu' x scale2), etc.

@@ -13,7 +13,7 @@ struct mg_gan {
     // derived sizes
     int B, T, L0, zin;             // batch, max_notes, max_notes/8, noise+embed
     bool bf16;
-    bool bias_fused_c2 = false, bias_fused_c0 = false;   // disc_dgrad's epilogues already summed these bias gradients
+    bool bias_fused_c2 = false, bias_fused_c0 = false, bias_fused_c4 = false;   // disc_dgrad already summed these bias gradients
 
     // ---- bound parameters / gradients (caller-owned device memory) ----
     struct EP { float *ln_w, *ln_b, *w1, *b1, *w2, *b2, *w3, *b3; } E{}, gE{};

@@ -26,6 +26,12 @@ def _run(no_fuse):
         cb = cuda_batch(batch)
         md = eng.critic_step(cb["notes_real"], cb["numeric"], cb["noise_d"], cb["alpha"], cb["mask1_d"], cb["mask2_d"]).clone()
         gD = {k: v.clone() for k, v in grads["D"].items()}
+        # the three conv bias gradients are column sums of the stored dz tensors over the real + fake rows (first 2B samples)
+        for key, buf, C in (("conv.4.bias", "d.dz3", 256), ("conv.2.bias", "d.dz2", 128), ("conv.0.bias", "d.dz1", 64)):
+            dz = eng.buffer(buf, torch.bfloat16).view(3 * B, -1, C)[:2 * B].double()
+            want = dz.sum(dim=(0, 1))
+            err = ((gD[key].double() - want).abs().max() / want.abs().max()).item()
+            assert err < 1e-4, f"{key}: bias gradient vs column sums of {buf}: {err:.2e} (no_fuse={no_fuse})"
         mg = eng.generator_step(cb["numeric"], cb["noise_g"], cb["emot_idx"], cb["mask1_g"], cb["mask2_g"]).clone()
         gG = {k: v.clone() for k, v in grads["G"].items()}
         gE = {k: v.clone() for k, v in grads["E"].items()}
