@@ -480,6 +480,16 @@ def main():
     eager_cycle = lambda: tr.train_cycle(reals[0], numerics[0], labels)
     pr = probe_family(L, family, eager_cycle)
     probe_launches, probe_ms, probe_flops, probe_bytes = pr["launches"], pr["ms"], pr["flops"], pr["bytes"]
+    # the same family with the epilogue reductions (pooling, bias-gradient sums, BatchNorm statistics) switched off, i.e. the
+    # contractions alone as in round 1 (the 35 separate passes then run in the element-wise family instead)
+    pr_plain = None
+    if family == 3:
+        try:
+            L.mg_debug_set(b"no_fuse", 7)
+            eager_cycle()
+            pr_plain = probe_family(L, family, eager_cycle)
+        finally:
+            L.mg_debug_set(b"no_fuse", 0)
     if family == 3 and probe_launches == 0:      # bf16 mode without tensor-core kernels yet
         family = 1
     peaks = {}
@@ -564,6 +574,16 @@ def main():
                      "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peak_src,
                      "traffic_note": traffic_note,
                      "launches_per_step": probe_launches, "kernel_ms_per_step": probe_ms,
+                     "flops_note": "algorithmic FLOPs per launch (2 x rows x N x taps x K); the banded 4-channel layers count their "
+                                   "zero-padded K = 64 windows (20 useful taps x channels), about 1 % of the family total",
+                     "fused_reductions_note": "these launches also do the pooling, bias-gradient and BatchNorm-statistics reductions "
+                                              "of 35 former element-wise passes in their epilogues: kernel_ms includes that work, "
+                                              "the FLOP count does not",
+                     "contractions_only": ({"kernel_ms_per_step": pr_plain["ms"],
+                                            "achieved": pr_plain["flops"] / (pr_plain["ms"] * 1e-3) / 1e12,
+                                            "frac": pr_plain["flops"] / (pr_plain["ms"] * 1e-3) / 1e12 / peak_tf,
+                                            "what": "same launches with mg_debug_set('no_fuse', 7): reductions back in separate passes"}
+                                           if pr_plain and pr_plain["ms"] > 0 else None),
                      "share_of_step": probe_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
                      "hbm_view": {"achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s",
                                   "frac": achieved_gbs / peak_gbs if peak_gbs else None}},
