@@ -259,6 +259,81 @@ def aux_records(dev, steps=30):
     return out
 
 
+def run_aux_workload(args):
+    """`--workload ae|ed`: one training step (forward + loss + backward + clip + AdamW) of BASELINE config #2 / #3 per "step",
+    replayed as one CUDA graph; `value` with the batch resident on the device, `e2e` with the batch copied from pinned host
+    memory and the loss read back on the host every step.  Batch: --batch if given on the command line, else 1024."""
+    import contextlib
+    import torch
+    import yaml
+    from melogan import _native
+    from melogan.aux_trainers import EdTrainer, VaeTrainer
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    B = args.batch if "--batch" in sys.argv else 1024
+    W = max(3, args.warmup)
+    name = {"ae": "ae_config.yaml", "ed": "ed_config.yaml"}[args.workload]
+    with open(os.path.join(PKG, "config", name)) as f:
+        cfg = yaml.safe_load(f)
+    with contextlib.redirect_stdout(sys.stderr):
+        tr = (VaeTrainer if args.workload == "ae" else EdTrainer)(dict(cfg), batch=B, precision=args.precision, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    xs = [torch.rand((B, tr.T, 4), generator=g, device=dev) * 2 - 1 for _ in range(3)]
+    hx = [x.cpu().pin_memory() for x in xs]
+    y = (torch.arange(B, device=dev) % 4).to(torch.int64)
+    L = _native.lib()
+    step = (lambda x: tr.step(x)) if args.workload == "ae" else (lambda x: tr.step(x, y))
+    step(xs[0])
+    torch.cuda.synchronize(dev)
+    n0 = L.mg_launch_count()
+    step(xs[1])
+    torch.cuda.synchronize(dev)
+    launches = int(L.mg_launch_count() - n0)
+    cap = tr.capture()
+    sx = cap if args.workload == "ae" else cap[0]
+    if args.workload == "ed":
+        cap[1].copy_(y)
+    h_loss = torch.empty_like(tr.metrics, device="cpu").pin_memory()
+
+    def dev_step(i):
+        sx.copy_(xs[i % 3]); tr.replay()
+
+    def e2e_step(i):
+        sx.copy_(hx[i % 3], non_blocking=True); tr.replay()
+        h_loss.copy_(tr.metrics, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    def timed(fn):
+        for i in range(W):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            fn(W + i)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / args.steps
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(dev_step)
+    sampler.stop_flag.set(); sampler.join(timeout=3)
+    ms_e2e = timed(e2e_step)
+    what = {"ae": "VAE train step (config #2: forward, vae_loss, backward, clip_grad_norm_(1.0), AdamW)",
+            "ed": "emotion-discriminator train step (config #3: forward, cross-entropy, backward, AdamW)"}[args.workload]
+    print(json.dumps({
+        "metric": what + " rolls/sec", "value": B / ms * 1e3, "unit": "rolls/s", "n_gpus": 1, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"{what}, config/{name} shapes, batch {B}", "per_gpu_batch": B, "precision": args.precision,
+                   "cuda_graph": True, "l2": "3 rotating input batches"},
+        "e2e": {"value": B / ms_e2e * 1e3, "unit": "rolls/s", "h2d_bytes_per_step": B * tr.T * 16,
+                "d2h_bytes_per_step": int(tr.metrics.numel()) * 4, "ms_per_step": ms_e2e},
+        "gpu_launches": launches * args.steps, "clocks": sampler.summary()}))
+
+
 def parity_check(tr, cfg, ed_cfg, reals, numerics, labels, dev):
     """One critic step and one generator step of the BENCHED configuration (bf16 mode, bench batch, trained-for-a-few-
     steps parameters) against this engine's own fp32 parity mode (CUDA-core kernels, pinned to the oracle at 1e-5 by
@@ -351,6 +426,9 @@ def main():
                     help="per-GPU batch B of every critic/generator step")
     ap.add_argument("--precision", default=os.environ.get("MELOGAN_PRECISION", "bf16"), choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core mode (north_star tolerance 1e-2); fp32 = CUDA-core parity mode (1e-5)")
+    ap.add_argument("--workload", default="gan", choices=["gan", "ae", "ed"],
+                    help="gan = the headline cycle (BASELINE config #4); ae / ed = one training step of BASELINE config #2 / #3 "
+                         "through melogan.aux_trainers (single GPU)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the HBM-kernel, note-extraction, parity and yardstick records")
@@ -358,6 +436,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "gan":
+        return run_aux_workload(args)
 
     import torch
     import torch.distributed as dist
