@@ -104,6 +104,25 @@ bool ws_enabled() {
     }
     return v == 1;
 }
+__nv_bfloat16* wgrad_cast_scratch(size_t elems, cudaStream_t st) {
+    // Grows by allocating a NEW buffer; the old ones stay alive until the process ends: CUDA graphs captured earlier have
+    // their addresses baked in.  A growth request inside a stream capture fails (cudaMalloc is not capturable): the caller
+    // then keeps the CUDA-core kernel for that launch -- callers run one eager step before they capture.
+    static std::vector<__nv_bfloat16*> kept;
+    static __nv_bfloat16* buf = nullptr;
+    static size_t cap = 0;
+    if (elems > cap) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cs != cudaStreamCaptureStatusNone) return nullptr;      // (an allocation would invalidate the capture)
+        __nv_bfloat16* nb = nullptr;
+        if (cudaMalloc(&nb, elems * sizeof(__nv_bfloat16)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (buf) kept.push_back(buf);
+        buf = nb;
+        cap = elems;
+    }
+    return buf;
+}
 bool pair_enabled() {
     static const bool on = getenv("MELOGAN_DISABLE_PAIR") == nullptr;
     return on;

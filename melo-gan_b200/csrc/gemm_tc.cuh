@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <cstdio>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "gemm_simt.cuh"
@@ -1805,8 +1806,42 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     return rc == MG_OK ? 1 : rc;
 }
 
+// fp32 -> bf16 copy (operands of the float32 Linears' weight gradients in bf16 mode, see try_tc_wgrad)
+static __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 v = __ldg(x + i);
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        y[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+}
+// growable device scratch for those copies (allocated by the first eager call, never inside a stream capture)
+__nv_bfloat16* wgrad_cast_scratch(size_t elems, cudaStream_t st);
+
 template <typename TG, typename TA>
 int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
+    if (std::is_same<TG, float>::value && std::is_same<TA, float>::value) {
+        // bf16 mode: the weight gradients of the float32 Linears (critic fc.1, the generator's / encoder's MLPs) ran on the CUDA
+        // cores (critic fc.1: 122 us for 3.2 GFLOP).  Their forward and dgrad already read the operands as TF32 (10 mantissa
+        // bits); here both operands are rounded to bf16 copies (8 bits, like every conv's weight gradient) and the reduction over
+        // the rows runs on the tensor cores (kind::tf32 has no MN-major form, which a reduction over rows needs).
+        const long long nrows = (long long)P.row_end - P.row_begin;
+        if (!enabled() || !tf32_enabled() || P.Mper != 1 || P.ntaps != 1 || P.row_begin != 0 || nrows < 1024 || P.K % 64 || P.N % 128 ||
+            P.g_off || P.g_bstride != P.N || P.a_bstride != P.K || P.a_valid != P.K || P.a_toff[0] != 0 ||
+            ((uintptr_t)P.A) % 16 || ((uintptr_t)P.G) % 16)
+            return 0;
+        const size_t ng = (size_t)nrows * P.N, na = (size_t)nrows * P.K;
+        __nv_bfloat16* buf = wgrad_cast_scratch(ng + na, st);
+        if (!buf) return 0;
+        const int blocks_g = (int)std::min<long long>((ng / 4 + 255) / 256, (long long)num_sms() * 8);
+        const int blocks_a = (int)std::min<long long>((na / 4 + 255) / 256, (long long)num_sms() * 8);
+        f32_to_bf16_kernel<<<blocks_g, 256, 0, st>>>(reinterpret_cast<const float4*>(P.G), reinterpret_cast<uint2*>(buf), (long long)(ng / 4));
+        MG_LAUNCH_OK();
+        f32_to_bf16_kernel<<<blocks_a, 256, 0, st>>>(reinterpret_cast<const float4*>(P.A), reinterpret_cast<uint2*>(buf + ng), (long long)(na / 4));
+        MG_LAUNCH_OK();
+        WgradArgs Q = P;
+        Q.G = buf; Q.A = buf + ng;
+        return try_tc_wgrad<__nv_bfloat16, __nv_bfloat16>(Q, st);
+    }
     if (!std::is_same<TG, __nv_bfloat16>::value || !std::is_same<TA, __nv_bfloat16>::value || !enabled()) return 0;
     if (P.K % 64 || P.N % 128 || P.ntaps < 1 || P.ntaps > kMaxTaps || P.g_off) return 0;
     if (!is_pow2(P.Mper) || (P.Mper > 64 && P.Mper % 64)) return 0;

@@ -97,6 +97,9 @@ def cycle_layers(B):
     add("D.fc.dgrad.tf32", 5, op=4, R=R, Cin=256, Cout=256, in_bf16=0, out_bf16=0, mask_bf16=0, tf32=1)
     add("G.n2l0.fwd.tf32", 6, op=3, R=B, Cin=256, Cout=512, act=ACT_RELU, bias=True, in_bf16=0, out_bf16=0, mask_bf16=0, tf32=1)
     add("G.pre0.fwd.tf32", 6, op=3, R=B, Cin=64, Cout=512, act=ACT_RELU, bias=True, in_bf16=0, out_bf16=1, mask_bf16=1, tf32=1)
+    # ---- their weight gradients: float32 operands cast to bf16 copies, reduction over the rows on tc_wgrad_kernel ----
+    add("D.fc.wgrad.f32", 5, op=7, R=R, Cin=256, Cout=256, in_bf16=0, out_bf16=0, mask_bf16=0, tf32=1)
+    add("G.n2l0.wgrad.f32", 1, op=7, R=B, Cin=256, Cout=512, in_bf16=0, out_bf16=0, mask_bf16=0, tf32=1)
     return S
 
 
