@@ -50,11 +50,35 @@ class ConvEncoder(nn.Module):
     def forward(self, x):
         """Stand-alone use only materialises `_linear` (what the reference's dummy pass at train_ae.py:75-77 is for) and
         returns None; the hidden state itself is computed inside VAE.forward's single native call."""
-        if self._linear is None:
+        first = self._linear is None
+        if first:
             self.build_linear(x.shape[1])
         if torch.is_grad_enabled() and x.requires_grad:
             raise NotImplementedError("ConvEncoder runs fused inside VAE.forward on the CUDA path")
+        if self.training and not bool(x.any()):
+            self._dummy_pass_running_stats(2 if first else 1)
         return None
+
+    @torch.no_grad()
+    def _dummy_pass_running_stats(self, passes):
+        """The reference's dummy pass (train_ae.py:75-77: model.encoder(zeros) in train mode, under no_grad) runs self.conv once
+        in forward and once more inside build_linear (model.py:27-44), and BatchNorm updates its running statistics both
+        times.  On an all-zero input every conv output is its bias at every position (the next layer sees ReLU(beta)), so
+        each update is running_mean <- (1-m) running_mean + m * mean, running_var <- (1-m) running_var + m * 0 -- done here
+        on the buffers, so that state_dict() after construction matches the reference's."""
+        const = torch.zeros(self.conv[0].in_channels, device=self.conv[0].weight.device)
+        layers = [(self.conv[i], self.conv[i + 1]) for i in range(0, len(self.conv), 3)]
+        for _ in range(passes):
+            c = const
+            for conv, bn in layers:
+                if bool(c.any()):          # a non-zero constant is not constant after zero padding: not the dummy pass
+                    return
+                mean = conv.bias.detach().clone() if conv.bias is not None else torch.zeros_like(bn.running_mean)
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+                bn.running_mean.mul_(1.0 - m).add_(m * mean)
+                bn.running_var.mul_(1.0 - m)
+                bn.num_batches_tracked += 1
+                c = torch.relu(bn.bias.detach())       # x_hat = 0 -> BatchNorm output = beta
 
 
 class ConvDecoder(nn.Module):

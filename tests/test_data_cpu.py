@@ -102,3 +102,23 @@ def test_split_directory_convention_and_plateau_scheduler(tmp_path):
     for m in [1.0, 0.9, 0.95, 0.95, 0.95, 0.95, 0.8, 0.81, 0.82, 0.83, 0.84, 0.85, 0.86, 0.87, 0.88, 0.89, 0.9, 0.91]:
         mine.step(m); ref.step(m)
         assert abs(o.lr - topt.param_groups[0]["lr"]) < 1e-12, (m, o.lr, topt.param_groups[0]["lr"])
+
+
+def test_conv_encoder_dummy_pass_updates_running_stats_like_the_reference():
+    """reference src/ae/train_ae.py:75-77 + model.py:27-44: the zero dummy pass runs the conv stack twice in train mode."""
+    import torch
+    import torch.nn as nn
+    from src.ae.model import ConvEncoder
+    torch.manual_seed(0)
+    enc = ConvEncoder(in_channels=4, latent_dim=8, hidden_dim=32)
+    ref = nn.Sequential(*[m for ci, co in ((4, 32), (32, 64), (64, 128))
+                          for m in (nn.Conv1d(ci, co, 5, 2, 2), nn.BatchNorm1d(co), nn.ReLU(inplace=True))])
+    ref.load_state_dict(enc.conv.state_dict())
+    with torch.no_grad():
+        enc(torch.zeros(1, 64, 4))
+        for _ in range(2):                       # forward's own pass + the one inside build_linear
+            ref(torch.zeros(1, 4, 64))
+    for k, v in ref.state_dict().items():
+        got = enc.conv.state_dict()[k]
+        assert torch.allclose(got.float(), v.float(), rtol=1e-5, atol=5e-6), k     # (x - mean) / sqrt(0 + eps) amplifies fp32 rounding noise of the reference pass to ~1e-6
+    assert enc._linear is not None and enc._linear[1].in_features == 128 * 8
