@@ -106,8 +106,10 @@ class VaeTrainer(_StepGraph):
         self.cfg, self.precision = cfg, precision
         self.B, self.T, self.latent = int(batch or cfg['BATCH_SIZE']), int(cfg['MAX_NOTES']), int(cfg['LATENT_DIM'])
         self.model = (model if model is not None else VAE(cfg)).to(self.device)
-        if self.model.encoder._linear is None:
-            self.model.encoder.build_linear(self.T)
+        if self.model.encoder._linear is None:       # the reference's dummy pass (train_ae.py:75-77): materialises the lazy
+            self.model.train()                       # Linear and, in train mode, updates the BatchNorm running statistics
+            with torch.no_grad():
+                self.model.encoder(torch.zeros(1, self.T, 4, device=self.device))
             self.model.to(self.device)
         self.model.train()
         named = dict(self.model.named_parameters())

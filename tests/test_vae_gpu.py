@@ -149,7 +149,7 @@ def test_train_ae_iteration_on_the_dropin_module_matches_reference_golden():
             tol = 2e-4 if (tight and not k.startswith("decoder")) else 5e-2
             assert abs(got.norm().item() - want[1]) <= tol * want[1], (i, k, got.norm().item(), want[1])
     sd = model.state_dict()
-    assert int(sd["encoder.conv.1.num_batches_tracked"]) == 2
+    assert int(sd["encoder.conv.1.num_batches_tracked"]) == 4      # the zero dummy pass counts twice (reference model.py:27-44), then 2 steps
     for k in E.VAE_PARAM_KEYS + E.VAE_BUFFER_KEYS:
         if k in O.VAE_NOISE_BIASES:
             continue
