@@ -104,6 +104,7 @@ extern "C" int mg_debug_set(const char* key, int value) {
     if (!strcmp(key, "no_pair")) { t.no_pair = value; return MG_OK; }
     if (!strcmp(key, "no_rot")) { t.no_rot = value; return MG_OK; }
     if (!strcmp(key, "no_fuse")) { t.no_fuse = value; return MG_OK; }
+    if (!strcmp(key, "ring2_stages")) { t.ring2_stages = value; return MG_OK; }
     if (!strcmp(key, "dbg")) { t.dbg = value; return MG_OK; }
     if (!strcmp(key, "reverse")) { t.reverse = value; return MG_OK; }
     if (!strcmp(key, "no_tma_store")) { t.no_tma_store = value; return MG_OK; }

@@ -574,6 +574,8 @@ int ed_forward(mg_gan* c, const float* notes, float* logits_out, cudaStream_t st
         MG_TRY((conv_fwd<T, T>((const T*)c->ed_h[i - 1], (T*)c->ed_h[i], c->ED.conv[i].w, c->ed_shift[i], B, T4, ci[i],
                                co[i], 3, 1, 1, ACT_GELU, c->ed_scale[i], c->ed_g[i], nullptr, MUL_NONE, st, -1, -1,
                                i == 3 ? c->ed_pool : nullptr, 1.0f / (float)T4, i == 3 ? &pooled : nullptr)));
+    // (ed_h[3] feeds only the pooling; not storing it when the epilogue pools -- TapGemmArgs::pool_only -- was measured:
+    //  no gain, conv.3 forward is bound by its GELU epilogue and the derivative tile's store, so the buffer stays valid)
     if (!pooled) {
         ProbeScope probe(PROBE_ELEM, 0.0, (double)B * T4 * 256 * sizeof(T), st);
         pool_rows_kernel<T, float><<<B, 256, 0, st>>>((const T*)c->ed_h[3], c->ed_pool, B, T4, 256, 1.0f / (float)T4);

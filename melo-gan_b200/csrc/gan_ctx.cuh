@@ -130,9 +130,9 @@ template <typename TA, typename TO, typename TMSK = TO>
 int conv_fwd(const TA* in, TO* out, const float* W, const float* bias, int R, int Lin, int Cin, int Cout, int ks,
              int stride, int pad, int act, const float* col_scale, void* aux, const void* mul_src, int mul_mode,
              cudaStream_t st, int w_nstride = -1, int w_kstride = -1, float* pool_out = nullptr, float pool_scale = 0.0f,
-             int* pool_done = nullptr) {
+             int* pool_done = nullptr, int pool_only = 0) {
     TapGemmArgs a = tap_defaults();
-    a.pool_out = pool_out; a.pool_scale = pool_scale; a.pool_done = pool_done;
+    a.pool_out = pool_out; a.pool_scale = pool_scale; a.pool_done = pool_done; a.pool_only = pool_only;
     const int Lout = Lin / stride;
     a.A = in; a.a_bstride = (long long)Lin * Cin; a.a_mstride = stride * Cin; a.a_valid = Lin * Cin;
     a.ntaps = ks; a.K = Cin;

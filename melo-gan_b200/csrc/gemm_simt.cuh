@@ -48,6 +48,7 @@ struct TapGemmArgs {
     // the weight-stationary tensor-core kernels do it (from their staging tile); *pool_done is set to 1 when they did, else the
     // caller runs pool_rows_kernel over Out as before.
     float* pool_out; float pool_scale; int* pool_done;
+    int pool_only;                // with pool_out: if the pooling is fused, Out itself need not be stored (nothing else reads it)
     // optional fused column sums (bias gradients): colsum_out[n] += sum of the STORED Out[b, m, n] over the flattened rows
     // r = b * Mper + m < colsum_rows (a multiple of 128), by atomicAdd; same contract as pool_done for *colsum_done
     float* colsum_out; long long colsum_rows; int* colsum_done;

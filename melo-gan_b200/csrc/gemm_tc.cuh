@@ -299,6 +299,7 @@ struct TcTapArgs {
     float* pool_out; float pool_scale;  // fused mean over the rows of a sample (see ws_pool_*): pool_out[b * N + n]
     int pool_atomic;                    // a sample spans several tiles (Mper > 128): atomicAdd into a zeroed pool_out
     int* pool_done;                     // host only
+    int skip_out;                       // the caller only wants the fused pooling (and the derivative tile): Out is not stored
     float* colsum_out; int colsum_tiles; int* colsum_done;   // fused column sums over the row tiles < colsum_tiles (bias gradients)
     float* stats_out; int* stats_done;  // fused BatchNorm statistics of a float32 output: [sum | sum of squares][N]
     int rot_step;                       // weight-stationary kernels: slab y starts its walk y * rot_step tiles further (see ws_row_tile)
@@ -714,8 +715,10 @@ __device__ __forceinline__ void ws_epilogue_loop(const TcTapArgs& P, const CUten
         asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
         if (et == 0) {
             if (!(P.dbg & 1)) {
+                if (!P.skip_out) {
 #pragma unroll
-                for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, stage_out + bx * 16384, n0 + bx * EPB, row0);
+                    for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(o_map, stage_out + bx * 16384, n0 + bx * EPB, row0);
+                }
                 if (has_aux) {
 #pragma unroll
                     for (int bx = 0; bx < BN / EPB; ++bx) tma_store_2d(x_map, stage_aux + bx * 16384, n0 + bx * EPB, row0);
@@ -1536,6 +1539,7 @@ struct Tuning {
     int no_tma_store = 0, no_tma_mask = 0, no_reuse = 0;
     int no_pair = 0;         // 1 = never the CTA-pair (cta_group::2) kernel
     int no_rot = 0;          // 1 = every slab walks the row tiles in the same order
+    int ring2_stages = 0;    // activation stages a second staging set must leave (0 = 4)
     int no_fuse = 0;         // bits: 1 = no pooling, 2 = no column sums, 4 = no BatchNorm statistics in the epilogues (the callers
                              // then run their own passes)
 };
@@ -1555,7 +1559,7 @@ LaunchInfo& last_launch();
 // am_halo (optional): the same activation view with boxes of 128 + a.halo rows, a.ngroups/g_* describing the tap groups.
 template <typename TO, typename TMSK, bool TF32 = false>
 int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN, int K, cudaStream_t st,
-               const CUtensorMap* am_halo = nullptr, const CUtensorMap* bm_half = nullptr) {
+               const CUtensorMap* am_halo = nullptr, const CUtensorMap* bm_half = nullptr, bool pool_only = false) {
     a.ktile = TF32 ? 32 : 64;
     if (!is_pow2(a.Mper) || !is_pow2(a.mpt) || a.mpt * a.bpt != kTileM || (a.Mper > kTileM && a.Mper % kTileM)) {
         set_error("run_tc_tap: Mper=%d mpt=%d bpt=%d is not a power-of-two tiling", a.Mper, a.mpt, a.bpt);
@@ -1650,8 +1654,12 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
         }
         // a second staging tile when it still leaves 4 activation stages: the drain of the bulk store (shared memory ->
         // L2) then overlaps the next tile's TMEM read and epilogue math instead of serialising with them
+        // (GELU layers that also store the derivative tile are bound by their epilogue, not by the activation ring: two tiles'
+        // worth of staging with a 2-deep ring beats one with 6 -- ED conv.2 forward 1450 -> 1284 us -- because with a single
+        // staging set every tile waits for the previous tile's 64 KB bulk store to drain)
+        const int ring2_min_stages = tn.ring2_stages > 0 ? tn.ring2_stages : ((a.aux && a.act == ACT_GELU) ? 2 : 4);
         if (a.tma_store && tn.staging_bufs != 1 &&
-            wbytes + 4 * a_stage + 2 * staging + (a.tma_mask ? maskbytes : 0) <= avail)
+            wbytes + ring2_min_stages * a_stage + 2 * staging + (a.tma_mask ? maskbytes : 0) <= avail)
             a.nsb = 2 * per_tile;
         // a second mask tile (prefetch distance two tiles) when it still leaves 4 activation stages
         a.nmb = 1;
@@ -1667,6 +1675,7 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
                           wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
         if (!pool) a.pool_out = nullptr;
         a.pool_atomic = a.Mper > 128;
+        a.skip_out = pool && pool_only;
         // fused column sums (bias gradients): any bf16 staging tile; whole tiles only
         const bool colsum = a.colsum_out && !pool && a.tma_store && sizeof(TO) == 2 && !a.accumulate && rows % 128 == 0 &&
                             wbytes + 3 * a_stage + (size_t)128 * BN * sizeof(TO) * a.nsb + (a.tma_mask ? maskbytes * a.nmb : 0) + poolbytes <= avail;
@@ -1735,7 +1744,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     a.bias = P.bias; a.col_scale = P.col_scale; a.act = P.act; a.mul_src = P.mul_src; a.mul_mode = P.mul_mode;
     a.aux = P.aux; a.alpha = P.alpha; a.accumulate = P.accumulate;
     a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
-    a.pool_out = P.pool_out; a.pool_scale = P.pool_scale; a.pool_done = P.pool_done;
+    a.pool_out = P.pool_out; a.pool_scale = P.pool_scale; a.pool_done = P.pool_done; a.skip_out = 0;
     a.colsum_out = P.colsum_out; a.colsum_tiles = (int)(P.colsum_rows / 128); a.colsum_done = P.colsum_done;
     a.stats_out = P.stats_out; a.stats_done = P.stats_done;
 
@@ -1802,7 +1811,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
         if (rc != MG_OK) return rc;
         half_map = &bmh;
     }
-    rc = run_tc_tap<TO, TMSK, TF32>(am, bm, a, BN, P.K, st, halo_map, half_map);
+    rc = run_tc_tap<TO, TMSK, TF32>(am, bm, a, BN, P.K, st, halo_map, half_map, P.pool_only != 0);
     return rc == MG_OK ? 1 : rc;
 }
 
