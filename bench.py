@@ -429,6 +429,8 @@ def main():
     ap.add_argument("--workload", default="gan", choices=["gan", "ae", "ed"],
                     help="gan = the headline cycle (BASELINE config #4); ae / ed = one training step of BASELINE config #2 / #3 "
                          "through melogan.aux_trainers (single GPU)")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="N > 1: BatchNorm statistics over all ranks through NVLink peer memory (default: local, like torch DDP)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the HBM-kernel, note-extraction, parity and yardstick records")
@@ -460,7 +462,8 @@ def main():
     B, K = args.batch, int(cfg.get("CRITIC_ITERS", 5))
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):     # the drop-in modules print like the reference's; stdout is ONE JSON line
-        tr = GanTrainer(cfg, ed_cfg, batch=B, precision=args.precision, device=dev, process_group=pg, seed_offset=rank)
+        tr = GanTrainer(cfg, ed_cfg, batch=B, precision=args.precision, device=dev, process_group=pg, seed_offset=rank,
+                        sync_bn=args.sync_bn)
 
     # synthetic inputs: several resident cycles so consecutive steps read different data
     NSETS = 3
@@ -639,7 +642,7 @@ def main():
                                f"(512x4 rolls, noise 128, latent 64, 4 emotion classes), per-GPU batch B={B}",
                    "per_gpu_batch": B, "rolls_per_step_per_gpu": K * B, "precision": args.precision,
                    "cuda_graph": use_graph, "parallelism": f"dp{world}" if world > 1 else "single",
-                   "bn": "local" if world > 1 else "n/a",
+                   "bn": ("sync (peer memory)" if tr.sync_bn else "local") if world > 1 else "n/a",
                    "l2": f"{NSETS} rotating input sets; per-step activation working set {tr.engine.workspace_bytes() / 1e6:.0f} MB >> 126 MB L2",
                    "algorithmic_mflop_per_roll": MFLOP_PER_ROLL},
         "e2e": {"value": e2e_value, "unit": "rolls/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,

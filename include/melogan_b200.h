@@ -308,6 +308,20 @@ int mg_act_dropout_forward(const float* z, const float* mask, float scale, int a
 int mg_act_dropout_backward(const float* dh, const float* z, const float* mask, float scale, int act, float* dz,
                             long long n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SyncBatchNorm for data parallelism (what nn.SyncBatchNorm.convert_sync_batchnorm would do to the reference's
+ * GeneratorDecoder, src/gan/models.py:57,60): the batch statistics of the generator's two BatchNorm layers (forward: sum x,
+ * sum x^2; backward: sum dy, sum dy*xhat) are summed over all ranks of ONE node through NVLink peer memory -- a one-CTA kernel
+ * per sync point that writes the rank's vector into its own exchange buffer and reads the peers' (CUDA IPC), no NCCL call,
+ * capturable in a CUDA graph.  Every rank adds in rank order: statistics are bit-identical on all ranks.
+ *   1. every rank: mg_gan_sync_bn_export(ctx, rank, world, handle[64])   allocates the exchange buffer, returns its IPC handle
+ *   2. exchange the handles between the processes (any transport; melogan.engine uses torch.distributed.all_gather)
+ *   3. every rank: mg_gan_sync_bn_connect(ctx, handles[world * 64])       opens the peers' buffers and switches the mode on
+ * world <= 8, one process per GPU.  Every rank must then run the same sequence of generator forwards / backwards.
+ * ---------------------------------------------------------------------------------------- */
+int mg_gan_sync_bn_export(mg_gan* ctx, int rank, int world, unsigned char* handle_out);
+int mg_gan_sync_bn_connect(mg_gan* ctx, const unsigned char* handles);
+
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
 

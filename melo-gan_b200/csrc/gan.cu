@@ -258,14 +258,14 @@ int gen_forward(mg_gan* c, const float* noise, const float* emb, int train, floa
                                     ACT_NONE, nullptr, MUL_NONE, 0, st, nullptr, 0, nullptr, train ? c->g_bn1_stats : nullptr, &s1)));
     MG_REQUIRE(s1 >= 0, "gen_forward: the two sub-pixel phases of deconv.0 took different kernels");
     MG_TRY((bn_train_or_eval<T>(c, c->g_x1, (T*)c->g_y1, (long long)B * 2 * L0, 128, c->g_bn1_stats,
-                                c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->G.bn1_b, c->G.bn1_rm, c->G.bn1_rv, train, st, s1 > 0)));
+                                c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->G.bn1_b, c->G.bn1_rm, c->G.bn1_rv, train, st, s1 > 0, 0)));
     // deconv.3 -> BN -> ReLU
     if (train) MG_CUDA_OK(cudaMemsetAsync(c->g_bn2_stats, 0, 2 * 64 * sizeof(float), st));
     MG_TRY((upsample2_fwd<T, float>((const T*)c->g_y1, c->g_x2, c->G.d3_w, c->G.d3_b, B, 2 * L0, 128, 64, 5, 64 * 5,
                                     ACT_NONE, nullptr, MUL_NONE, 0, st, nullptr, 0, nullptr, train ? c->g_bn2_stats : nullptr, &s2)));
     MG_REQUIRE(s2 >= 0, "gen_forward: the two sub-pixel phases of deconv.3 took different kernels");
     MG_TRY((bn_train_or_eval<T>(c, c->g_x2, (T*)c->g_y2, (long long)B * 4 * L0, 64, c->g_bn2_stats,
-                                c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st, s2 > 0)));
+                                c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->G.bn2_b, c->G.bn2_rm, c->G.bn2_rv, train, st, s2 > 0, 1)));
     // deconv.6 -> notes (B, T, 4) float32, already in the reference's permuted (B, notes, 4) order
     float* notes = notes_out ? notes_out : c->g_notes;
     if (use_banded<T>(c)) {
@@ -299,7 +299,7 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     }
     // ---- BN2 backward ----
     MG_TRY((bn_backward<T>(c, c->g_x2, c->g_dy2, (T*)c->g_dx2, (long long)B * 4 * L0, 64,
-                           c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->gG.bn2_w, c->gG.bn2_b, st)));
+                           c->g_bn2_mean, c->g_bn2_is, c->G.bn2_w, c->gG.bn2_w, c->gG.bn2_b, st, 2)));
     // ---- deconv.3 ----
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx2, 64, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
                                   (long long)B * 4 * L0, 64, c->gG.d3_b, 0, 0, 0, 1.0f, 1, st)));
@@ -307,7 +307,7 @@ int gen_backward(mg_gan* c, const float* dnotes, const float* dlatent, float* de
     MG_TRY((conv_fwd<T, float, T>((const T*)c->g_dx2, c->g_dy1, c->G.d3_w, nullptr, B, 4 * L0, 64, 128, 5, 2, 2, ACT_NONE,
                                   nullptr, nullptr, c->g_y1, MUL_RELU_SIGN, st, 64 * 5, 5)));
     MG_TRY((bn_backward<T>(c, c->g_x1, c->g_dy1, (T*)c->g_dx1, (long long)B * 2 * L0, 128,
-                           c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->gG.bn1_w, c->gG.bn1_b, st)));
+                           c->g_bn1_mean, c->g_bn1_is, c->G.bn1_w, c->gG.bn1_w, c->gG.bn1_b, st, 3)));
     // ---- deconv.0 ----
     MG_TRY((colreduce<T, COL_SUM>(c, (const T*)c->g_dx1, 128, nullptr, 0, nullptr, nullptr, nullptr, 1, 0,
                                   (long long)B * 2 * L0, 128, c->gG.d0_b, 0, 0, 0, 1.0f, 1, st)));
@@ -861,8 +861,48 @@ extern "C" int mg_gan_create(const mg_gan_config* cfg, mg_gan** out) {
     return MG_OK;
 }
 
+// ---- SyncBatchNorm over peer memory (the one semantic catch of data parallelism) ----
+extern "C" int mg_gan_sync_bn_export(mg_gan* c, int rank, int world, unsigned char* handle_out) {
+    MG_CTX_CHECK(c);
+    MG_REQUIRE(handle_out && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "sync_bn_export: bad rank / world");
+    MG_REQUIRE(!c->sync.base[rank], "sync_bn_export: already exported");
+    float* buf = nullptr;
+    MG_CUDA_OK(cudaMalloc(&buf, kSyncBytes));
+    MG_CUDA_OK(cudaMemset(buf, 0, kSyncBytes));
+    cudaIpcMemHandle_t h;
+    MG_CUDA_OK(cudaIpcGetMemHandle(&h, buf));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle_out, &h, sizeof(h));
+    c->sync.base[rank] = buf;
+    c->sync.rank = rank;
+    c->sync.world = 1;                       // local statistics until mg_gan_sync_bn_connect
+    c->sync_opened[rank] = nullptr;
+    c->sync_pending_world = world;
+    return MG_OK;
+}
+
+extern "C" int mg_gan_sync_bn_connect(mg_gan* c, const unsigned char* handles) {
+    MG_CTX_CHECK(c);
+    const int world = c->sync_pending_world, rank = c->sync.rank;
+    MG_REQUIRE(handles && world >= 1 && c->sync.base[rank], "sync_bn_connect: call mg_gan_sync_bn_export first");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, sizeof(h));
+        void* p = nullptr;
+        MG_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->sync.base[r] = static_cast<float*>(p);
+        c->sync_opened[r] = p;
+    }
+    c->sync.world = world;                   // from here on G's BatchNorm layers use statistics over all ranks
+    return MG_OK;
+}
+
 extern "C" void mg_gan_destroy(mg_gan* c) {
     if (!c) return;
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (c->sync_opened[r]) cudaIpcCloseMemHandle(c->sync_opened[r]);
+    if (c->sync.base[c->sync.rank] && c->sync_pending_world) cudaFree(c->sync.base[c->sync.rank]);
     if (c->arena) cudaFree(c->arena);
     if (c->ed_train_arena) cudaFree(c->ed_train_arena);
     delete c;

@@ -8,12 +8,71 @@
 #include "thin.cuh"
 #include "banded.cuh"
 
+// ---- cross-GPU sum of a small vector through peer memory (SyncBatchNorm statistics) ----
+// Each rank owns one exchange buffer (cudaMalloc + CUDA IPC handle): kSyncSlots slots x 2 parities x kSyncMax floats, then one
+// flag and one epoch counter per slot.  A sync point of slot s: write my vector into parity (epoch & 1) of my slot, publish
+// flag = epoch with a system-scope release, spin until every peer's flag reached the epoch, add the peers' vectors in RANK
+// order (every rank computes bit-identical sums).  Two parities suffice: a rank can reach epoch e + 2 of a slot only after
+// every peer published e + 1, i.e. after they all finished reading epoch e.  One CTA, no NCCL, capturable in a CUDA graph.
+constexpr int kMaxPeers = 8, kSyncSlots = 4, kSyncMax = 512;
+constexpr int kSyncFlagOff = kSyncSlots * 2 * kSyncMax;                 // in 4-byte words
+constexpr size_t kSyncBytes = (size_t)(kSyncFlagOff + 2 * kSyncSlots) * 4;
+struct PeerSet { float* base[kMaxPeers]; int world, rank; };
+
+static __global__ void __launch_bounds__(kSyncMax) peer_allreduce_kernel(const PeerSet P, float* __restrict__ data, int n, int slot) {
+    __shared__ unsigned e_s;
+    float* mine = P.base[P.rank];
+    unsigned* flags = reinterpret_cast<unsigned*>(mine + kSyncFlagOff);
+    const int tid = threadIdx.x;
+    if (tid == 0) e_s = flags[kSyncSlots + slot] + 1u;                   // my epoch counter of this slot
+    __syncthreads();
+    const unsigned e = e_s;
+    const int off = (slot * 2 + (int)(e & 1u)) * kSyncMax;
+    const float v = tid < n ? data[tid] : 0.0f;
+    if (tid < n) mine[off + tid] = v;
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        flags[kSyncSlots + slot] = e;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags + slot), "r"(e) : "memory");
+    }
+    if (tid < P.world && tid != P.rank) {
+        const unsigned* pf = reinterpret_cast<const unsigned*>(P.base[tid] + kSyncFlagOff) + slot;
+        unsigned seen = 0;
+        for (unsigned spins = 0;; ++spins) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(pf) : "memory");
+            if ((int)(seen - e) >= 0) break;
+            if (spins > (1u << 28)) asm volatile("trap;");              // a lost peer must not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (tid < n) {
+        float s = 0.0f;
+        for (int r = 0; r < P.world; ++r) s += (r == P.rank) ? v : __ldcv(P.base[r] + off + tid);
+        data[tid] = s;
+    }
+}
+
+struct mg_gan;
+inline int peer_allreduce(const PeerSet& P, float* data, int n, int slot, cudaStream_t st) {
+    if (P.world <= 1) return MG_OK;
+    MG_REQUIRE(n <= kSyncMax && slot >= 0 && slot < kSyncSlots, "peer_allreduce: bad size / slot");
+    peer_allreduce_kernel<<<1, kSyncMax, 0, st>>>(P, data, n, slot);
+    MG_LAUNCH_OK();
+    return MG_OK;
+}
+
 struct mg_gan {
     mg_gan_config cfg;
     // derived sizes
     int B, T, L0, zin;             // batch, max_notes, max_notes/8, noise+embed
     bool bf16;
     bool bias_fused_c2 = false, bias_fused_c0 = false, bias_fused_c4 = false;   // disc_dgrad already summed these bias gradients
+    // SyncBatchNorm over NVLink peer memory (mg_gan_sync_bn_*): every rank's exchange buffer, opened through CUDA IPC
+    PeerSet sync{};
+    void* sync_opened[kMaxPeers] = {};
+    int sync_pending_world = 0;
 
     // ---- bound parameters / gradients (caller-owned device memory) ----
     struct EP { float *ln_w, *ln_b, *w1, *b1, *w2, *b2, *w3, *b3; } E{}, gE{};
@@ -280,12 +339,15 @@ inline int grid_for(long long n, int threads = 256, int max_per_sm = 8) {
 template <typename T>
 int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, float* stats, float* mean, float* invstd,
                      const float* gamma, const float* beta, float* rm, float* rv, int train, cudaStream_t st,
-                     bool stats_ready = false) {   // the producing epilogue already summed x and x^2 into `stats`
+                     bool stats_ready = false,     // the producing epilogue already summed x and x^2 into `stats`
+                     int sync_slot = -1) {         // SyncBatchNorm: statistics over all ranks (mg_gan_sync_bn_connect)
     if (train) {
         if (!stats_ready)
             MG_TRY((colreduce<float, COL_SUM_SQ>(c, x, C, nullptr, 0, nullptr, nullptr, nullptr, 1, 0, rows, C, stats, C, 0, 0,
                                              1.0f, 0, st)));
-        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows, (float)c->cfg.bn_eps,
+        const int world = (sync_slot >= 0 && c->sync.world > 1) ? c->sync.world : 1;
+        if (world > 1) MG_TRY(peer_allreduce(c->sync, stats, 2 * C, sync_slot, st));
+        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, rows * world, (float)c->cfg.bn_eps,
                                                             (float)c->cfg.bn_momentum, mean, invstd, rm, rv, 1);
     } else {
         bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rm, rv, (float)c->cfg.bn_eps, C, mean, invstd);
@@ -302,15 +364,19 @@ int bn_train_or_eval(mg_gan* c, const float* x, T* y, long long rows, int C, flo
 // ---- its backward: dy (float32, ReLU mask already applied) -> dx, accumulates d gamma / d beta ----
 template <typename T>
 int bn_backward(mg_gan* c, const float* x, const float* dy, T* dx, long long rows, int C, const float* mean,
-                const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st) {
+                const float* invstd, const float* gamma, float* dgamma, float* dbeta, cudaStream_t st, int sync_slot = -1) {
     // sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat
     MG_TRY((colreduce<float, COL_BN_BWD, float>(c, x, C, dy, C, mean, invstd, nullptr, 1, 0, rows, C, c->g_bn_sums, C, 0, 0, 1.0f,
                                      0, st)));
     add2_kernel<<<(C + 127) / 128, 128, 0, st>>>(dbeta, c->g_bn_sums, dgamma, c->g_bn_sums + C, C);
     MG_LAUNCH_OK();
+    // SyncBatchNorm: the parameter gradients above stay local sums (the gradient all-reduce adds them up); dx needs the sums
+    // over the GLOBAL batch -- this rank computes d(its own loss), the 1/world of the mean over ranks is Adam's grad_scale
+    const int world = (sync_slot >= 0 && c->sync.world > 1) ? c->sync.world : 1;
+    if (world > 1) MG_TRY(peer_allreduce(c->sync, c->g_bn_sums, 2 * C, sync_slot, st));
     const long long n4 = rows * C / 4;
     ProbeScope probe(PROBE_ELEM, 0.0, (double)rows * C * (8 + sizeof(T)), st);
-    bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)rows, mean, invstd, gamma,
+    bn_bwd_apply_kernel<float, T, float><<<grid_for(n4), 256, 0, st>>>(x, dy, dx, n4, C, 1.0f / (float)(rows * world), mean, invstd, gamma,
                                                          c->g_bn_sums);
     MG_LAUNCH_OK();
     return MG_OK;

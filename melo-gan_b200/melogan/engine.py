@@ -147,6 +147,24 @@ class GanEngine:
         _check_f32_cuda(demb, "demb", (self.B, self.embed_dim))
         self._call("mg_feature_encoder_backward", _ptr(demb), self._stream())
 
+    # ---- SyncBatchNorm over NVLink peer memory ----
+    def sync_bn_connect(self, process_group=None):
+        """Collective: from here on the generator's two BatchNorm layers use batch statistics over ALL ranks of the group (one
+        node, <= 8 GPUs, one process per GPU), exchanged by a one-CTA kernel through CUDA-IPC peer buffers -- no NCCL call in
+        the step, so the captured step graphs stay valid.  The handles travel once, through torch.distributed."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        h = (ctypes.c_ubyte * 64)()
+        self._call("mg_gan_sync_bn_export", rank, world, ctypes.cast(h, ctypes.c_void_p))
+        mine = torch.tensor(list(bytes(h)), dtype=torch.uint8, device=self.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=process_group)
+        blob = bytes(torch.cat(allh).cpu().tolist())
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._call("mg_gan_sync_bn_connect", ctypes.cast(buf, ctypes.c_void_p))
+        dist.barrier(group=process_group)          # every rank has opened every buffer before the first sync point
+        self.sync_bn = True
+
     # ---- A-2..A-4 ----
     def set_condition(self, encoder_latent):
         """'conditioning' mode: the AE latent block of G's input row, read by every later generator forward / fused step."""

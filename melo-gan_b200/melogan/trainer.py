@@ -48,7 +48,7 @@ def weights_init(m):
 
 class GanTrainer:
     def __init__(self, cfg, ed_cfg, batch=None, precision="fp32", device=None, ed_state_dict=None,
-                 process_group=None, seed_offset=0, modules=None):
+                 process_group=None, seed_offset=0, modules=None, sync_bn=False):
         from src.gan.feature_encoder import FeatureEncoder
         from src.gan.models import Discriminator, Generator
         from src.emotion_discriminator.ed_model import EmotionDiscriminator
@@ -104,6 +104,11 @@ class GanTrainer:
         self.cond = torch.zeros((self.B, self.cond_dim), device=self.device) if self.cond_dim else None
         if self.cond is not None:
             self.engine.set_condition(self.cond)
+        # data parallel: BatchNorm batch statistics are local to the rank by default (what torch DDP does to the reference);
+        # sync_bn=True (config key SYNC_BN) makes them global, over NVLink peer memory (engine.sync_bn_connect)
+        self.sync_bn = bool(sync_bn or cfg.get('SYNC_BN', False)) and self.world > 1
+        if self.sync_bn:
+            self.engine.sync_bn_connect(self.pg)
         self.rebind()
 
         dev, B = self.device, self.B
@@ -311,7 +316,7 @@ class GanTrainer:
         the running estimates drift apart.  Before a checkpoint / evaluation they are replaced by their mean over ranks
         (the running mean of rank-local batch means IS the global-batch mean; for the variance the mean of the
         rank-local unbiased variances, torch SyncBatchNorm's estimate minus the between-rank term)."""
-        if self.world > 1:
+        if self.world > 1 and not self.sync_bn:          # (with SyncBatchNorm every rank already holds the same estimates)
             for bn in (self.G.decoder.deconv[1], self.G.decoder.deconv[4]):
                 for t in (bn.running_mean, bn.running_var):
                     torch.distributed.all_reduce(t, group=self.pg)

@@ -157,7 +157,8 @@ def main(argv=None):
     if B % world:
         raise SystemExit(f"BATCH_SIZE {B} must be divisible by the world size {world}")
     tr = GanTrainer(cfg, ed_cfg, batch=B // world, precision=os.environ.get("MELOGAN_PRECISION", "fp32"), device=device,
-                    ed_state_dict=ed_state, process_group=pg, seed_offset=rank)
+                    ed_state_dict=ed_state, process_group=pg, seed_offset=rank,
+                    sync_bn=os.environ.get("MELOGAN_SYNC_BN") == "1" or bool(cfg.get("SYNC_BN", False)))
     d_notes, d_numeric, d_labels = (torch.from_numpy(a).to(device) for a in (notes, numeric, labels))   # 7 MB: resident
     d_cond = None
     if tr.cond_dim:                             # INTEGRATION_MODE 'conditioning': AE latents from src/ae/encode.py

@@ -134,3 +134,104 @@ def _run(one_graph):
 @pytest.mark.timeout(600)
 def test_dp_two_gpus_gradients_and_captured_cycle():
     _run(False)
+
+
+def _worker_syncbn(rank, world, port, precision, out):
+    for p in (ROOT, os.path.join(ROOT, "melo-gan_b200"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import contextlib
+    import io
+    import yaml
+    from melogan.trainer import GanTrainer
+    cfgd = os.path.join(ROOT, "melo-gan_b200", "config")
+    cfg = yaml.safe_load(open(os.path.join(cfgd, "gan_config.yaml")))
+    ed_cfg = yaml.safe_load(open(os.path.join(cfgd, "ed_config.yaml")))
+    Bl = 16
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = GanTrainer(cfg, ed_cfg, batch=Bl, precision=precision, device=dev, process_group=dist.group.WORLD, seed_offset=rank,
+                        sync_bn=True)
+        ref = GanTrainer(cfg, ed_cfg, batch=Bl * world, precision=precision, device=dev) if rank == 0 else None
+    assert tr.sync_bn
+    full = _inputs(9, Bl * world, cfg)
+    mine = {k: v[rank * Bl:(rank + 1) * Bl].to(dev) for k, v in full.items()}
+    res = {}
+    # one generator step on the shard, statistics over the global batch
+    tr.generator_step(mine["numeric"], mine["labels"], noise=mine["noise"], mask1=mine["mask1"], mask2=mine["mask2"])
+    notes = tr.engine.buffer("g.notes")[:Bl * 512 * 4].clone()
+    gg = tr.flat_g.grad.clone()                         # all-reduced SUM over ranks; the mean is grad_scale = 1/world in Adam
+    bn = [b.clone() for b in (tr.G.decoder.deconv[1].running_mean, tr.G.decoder.deconv[1].running_var,
+                              tr.G.decoder.deconv[4].running_mean, tr.G.decoder.deconv[4].running_var)]
+    gathered = [torch.empty_like(notes) for _ in range(world)]
+    dist.all_gather(gathered, notes)
+    for name, t in zip(("rm1", "rv1", "rm2", "rv2"), bn):
+        mx, mn = t.clone(), t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        res[f"spread_{name}"] = float((mx - mn).abs().max())
+    if rank == 0:
+        f = {k: v.to(dev) for k, v in full.items()}
+        ref.generator_step(f["numeric"], f["labels"], noise=f["noise"], mask1=f["mask1"], mask2=f["mask2"])
+        want_notes = ref.engine.buffer("g.notes")[:Bl * world * 512 * 4]
+        got_notes = torch.cat(gathered)
+        res["notes_err"] = float((got_notes - want_notes).abs().max() / want_notes.abs().max())
+        want_g = ref.flat_g.grad
+        res["grad_err"] = float(((gg / world) - want_g).norm() / want_g.norm())
+        rbn = (ref.G.decoder.deconv[1].running_mean, ref.G.decoder.deconv[1].running_var,
+               ref.G.decoder.deconv[4].running_mean, ref.G.decoder.deconv[4].running_var)
+        res["bn_err"] = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(bn, rbn))
+    # the peer exchange inside captured step graphs: a captured cycle reproduces an eager one
+    K = tr.critic_iters
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    reals = torch.rand((K, Bl, cfg['MAX_NOTES'], 4), generator=g, device=dev) * 2 - 1
+    nums = torch.randn((K, Bl, cfg.get('NUMERIC_INPUT_DIM', 6)), generator=g, device=dev)
+    labels = (torch.arange(Bl, device=dev) % 4).to(torch.int64)
+    snap = (tr.flat_d.data.clone(), tr.flat_g.data.clone(), tr.rng_counter.clone(), tr.opt_D.state_dict(), tr.opt_G.state_dict())
+    tr.train_cycle(reals, nums, labels)
+    eager_g = tr.flat_g.data.clone()
+    tr.flat_d.data.copy_(snap[0]); tr.flat_g.data.copy_(snap[1]); tr.rng_counter.copy_(snap[2])
+    tr.opt_D.load_state_dict(snap[3]); tr.opt_G.load_state_dict(snap[4])
+    tr.engine.weight_cache(True)
+    s_reals, s_nums, s_labels = tr.capture_cycle()
+    s_reals.copy_(reals); s_nums.copy_(nums); s_labels.copy_(labels)
+    tr.replay_cycle()
+    torch.cuda.synchronize(dev)
+    res["graph_vs_eager_g"] = float((tr.flat_g.data - eager_g).abs().max() / eager_g.abs().max())
+    if rank == 0:
+        out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sync_batchnorm_over_peer_memory_equals_single_gpu_full_batch(precision):
+    """SyncBatchNorm (mg_gan_sync_bn_*: statistics summed over the ranks through NVLink peer memory, no NCCL in the step):
+    two ranks with 16 samples each must reproduce ONE GPU running the 32-sample batch -- generated notes, BatchNorm running
+    statistics and the averaged generator gradient -- which local BatchNorm cannot (its statistics see 16 samples)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29900 + os.getpid() % 90 + (5 if precision == "bf16" else 0)
+    procs = [ctx.Process(target=_worker_syncbn, args=(r, 2, port, precision, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not alive, "SyncBatchNorm worker hung"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = out.get(timeout=10)
+    print(precision, res)
+    assert all(res[f"spread_{n}"] == 0.0 for n in ("rm1", "rv1", "rm2", "rv2")), res      # rank-order sums: bit-identical
+    tight = precision == "fp32"
+    assert res["notes_err"] < (2e-5 if tight else 2e-2), res
+    assert res["bn_err"] < (2e-5 if tight else 1e-3), res
+    assert res["grad_err"] < (2e-4 if tight else 1.5e-1), res        # bf16: mask flips between a 16- and a 32-sample tiling
+    assert res["graph_vs_eager_g"] < 2e-3, res
