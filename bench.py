@@ -431,6 +431,8 @@ def main():
                          "through melogan.aux_trainers (single GPU)")
     ap.add_argument("--sync-bn", action="store_true",
                     help="N > 1: BatchNorm statistics over all ranks through NVLink peer memory (default: local, like torch DDP)")
+    ap.add_argument("--peer-allreduce", action="store_true",
+                    help="N > 1: gradient exchange as kernels over NVLink peer memory (one graph per cycle) instead of NCCL")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the HBM-kernel, note-extraction, parity and yardstick records")
@@ -463,7 +465,7 @@ def main():
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):     # the drop-in modules print like the reference's; stdout is ONE JSON line
         tr = GanTrainer(cfg, ed_cfg, batch=B, precision=args.precision, device=dev, process_group=pg, seed_offset=rank,
-                        sync_bn=args.sync_bn)
+                        sync_bn=args.sync_bn, peer_allreduce=True if args.peer_allreduce else None)
 
     # synthetic inputs: several resident cycles so consecutive steps read different data
     NSETS = 3
@@ -642,6 +644,8 @@ def main():
                                f"(512x4 rolls, noise 128, latent 64, 4 emotion classes), per-GPU batch B={B}",
                    "per_gpu_batch": B, "rolls_per_step_per_gpu": K * B, "precision": args.precision,
                    "cuda_graph": use_graph, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "gradient_exchange": ("peer memory (NVLink P2P kernels, one graph per cycle)" if tr._peer is not None
+                                         else "NCCL all-reduce between two graphs per step") if world > 1 else "n/a",
                    "bn": ("sync (peer memory)" if tr.sync_bn else "local") if world > 1 else "n/a",
                    "l2": f"{NSETS} rotating input sets; per-step activation working set {tr.engine.workspace_bytes() / 1e6:.0f} MB >> 126 MB L2",
                    "algorithmic_mflop_per_roll": MFLOP_PER_ROLL},

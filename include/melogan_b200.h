@@ -322,6 +322,22 @@ int mg_act_dropout_backward(const float* dh, const float* z, const float* mask, 
 int mg_gan_sync_bn_export(mg_gan* ctx, int rank, int world, unsigned char* handle_out);
 int mg_gan_sync_bn_connect(mg_gan* ctx, const unsigned char* handles);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradient exchange of data parallelism over NVLink peer memory (the all-reduce torch DDP would add behind
+ * loss.backward(), reference src/gan/train_gan.py:203,247): in-place SUM over the ranks of one node (<= 8, one process per
+ * GPU) of a float32 vector, as three kernel launches on the caller's stream -- stage into the rank's CUDA-IPC exchange
+ * region, publish an epoch flag (system-scope release), wait for the peers' flags and add their staged copies in RANK order
+ * (bit-identical result on every rank).  No NCCL and no host synchronisation: graph-capturable.
+ *   mg_peer_create(rank, world, max_floats, &peer, handle[64]) on every rank; exchange the handles;
+ *   mg_peer_connect(peer, handles[world * 64]); then mg_peer_allreduce_sum(peer, data, n <= max_floats, stream), the same
+ *   sequence of calls on every rank.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mg_peer mg_peer;
+int mg_peer_create(int rank, int world, long long max_floats, mg_peer** out, unsigned char* handle_out);
+int mg_peer_connect(mg_peer* peer, const unsigned char* handles);
+int mg_peer_allreduce_sum(mg_peer* peer, float* data, long long n, void* stream);
+void mg_peer_destroy(mg_peer* peer);
+
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
 

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "mg_vae_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_vae_buffer": ([_vp, ctypes.c_char_p, _vp, _vp], _i),
     "mg_vae_loss_step": ([_vp, _vp, _vp, _d, _vp, _vp], _i),
+    "mg_peer_create": ([_i, _i, _ll, _vp, _vp], _i),
+    "mg_peer_connect": ([_vp, _vp], _i),
+    "mg_peer_allreduce_sum": ([_vp, _vp, _ll, _vp], _i),
+    "mg_peer_destroy": ([_vp], None),
     "mg_gan_sync_bn_export": ([_vp, _i, _i, _vp], _i),
     "mg_gan_sync_bn_connect": ([_vp, _vp], _i),
     "mg_linear_forward": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),

@@ -47,3 +47,55 @@ def broadcast_module_state_(modules, src=0, group=None):
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             dist.broadcast(t.data, src=src, group=group)
+
+
+class PeerAllReduce:
+    """The gradient exchange over NVLink peer memory (csrc/peer.cu, include/melogan_b200.h: mg_peer_*): in-place sum over the
+    ranks of one node as three kernel launches on the current stream -- no NCCL call and no host synchronisation, so a whole
+    data-parallel training cycle can be captured as ONE CUDA graph, and every rank gets bit-identical sums (rank-order
+    addition).  Collective constructor: the CUDA IPC handles of the exchange regions travel once through torch.distributed.
+    One node, <= 8 ranks, one process per GPU."""
+
+    def __init__(self, max_floats, group=None, device=None):
+        import ctypes
+        from . import _native
+        self._native, self._ct = _native, ctypes
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.world > 8:
+            raise ValueError("PeerAllReduce: at most 8 ranks (one NVSwitch node)")
+        self._h = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _native.call("mg_peer_create", self.rank, self.world, int(max_floats), ctypes.byref(self._h),
+                         ctypes.cast(handle, ctypes.c_void_p))
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=group)
+        blob = bytes(torch.cat(allh).cpu().tolist())
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        with torch.cuda.device(self.device):
+            _native.call("mg_peer_connect", self._h, ctypes.cast(buf, ctypes.c_void_p))
+        dist.barrier(group=group)                    # every rank has opened every region before the first exchange
+        self.max_floats = int(max_floats)
+
+    def allreduce_sum_(self, flat):
+        """In place; returns the factor that turns the sum into the mean (like allreduce_sum_)."""
+        if flat.dtype != torch.float32 or not flat.is_contiguous() or not flat.is_cuda:
+            raise ValueError("PeerAllReduce: contiguous float32 CUDA tensors")
+        with torch.cuda.device(self.device):
+            self._native.call("mg_peer_allreduce_sum", self._h, flat.data_ptr(), flat.numel(),
+                              torch.cuda.current_stream(self.device).cuda_stream)
+        return 1.0 / self.world
+
+    def close(self):
+        if self._h:
+            self._native.lib().mg_peer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

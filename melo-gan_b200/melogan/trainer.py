@@ -48,7 +48,7 @@ def weights_init(m):
 
 class GanTrainer:
     def __init__(self, cfg, ed_cfg, batch=None, precision="fp32", device=None, ed_state_dict=None,
-                 process_group=None, seed_offset=0, modules=None, sync_bn=False):
+                 process_group=None, seed_offset=0, modules=None, sync_bn=False, peer_allreduce=None):
         from src.gan.feature_encoder import FeatureEncoder
         from src.gan.models import Discriminator, Generator
         from src.emotion_discriminator.ed_model import EmotionDiscriminator
@@ -124,6 +124,14 @@ class GanTrainer:
         self.m_d = torch.empty(4, device=dev)
         self.m_g = torch.empty(2, device=dev)
         self._graph = None
+        # gradient exchange: NCCL all-reduce between two graphs per step (default), or kernels over NVLink peer memory
+        # (peer_allreduce=True / MELOGAN_PEER_ALLREDUCE=1: no NCCL in the step, the whole data-parallel cycle is ONE graph)
+        if peer_allreduce is None:
+            peer_allreduce = os.environ.get("MELOGAN_PEER_ALLREDUCE") == "1"
+        self._peer = None
+        if peer_allreduce and self.world > 1:
+            n = max(self.flat_g.grad.numel(), self.flat_d.grad.numel())
+            self._peer = D_.PeerAllReduce(n, group=self.pg, device=self.device)
 
     # ---- binding ----
     def rebind(self):
@@ -159,7 +167,9 @@ class GanTrainer:
             _native.check(L.mg_counter_add(ctr, 1, st))
 
     def _allreduce(self, flat):
-        if self.world > 1:
+        if self._peer is not None:
+            self._peer.allreduce_sum_(flat.grad)       # three kernels over NVLink peer memory (graph-capturable)
+        elif self.world > 1:
             D_.allreduce_sum_(flat.grad, self.pg)      # the 1/world factor is folded into Adam's grad_scale
 
     # ---- the two step bodies ----
@@ -227,11 +237,12 @@ class GanTrainer:
         # step copies its slice into the persistent buffer the native context reads
         self.s_conds = torch.zeros((K, B, self.cond_dim), device=dev) if self.cond_dim else None
         torch.cuda.synchronize(dev)
-        if self.world == 1:
+        if self.world == 1 or self._peer is not None:      # no NCCL in the step: the whole cycle is ONE graph
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.train_cycle(self.s_reals, self.s_numerics, self.s_labels, conds=self.s_conds)
             self._graph = g
+            self._one_graph = True
             return self.s_reals, self.s_numerics, self.s_labels
         pool = torch.cuda.graph_pool_handle()
         self._g_pre, self._g_post = [], []
@@ -267,7 +278,7 @@ class GanTrainer:
         return self.s_reals, self.s_numerics, self.s_labels
 
     def replay_cycle(self):
-        if self.world == 1:
+        if self.world == 1 or getattr(self, "_one_graph", False):
             self._graph.replay()
             return
         K = self.critic_iters

@@ -30,7 +30,7 @@ def _inputs(seed, B, cfg):
                 labels=torch.randint(0, 4, (B,), generator=g))
 
 
-def _worker(rank, world, port, one_graph, out):
+def _worker(rank, world, port, peer, out):
     for p in (ROOT, os.path.join(ROOT, "melo-gan_b200"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -48,8 +48,10 @@ def _worker(rank, world, port, one_graph, out):
     cfg["INTEGRATION_MODE"] = "numeric_only" if cfg.get("INTEGRATION_MODE") == "conditioning" else cfg.get("INTEGRATION_MODE")
     Bl = 8                                   # per-rank shard
     with contextlib.redirect_stdout(io.StringIO()):
-        tr = GanTrainer(cfg, ed_cfg, batch=Bl, precision="fp32", device=dev, process_group=dist.group.WORLD, seed_offset=rank)
+        tr = GanTrainer(cfg, ed_cfg, batch=Bl, precision="fp32", device=dev, process_group=dist.group.WORLD, seed_offset=rank,
+                        peer_allreduce=peer)
         ref = GanTrainer(cfg, ed_cfg, batch=Bl, precision="fp32", device=dev) if rank == 0 else None
+    assert (tr._peer is not None) == bool(peer)
     res = {}
     full = _inputs(5, Bl * world, cfg)
     mine = {k: v[rank * Bl:(rank + 1) * Bl].to(dev) for k, v in full.items()}
@@ -96,6 +98,7 @@ def _worker(rank, world, port, one_graph, out):
     torch.cuda.synchronize(dev)
     res["graph_vs_eager_d"] = float((tr.flat_d.data - eager_d).abs().max() / eager_d.abs().max())
     res["graph_vs_eager_g"] = float((tr.flat_g.data - eager_g).abs().max() / eager_g.abs().max())
+    res["one_graph"] = bool(getattr(tr, "_one_graph", False))
     ck = tr.state_dict()                                 # collective: BatchNorm running stats averaged over ranks
     rm = ck["G"]["decoder.deconv.1.running_mean"].clone()
     mx = rm.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -106,13 +109,13 @@ def _worker(rank, world, port, one_graph, out):
     dist.destroy_process_group()
 
 
-def _run(one_graph):
+def _run(peer):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29700 + os.getpid() % 200 + (50 if one_graph else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, one_graph, out)) for r in range(2)]
+    port = 29700 + os.getpid() % 200 + (50 if peer else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, peer, out)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -128,12 +131,20 @@ def _run(one_graph):
     assert res["param_spread_d"] == 0.0 and res["param_spread_g"] == 0.0 and res["g_grad_same_on_ranks"] == 0.0, res
     assert res["graph_vs_eager_d"] < 2e-3 and res["graph_vs_eager_g"] < 2e-3, res     # fp32 atomics + Adam on near-zero g
     assert res["bn_running_mean_spread"] == 0.0, res
+    assert res["one_graph"] == bool(peer), res           # peer-memory exchange: the whole data-parallel cycle is ONE graph
     return res
 
 
 @pytest.mark.timeout(600)
 def test_dp_two_gpus_gradients_and_captured_cycle():
     _run(False)
+
+
+@pytest.mark.timeout(600)
+def test_dp_two_gpus_gradient_exchange_over_peer_memory_one_graph():
+    """The same checks with the gradient all-reduce as kernels over NVLink peer memory (csrc/peer.cu) instead of NCCL: no
+    collective library call in the step, the data-parallel cycle is captured as ONE CUDA graph."""
+    _run(True)
 
 
 def _worker_syncbn(rank, world, port, precision, out):
