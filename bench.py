@@ -607,9 +607,17 @@ def main():
         # HBM-class kernels north_star names: fused Adam, the element-wise / reduction family, note extraction
         hbm = []
         pa = probe_family(L, 6, eager_cycle)
-        hbm.append(hbm_record("adam_kernel (fused Adam over the flat groups)", pa, peak_gbs, "28 B per parameter and step"))
+        hbm.append(hbm_record("adam_kernel (fused Adam over the flat groups)", pa, peak_gbs,
+                              "28 B per parameter and step; 5 launches on the critic's 0.27 M parameters (7.6 MB: latency-bound) + "
+                              "1 on the generator's 8.85 M (248 MB), see largest_group"))
+        try:       # the generator group alone: the one Adam launch that is large enough to be bandwidth-bound
+            pg_ = probe_family(L, 6, lambda: tr.generator_step(numerics[0][K - 1], labels))
+            hbm[-1]["largest_group"] = hbm_record("adam_kernel, generator + encoder group", pg_, peak_gbs, "8.85 M parameters")
+        except Exception as e:
+            hbm[-1]["largest_group"] = {"error": f"{type(e).__name__}: {e}"}
         pe = probe_family(L, 7, eager_cycle)
-        hbm.append(hbm_record("element-wise / reduction family (colreduce, BatchNorm apply + backward, pooling, row broadcast)",
+        hbm.append(hbm_record("element-wise / reduction family (remaining column sums, BatchNorm apply + backward, row broadcast x mask; pooling, bias-gradient sums and "
+                              "BatchNorm statistics now ride in the tap-GEMM epilogues)",
                               pe, peak_gbs, "one read (+ one write) of the activation per kernel"))
         extra["roofline_hbm"] = hbm
         try:
