@@ -246,3 +246,73 @@ def test_sync_batchnorm_over_peer_memory_equals_single_gpu_full_batch(precision)
     assert res["bn_err"] < (2e-5 if tight else 1e-3), res
     assert res["grad_err"] < (2e-4 if tight else 1.5e-1), res        # bf16: mask flips between a 16- and a 32-sample tiling
     assert res["graph_vs_eager_g"] < 2e-3, res
+
+
+def _worker_peer(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "melo-gan_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from melogan.dist import PeerAllReduce
+    sizes = [8848000, 272384, 4096 * world, 1000, 8848000, 12, 272384]      # both algorithms, odd tails, repeated epochs
+    peer = PeerAllReduce(max(sizes), device=dev)
+    worst, spread = 0.0, 0.0
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    for it, n in enumerate(sizes * 2):
+        x = torch.randn(n, generator=g, device=dev)
+        want = x.double().clone()
+        dist.all_reduce(want)
+        got = x.clone()
+        peer.allreduce_sum_(got)
+        worst = max(worst, float((got.double() - want).abs().max() / want.abs().max()))
+        mx, mn = got.clone(), got.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        spread = max(spread, float((mx - mn).abs().max()))
+    # inside a CUDA graph, replayed
+    x = torch.randn(sizes[0], generator=g, device=dev)
+    buf = x.clone()
+    torch.cuda.synchronize(dev)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        peer.allreduce_sum_(buf)
+    for _ in range(3):
+        buf.copy_(x)
+        gr.replay()
+    want = x.double().clone()
+    dist.all_reduce(want)
+    graph_err = float((buf.double() - want).abs().max() / want.abs().max())
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        out.put({"worst": worst, "spread": spread, "graph_err": graph_err})
+    dist.barrier()
+    peer.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_allreduce_equals_nccl(world):
+    """mg_peer_allreduce_sum (csrc/peer.cu) against NCCL's all-reduce in float64 on random vectors of the flat-gradient
+    sizes: 2 ranks take the read-everything form, 4 ranks the reduce-scatter + all-gather form; results must be bit-identical
+    on all ranks (rank-order sums), also from inside a replayed CUDA graph."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 30100 + os.getpid() % 90 + world
+    procs = [ctx.Process(target=_worker_peer, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(200)
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not alive, "peer all-reduce worker hung"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = out.get(timeout=10)
+    print(world, res)
+    assert res["worst"] < 2e-6 and res["graph_err"] < 2e-6 and res["spread"] == 0.0, res
