@@ -338,6 +338,29 @@ int mg_peer_connect(mg_peer* peer, const unsigned char* handles);
 int mg_peer_allreduce_sum(mg_peer* peer, float* data, long long n, void* stream);
 void mg_peer_destroy(mg_peer* peer);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone forms of the conv-type inner blocks (fused inside their parents on the hot path):
+ *   ConvBlock1D.forward, NotesEncoder.forward      reference src/emotion_discriminator/ed_model.py:24-69
+ *   GeneratorDecoder.forward (deconv stack)        reference src/gan/models.py:52-83
+ *   ConvEncoder.forward, ConvDecoder.forward       reference src/ae/model.py:9-48,64-98
+ * are chains of ONE float32 operator, the "conv unit": Conv1d (stride 1; or k5 s2 p2) or ConvTranspose1d (k5 s2 p2 op1)
+ * [+ BatchNorm1d in train or eval mode] + activation (0 none, 1 ReLU, 2 GELU, 3 Tanh), channels-last activations
+ * x [R][Lin][Cin] -> y [R][Lout][Cout], weights in the reference's layouts (Conv1d [Cout][Cin][ks], ConvTranspose1d
+ * [Cin][Cout][5]).  kind: 0 Conv1d, 1 ConvTranspose1d.  The forward also returns what the backward needs (z = pre-BatchNorm
+ * output, mean / invstd, the GELU derivative tile); the backward accumulates parameter gradients (+=).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mg_convunit mg_convunit;
+int mg_convunit_create(mg_convunit** out);
+void mg_convunit_destroy(mg_convunit* unit);
+int mg_convunit_forward(mg_convunit* unit, int kind, const float* x, const float* W, const float* bias, int R, int Lin, int Cin,
+                        int Cout, int ks, int stride, int pad, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, int train, int act, float* z, float* y, float* gd, float* mean, float* invstd,
+                        void* stream);
+int mg_convunit_backward(mg_convunit* unit, int kind, const float* x, const float* W, int R, int Lin, int Cin, int Cout, int ks,
+                         int stride, int pad, const float* gamma, int train, int act, const float* z, const float* y,
+                         const float* gd, const float* mean, const float* invstd, const float* dy, float* scratch0,
+                         float* scratch1, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta, void* stream);
+
 /* Stream-ordered copy between any two device/pinned-host pointers (cudaMemcpyDefault). */
 int mg_device_copy(void* dst, const void* src, long long nbytes, void* stream);
 

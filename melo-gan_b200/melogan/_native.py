@@ -78,6 +78,12 @@ _SIGNATURES = {
     "mg_peer_destroy": ([_vp], None),
     "mg_gan_sync_bn_export": ([_vp, _i, _i, _vp], _i),
     "mg_gan_sync_bn_connect": ([_vp, _vp], _i),
+    "mg_convunit_create": ([_vp], _i),
+    "mg_convunit_destroy": ([_vp], None),
+    "mg_convunit_forward": ([_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp,
+                             _vp, _vp], _i),
+    "mg_convunit_backward": ([_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mg_linear_forward": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "mg_linear_backward": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "mg_act_dropout_forward": ([_vp, _vp, _f, _i, _vp, _ll, _vp], _i),

@@ -128,3 +128,132 @@ def run_mlp(seq, x, training, masks=None):
         if act != ACT_NONE or mask is not None:
             x = act_dropout(x, act, mask, scale)
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conv-type inner blocks (include/melogan_b200.h: mg_convunit_*): Conv1d / ConvTranspose1d [+ BatchNorm1d] + activation
+# ---------------------------------------------------------------------------------------------------------------------
+UNIT_CONV, UNIT_CONVT = 0, 1
+UACT_NONE, UACT_RELU, UACT_GELU, UACT_TANH = 0, 1, 2, 3
+_units = {}
+
+
+def _unit(device):
+    import ctypes
+    key = torch.device(device).index
+    if key not in _units:
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _native.call("mg_convunit_create", ctypes.byref(h))
+        _units[key] = h
+    return _units[key]
+
+
+class _ConvUnitFn(torch.autograd.Function):
+    """y = act(BN(conv(x))) on channels-last x (R, Lin, Cin); conv: nn.Conv1d or nn.ConvTranspose1d; bn: nn.BatchNorm1d or None"""
+
+    @staticmethod
+    def forward(ctx, x, W, b, gamma, beta, conv, bn, act):
+        _need_cuda(x, "conv unit")
+        transposed = isinstance(conv, nn.ConvTranspose1d)
+        ks, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if conv.dilation[0] != 1 or conv.groups != 1:
+            raise NotImplementedError("conv unit: dilation 1, groups 1")
+        if transposed and (ks, stride, pad, conv.output_padding[0]) != (5, 2, 2, 1):
+            raise NotImplementedError("conv unit: ConvTranspose1d k5 s2 p2 output_padding 1")
+        if not transposed and not ((stride == 1 and 2 * pad == ks - 1) or (ks, stride, pad) == (5, 2, 2)):
+            raise NotImplementedError("conv unit: Conv1d stride 1 'same' padding, or k5 s2 p2")
+        xc = x.detach().to(torch.float32).contiguous()
+        R, Lin, Cin = xc.shape
+        Cout = conv.out_channels
+        Lout = 2 * Lin if transposed else Lin // stride
+        Wc = W.detach().to(torch.float32).contiguous()
+        dev = x.device
+        z = torch.empty((R, Lout, Cout), device=dev)
+        y = torch.empty_like(z)
+        gd = torch.empty_like(z) if act == UACT_GELU else None
+        mean = torch.empty(Cout, device=dev) if bn is not None else None
+        invstd = torch.empty(Cout, device=dev) if bn is not None else None
+        train = bool(bn is not None and bn.training)
+        if bn is not None and (not bn.track_running_stats or bn.momentum is None or abs(bn.momentum - 0.1) > 1e-12
+                               or abs(bn.eps - 1e-5) > 1e-12):
+            raise NotImplementedError("conv unit: BatchNorm1d(eps=1e-5, momentum=0.1, track_running_stats=True)")
+        p = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            _native.call("mg_convunit_forward", _unit(dev), UNIT_CONVT if transposed else UNIT_CONV, xc.data_ptr(), Wc.data_ptr(),
+                         p(b.detach().contiguous() if b is not None else None), R, Lin, Cin, Cout, ks, stride, pad,
+                         p(gamma.detach() if gamma is not None else None), p(beta.detach() if beta is not None else None),
+                         p(bn.running_mean if bn is not None else None), p(bn.running_var if bn is not None else None),
+                         int(train), int(act), z.data_ptr(), y.data_ptr(), p(gd), p(mean), p(invstd), _stream(x))
+        if train:
+            bn.num_batches_tracked += 1
+        ctx.save_for_backward(xc, Wc, z, y, gd, mean, invstd, gamma.detach() if gamma is not None else None)
+        ctx.meta = (transposed, ks, stride, pad, int(act), train, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, Wc, z, y, gd, mean, invstd, gamma = ctx.saved_tensors
+        transposed, ks, stride, pad, act, train, has_bias = ctx.meta
+        R, Lin, Cin = xc.shape
+        Cout = y.shape[2]
+        dev = xc.device
+        dyc = dy.detach().to(torch.float32).contiguous()
+        s0, s1 = torch.empty_like(y), torch.empty_like(y)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        dW = torch.zeros_like(Wc)
+        db = torch.zeros(Cout, device=dev) if has_bias else None
+        dgamma = torch.zeros(Cout, device=dev) if gamma is not None else None
+        dbeta = torch.zeros(Cout, device=dev) if gamma is not None else None
+        p = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            _native.call("mg_convunit_backward", _unit(dev), UNIT_CONVT if transposed else UNIT_CONV, xc.data_ptr(), Wc.data_ptr(),
+                         R, Lin, Cin, Cout, ks, stride, pad, p(gamma), int(train), act, z.data_ptr(), y.data_ptr(), p(gd),
+                         p(mean), p(invstd), dyc.data_ptr(), s0.data_ptr(), s1.data_ptr(), p(dx), dW.data_ptr(), p(db),
+                         p(dgamma), p(dbeta), _stream(xc))
+        return dx, dW, db, dgamma, dbeta, None, None, None
+
+
+def conv_unit(x_cl, conv, bn=None, act=UACT_NONE):
+    """Channels-last (R, L, C) in and out."""
+    return _ConvUnitFn.apply(x_cl, conv.weight, conv.bias, bn.weight if bn is not None else None,
+                             bn.bias if bn is not None else None, conv, bn, act)
+
+
+_UACT_OF = {nn.ReLU: UACT_RELU, nn.GELU: UACT_GELU, nn.Tanh: UACT_TANH}
+
+
+def run_conv_stack(seq, x_cl):
+    """Runs an nn.Sequential of [Conv1d | ConvTranspose1d] [BatchNorm1d] [ReLU | GELU | Tanh] groups (the reference's conv
+    stacks) on channels-last activations (R, L, C); nested nn.Sequential / ConvBlock1D-style children (a module with a
+    `.net` Sequential) are flattened."""
+    mods = []
+
+    def flat(m):
+        for c in m:
+            inner = getattr(c, "net", None)
+            if isinstance(c, nn.Sequential):
+                flat(c)
+            elif isinstance(inner, nn.Sequential):
+                flat(inner)
+            else:
+                mods.append(c)
+    flat(seq)
+    i = 0
+    while i < len(mods):
+        conv = mods[i]
+        if not isinstance(conv, (nn.Conv1d, nn.ConvTranspose1d)):
+            raise NotImplementedError(f"no native operator for {type(conv).__name__} in a stand-alone conv stack")
+        i += 1
+        bn = None
+        if i < len(mods) and isinstance(mods[i], nn.BatchNorm1d):
+            bn = mods[i]
+            i += 1
+        act = UACT_NONE
+        if i < len(mods) and type(mods[i]) in _UACT_OF:
+            if isinstance(mods[i], nn.GELU) and getattr(mods[i], "approximate", "none") != "none":
+                raise NotImplementedError("tanh-approximated GELU")
+            act = _UACT_OF[type(mods[i])]
+            i += 1
+        x_cl = conv_unit(x_cl, conv, bn, act)
+    return x_cl

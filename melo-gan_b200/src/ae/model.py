@@ -9,6 +9,7 @@ reference draws it (model.py:127-133), so the torch RNG stream is the reference'
 import torch
 import torch.nn as nn
 
+from melogan import blocks as B_
 from melogan import engine as E
 from melogan import runtime as R
 
@@ -48,16 +49,25 @@ class ConvEncoder(nn.Module):
         self._linear = nn.Sequential(nn.Flatten(), nn.Linear(128 * length, self.hidden_dim), nn.ReLU(inplace=True)).to(device)
 
     def forward(self, x):
-        """Stand-alone use only materialises `_linear` (what the reference's dummy pass at train_ae.py:75-77 is for) and
-        returns None; the hidden state itself is computed inside VAE.forward's single native call."""
+        """Stand-alone call (VAE.forward computes the hidden state inside its single native call): (B, MAX_NOTES, 4) ->
+        (B, hidden_dim) on the native conv units / Linear of melogan.blocks, with full backward.  The first call also
+        materialises `_linear`; in train mode build_linear's own pass over zeros (reference model.py:27-36) updates the
+        BatchNorm running statistics once more, as the reference's does.  CPU tensors: only the reference's zero dummy pass
+        (train_ae.py:75-77) is supported -- it creates `_linear`, updates the running statistics and returns None."""
         first = self._linear is None
         if first:
             self.build_linear(x.shape[1])
-        if torch.is_grad_enabled() and x.requires_grad:
-            raise NotImplementedError("ConvEncoder runs fused inside VAE.forward on the CUDA path")
-        if self.training and not bool(x.any()):
-            self._dummy_pass_running_stats(2 if first else 1)
-        return None
+        if not x.is_cuda:
+            if bool(x.any()) or (torch.is_grad_enabled() and x.requires_grad):
+                raise RuntimeError("ConvEncoder: CUDA tensors only (the B200 path has no CPU fallback)")
+            if self.training:
+                self._dummy_pass_running_stats(2 if first else 1)
+            return None
+        if first and self.training:
+            self._dummy_pass_running_stats(1)
+        y = B_.run_conv_stack(self.conv, x)                          # channels-last (B, L, 128): no permute needed
+        flat = y.permute(0, 2, 1).reshape(y.shape[0], -1)            # channel-major, like y.view(B, -1) on (B, C, L)
+        return B_.run_mlp(nn.Sequential(*list(self._linear)[1:]), flat, self.training)
 
     @torch.no_grad()
     def _dummy_pass_running_stats(self, passes):
@@ -97,7 +107,19 @@ class ConvDecoder(nn.Module):
                                     nn.ConvTranspose1d(32, out_channels, **up), nn.Tanh())
 
     def forward(self, z):
-        raise NotImplementedError("ConvDecoder runs fused inside VAE.forward on the CUDA path")
+        """Stand-alone call (VAE.forward runs this block fused): (B, latent) -> (B, max_notes, 4) on the native operators of
+        melogan.blocks: the Linear stack, view (B, 128, L0), the transposed-conv units and Tanh on channels-last
+        activations, trimmed / zero-padded to max_notes like the reference (model.py:76-98)."""
+        y = B_.run_mlp(self.pre, z, self.training)
+        L0 = y.shape[1] // 128
+        x = y[:, :128 * L0].reshape(y.shape[0], 128, L0).permute(0, 2, 1)
+        out = B_.run_conv_stack(self.deconv, x)
+        T = out.shape[1]
+        if T > self.max_notes:
+            out = out[:, :self.max_notes]
+        elif T < self.max_notes:
+            out = nn.functional.pad(out, (0, 0, 0, self.max_notes - T))
+        return out
 
 
 class _VaeFn(torch.autograd.Function):

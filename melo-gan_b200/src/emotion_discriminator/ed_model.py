@@ -26,7 +26,9 @@ class ConvBlock1D(nn.Module):
         self.net = nn.Sequential(nn.Conv1d(in_ch, out_ch, kernel_size, stride, padding), nn.BatchNorm1d(out_ch), nn.GELU())
 
     def forward(self, x):
-        raise NotImplementedError("ConvBlock1D runs fused inside EmotionDiscriminator.forward on the CUDA path")
+        """Stand-alone call (the emotion discriminator runs its blocks fused): (B, C_in, T) -> (B, C_out, T) on the native
+        conv unit of melogan.blocks (Conv1d + BatchNorm1d + GELU, train or eval, full backward)."""
+        return B_.run_conv_stack(self.net, x.permute(0, 2, 1)).permute(0, 2, 1)
 
 
 class NotesEncoder(nn.Module):
@@ -44,7 +46,10 @@ class NotesEncoder(nn.Module):
         self.project = nn.Linear(c_in, hidden_dim)
 
     def forward(self, notes):
-        raise NotImplementedError("NotesEncoder runs fused inside EmotionDiscriminator.forward on the CUDA path")
+        """Stand-alone call: (B, T, note_dim) -> (B, hidden_dim).  The notes are already channels-last, so the reference's
+        permute (ed_model.py:63-64) disappears; conv units, mean over the note axis, projection."""
+        x = B_.run_conv_stack(self.conv, notes)
+        return B_.linear(x.mean(dim=1), self.project.weight, self.project.bias)
 
 
 class MLPClassifier(nn.Module):

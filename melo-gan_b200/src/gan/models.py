@@ -50,8 +50,17 @@ class GeneratorDecoder(nn.Module):
         return B_.run_mlp(self.pre, latent, self.training).view(-1, 256, self.reduced_len)
 
     def forward(self, latent):
-        raise NotImplementedError("GeneratorDecoder's transposed-conv stack runs fused inside Generator.forward on the "
-                                  "CUDA path (pre_forward gives the Linear stack alone); call the Generator")
+        """Stand-alone call (the Generator runs this block fused): (B, latent) -> (B, max_notes, out_channels) on the native
+        operators of melogan.blocks -- the Linear stack, then the three transposed-conv units on channels-last activations
+        (models.py:66-83; the reference's final permute back to (B, T, C) is the layout the units already produce)."""
+        x = self.pre_forward(latent).permute(0, 2, 1)             # (B, reduced_len, 256) channels-last
+        out = B_.run_conv_stack(self.deconv, x)
+        T = out.shape[1]
+        if T > self.max_notes:
+            out = out[:, :self.max_notes]
+        elif T < self.max_notes:
+            out = torch.nn.functional.pad(out, (0, 0, 0, self.max_notes - T))
+        return out
 
 
 class _GeneratorFn(torch.autograd.Function):

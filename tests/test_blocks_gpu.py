@@ -77,8 +77,6 @@ def test_generator_decoder_pre_standalone():
     assert out.shape == (7, 256, 8)
     ref = _ref_mlp(m.pre, x.double(), None, False).view(-1, 256, 8)
     assert_close(out, ref, 1e-5, "GeneratorDecoder.pre")
-    with pytest.raises(NotImplementedError):
-        m(x)
 
 
 @pytest.mark.parametrize("training", [True, False])
@@ -125,3 +123,118 @@ def test_cpu_tensor_raises():
     from src.gan.models import NoiseToLatent
     with pytest.raises(RuntimeError):
         NoiseToLatent(8, 4, hidden=16)(torch.zeros(2, 8))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conv-type inner blocks on the native conv unit (mg_convunit_*), against the SAME nn layers run by stock torch in float64
+# ---------------------------------------------------------------------------------------------------------------------
+import copy
+
+
+def _check_grads(mod, twin, skip=()):
+    for (k, p), (_, q) in zip(mod.named_parameters(), twin.named_parameters()):
+        if any(s in k for s in skip):
+            continue                                     # conv bias in front of a train-mode BatchNorm: exact gradient 0
+        assert p.grad is not None, k
+        assert_close(p.grad, q.grad, 1e-4, "d" + k)
+
+
+def _buffers_close(mod, twin):
+    for (k, b), (_, c) in zip(mod.named_buffers(), twin.named_buffers()):
+        if k.endswith("num_batches_tracked"):
+            assert int(b) == int(c), k
+        else:
+            assert_close(b, c, 2e-5, k)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_conv_block_1d_standalone(training):
+    from src.emotion_discriminator.ed_model import ConvBlock1D
+    torch.manual_seed(11)
+    m = ConvBlock1D(64, 128, kernel_size=3, padding=1).cuda().train(training)
+    with torch.no_grad():
+        m.net[1].running_mean.normal_(0, 0.1); m.net[1].running_var.uniform_(0.5, 1.5)
+        m.net[1].weight.uniform_(0.5, 1.5); m.net[1].bias.normal_(0, 0.1)
+    twin = copy.deepcopy(m).double()
+    x = torch.randn(6, 64, 96, device="cuda", requires_grad=True)
+    xd = x.detach().double().requires_grad_(True)
+    y, yd = m(x), twin.net(xd)
+    assert y.shape == (6, 128, 96)
+    assert_close(y, yd, 1e-5, "ConvBlock1D forward")
+    w = torch.randn_like(y)
+    (y * w).sum().backward(); (yd * w.double()).sum().backward()
+    assert_close(x.grad, xd.grad, 5e-5, "ConvBlock1D input gradient")
+    _check_grads(m, twin, skip=("net.0.bias",) if training else ())
+    _buffers_close(m, twin)
+
+
+def test_notes_encoder_standalone():
+    from src.emotion_discriminator.ed_model import NotesEncoder
+    torch.manual_seed(12)
+    m = NotesEncoder(note_dim=4, hidden_dim=256, num_blocks=4).cuda().train()
+    twin = copy.deepcopy(m).double()
+    notes = (torch.rand(5, 128, 4, device="cuda") * 2 - 1).requires_grad_(True)
+    nd = notes.detach().double().requires_grad_(True)
+    y = m(notes)
+    t = nd.permute(0, 2, 1)
+    for blk in twin.conv:                                 # stock torch layers of each block (blk.forward is the native path)
+        t = blk.net(t)
+    yd = twin.project(twin.pool(t).squeeze(-1))
+    assert_close(y, yd, 2e-5, "NotesEncoder forward")
+    w = torch.randn_like(y)
+    (y * w).sum().backward(); (yd * w.double()).sum().backward()
+    assert_close(notes.grad, nd.grad, 2e-4, "NotesEncoder input gradient")
+    _check_grads(m, twin, skip=("net.0.bias",))
+    _buffers_close(m, twin)
+
+
+def test_generator_decoder_standalone():
+    from src.gan.models import GeneratorDecoder
+    torch.manual_seed(13)
+    m = GeneratorDecoder(latent_dim=64, max_notes=64, out_channels=4).cuda().train()
+    twin = copy.deepcopy(m).double()
+    z = torch.randn(9, 64, device="cuda", requires_grad=True)
+    zd = z.detach().double().requires_grad_(True)
+    y = m(z)
+    yd = twin.deconv(twin.pre(zd).view(9, 256, 8)).permute(0, 2, 1)
+    assert y.shape == (9, 64, 4)
+    assert_close(y, yd, 2e-5, "GeneratorDecoder forward")
+    w = torch.randn_like(y)
+    (y * w).sum().backward(); (yd * w.double()).sum().backward()
+    assert_close(z.grad, zd.grad, 2e-4, "GeneratorDecoder input gradient")
+    _check_grads(m, twin, skip=("deconv.0.bias", "deconv.3.bias"))
+    _buffers_close(m, twin)
+
+
+def test_vae_conv_encoder_and_decoder_standalone():
+    from src.ae.model import ConvDecoder, ConvEncoder
+    torch.manual_seed(14)
+    enc = ConvEncoder(in_channels=4, latent_dim=8, hidden_dim=64).cuda().train()
+    with torch.no_grad():
+        enc(torch.zeros(1, 64, 4, device="cuda"))            # the reference's dummy pass: creates _linear, 2 BN updates
+    assert int(enc.conv[1].num_batches_tracked) == 2
+    twin = copy.deepcopy(enc).double()
+    x = (torch.rand(7, 64, 4, device="cuda") * 2 - 1).requires_grad_(True)
+    xd = x.detach().double().requires_grad_(True)
+    h = enc(x)
+    hd = twin._linear(twin.conv(xd.permute(0, 2, 1)))
+    assert_close(h, hd, 2e-5, "ConvEncoder forward")
+    w = torch.randn_like(h)
+    (h * w).sum().backward(); (hd * w.double()).sum().backward()
+    assert_close(x.grad, xd.grad, 2e-4, "ConvEncoder input gradient")
+    _check_grads(enc, twin, skip=("conv.0.bias", "conv.3.bias", "conv.6.bias"))
+    _buffers_close(enc, twin)
+
+    dec = ConvDecoder(out_channels=4, max_notes=64, latent_dim=8, hidden_dim=64).cuda().train()
+    twin = copy.deepcopy(dec).double()
+    z = torch.randn(7, 8, device="cuda", requires_grad=True)
+    zd = z.detach().double().requires_grad_(True)
+    y = dec(z)
+    yd = twin.deconv(twin.pre(zd).view(7, 128, 8)).permute(0, 2, 1)
+    assert y.shape == (7, 64, 4)
+    assert_close(y, yd, 2e-5, "ConvDecoder forward")
+    w = torch.randn_like(y)
+    (y * w).sum().backward(); (yd * w.double()).sum().backward()
+    assert_close(z.grad, zd.grad, 2e-4, "ConvDecoder input gradient")
+    _check_grads(dec, twin, skip=("deconv.0.bias", "deconv.3.bias"))
+    _buffers_close(dec, twin)
