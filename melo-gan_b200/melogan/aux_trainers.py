@@ -196,6 +196,9 @@ class EdTrainer(_StepGraph):
         self.model = (model if model is not None else EmotionDiscriminator(cfg)).to(self.device)
         if self.model.input_mode != 'notes':
             raise NotImplementedError("EdTrainer: input_mode 'notes' (config/ed_config.yaml)")
+        if getattr(self.model, "use_sn", False):
+            raise NotImplementedError("EdTrainer: the fused step binds raw weights; a spectral-norm model trains through "
+                                      "model(x) (unfused block operators) and a torch optimizer")
         self.model.train()
         named = dict(self.model.named_parameters())
         self.flat = FlatParams([named[k] for k in E.ED_GRAD_KEYS])

@@ -83,6 +83,16 @@ class _ActDropoutFn(torch.autograd.Function):
         return dz, None, None, None
 
 
+def effective_weight(m, x):
+    """The weight a layer would use in its own forward.  torch.nn.utils.spectral_norm (what the reference applies when
+    use_spectral_norm is set, ed_model.py:29-33,81-86) recomputes `weight` = weight_orig / sigma in a forward PRE-HOOK (one
+    power iteration in train mode); the native operators never call the layer, so its pre-hooks are run here.  The returned
+    tensor carries the autograd graph back to weight_orig."""
+    for hook in m._forward_pre_hooks.values():
+        hook(m, (x,))
+    return m.weight
+
+
 def linear(x, W, b=None):
     return _LinearFn.apply(x, W, b)
 
@@ -103,7 +113,7 @@ def run_mlp(seq, x, training, masks=None):
     while i < len(mods):
         m = mods[i]
         if isinstance(m, nn.Linear):
-            x = linear(x, m.weight, m.bias)
+            x = linear(x, effective_weight(m, x), m.bias)
             i += 1
             continue
         act = ACT_NONE
@@ -216,7 +226,7 @@ class _ConvUnitFn(torch.autograd.Function):
 
 def conv_unit(x_cl, conv, bn=None, act=UACT_NONE):
     """Channels-last (R, L, C) in and out."""
-    return _ConvUnitFn.apply(x_cl, conv.weight, conv.bias, bn.weight if bn is not None else None,
+    return _ConvUnitFn.apply(x_cl, effective_weight(conv, x_cl), conv.bias, bn.weight if bn is not None else None,
                              bn.bias if bn is not None else None, conv, bn, act)
 
 

@@ -21,9 +21,11 @@ from melogan import runtime as R
 class ConvBlock1D(nn.Module):
     def __init__(self, in_ch, out_ch, kernel_size=3, stride=1, padding=1, use_sn=False):
         super().__init__()
-        if use_sn:
-            raise NotImplementedError("use_spectral_norm is false in config/ed_config.yaml; no CUDA kernel for it")
-        self.net = nn.Sequential(nn.Conv1d(in_ch, out_ch, kernel_size, stride, padding), nn.BatchNorm1d(out_ch), nn.GELU())
+        conv = nn.Conv1d(in_ch, out_ch, kernel_size, stride, padding)
+        if use_sn:                           # same wrapper, same state_dict keys (weight_orig, weight_u, weight_v) as the reference
+            from torch.nn.utils import spectral_norm
+            conv = spectral_norm(conv)
+        self.net = nn.Sequential(conv, nn.BatchNorm1d(out_ch), nn.GELU())
 
     def forward(self, x):
         """Stand-alone call (the emotion discriminator runs its blocks fused): (B, C_in, T) -> (B, C_out, T) on the native
@@ -55,11 +57,13 @@ class NotesEncoder(nn.Module):
 class MLPClassifier(nn.Module):
     def __init__(self, in_dim: int, hidden_dims=(256, 128), n_classes: int = 4, dropout: float = 0.2, use_sn: bool = False):
         super().__init__()
-        if use_sn:
-            raise NotImplementedError("use_spectral_norm is false in config/ed_config.yaml; no CUDA kernel for it")
         stack, width = [], in_dim
         for h in hidden_dims:
-            stack += [nn.Linear(width, h), nn.GELU(), nn.Dropout(dropout)]
+            lin = nn.Linear(width, h)
+            if use_sn:
+                from torch.nn.utils import spectral_norm
+                lin = spectral_norm(lin)
+            stack += [lin, nn.GELU(), nn.Dropout(dropout)]
             width = h
         self.net = nn.Sequential(*stack)
         self.head = nn.Linear(width, n_classes)
@@ -67,7 +71,8 @@ class MLPClassifier(nn.Module):
     def forward(self, x, masks=None):
         """Stand-alone call, and the whole model when input_mode is 'latent' (ed_model.py:128-136): Linear -> GELU ->
         Dropout per hidden layer, then the head, on the native operators of melogan.blocks with full backward."""
-        return B_.linear(B_.run_mlp(self.net, x, self.training, masks), self.head.weight, self.head.bias)
+        h = B_.run_mlp(self.net, x, self.training, masks)
+        return B_.linear(h, B_.effective_weight(self.head, h), self.head.bias)
 
 
 class _EmotionFn(torch.autograd.Function):
@@ -163,6 +168,10 @@ class EmotionDiscriminator(nn.Module):
             return self.classifier(x, masks)          # 'latent' mode IS the MLP classifier (ed_model.py:156-160)
         if x.dim() != 3:
             raise ValueError(f"Expected notes input shape (B, T, note_dim), got {x.shape}")
+        if self.use_sn:
+            # spectral norm (off in config/ed_config.yaml): the fused kernels bind raw weights, so this variant runs unfused on the
+            # stand-alone block operators (conv units + Linears), whose weights come through the spectral-norm pre-hooks
+            return self.classifier(self.encoder(x), masks)
         if self.training:
             keep = 1.0 - self.dropout
             B, dev = x.shape[0], x.device

@@ -238,3 +238,44 @@ def test_vae_conv_encoder_and_decoder_standalone():
     assert_close(z.grad, zd.grad, 2e-4, "ConvDecoder input gradient")
     _check_grads(dec, twin, skip=("deconv.0.bias", "deconv.3.bias"))
     _buffers_close(dec, twin)
+
+
+def test_emotion_discriminator_with_spectral_norm():
+    """use_spectral_norm: true (reference ed_model.py:29-33,81-86: torch.nn.utils.spectral_norm on every Conv1d / hidden
+    Linear): same wrapper and state_dict keys; runs unfused on the block operators.  Against the same layers run by stock
+    torch in float64 from the same power-iteration state."""
+    from src.emotion_discriminator.ed_model import EmotionDiscriminator
+    torch.manual_seed(21)
+    cfg = {"input_mode": "notes", "note_dim": 4, "notes_hidden": 256, "notes_blocks": 4, "mlp_hidden": [256, 128], "n_classes": 4,
+           "dropout": 0.2, "use_spectral_norm": True}
+    m = EmotionDiscriminator(cfg).cuda().train()
+    keys = set(m.state_dict())
+    assert "encoder.conv.0.net.0.weight_orig" in keys and "encoder.conv.0.net.0.weight_u" in keys
+    assert "classifier.net.0.weight_orig" in keys and "classifier.head.weight" in keys
+    twin = copy.deepcopy(m).double()
+    B = 6
+    x = (torch.rand(B, 64, 4, device="cuda") * 2 - 1).requires_grad_(True)
+    xd = x.detach().double().requires_grad_(True)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    masks = [(torch.rand((B, h), generator=g, device="cuda") < 0.8).float() for h in (256, 128)]
+    y = m(x, masks=masks)
+    t = xd.permute(0, 2, 1)
+    for blk in twin.encoder.conv:
+        t = blk.net(t)
+    f = twin.encoder.project(twin.encoder.pool(t).squeeze(-1))
+    h = f
+    for i, mk in zip((0, 3), masks):
+        h = F.gelu(twin.classifier.net[i](h)) * mk.double() / 0.8
+    yd = twin.classifier.head(h)
+    assert_close(y, yd, 5e-5, "spectral-norm ED logits")
+    w = torch.randn_like(y)
+    (y * w).sum().backward(); (yd * w.double()).sum().backward()
+    assert_close(x.grad, xd.grad, 5e-4, "spectral-norm ED input gradient")
+    for (k, p), (_, q) in zip(m.named_parameters(), twin.named_parameters()):
+        if k.endswith("net.0.bias") and "encoder" in k:
+            continue
+        assert p.grad is not None, k
+        assert_close(p.grad, q.grad, 5e-4, "d" + k)
+    for (k, b), (_, c) in zip(m.named_buffers(), twin.named_buffers()):
+        if k.endswith(("weight_u", "weight_v")):
+            assert_close(b, c, 1e-4, k)                  # the power iteration advanced identically
