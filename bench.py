@@ -386,6 +386,53 @@ def parity_check(tr, cfg, ed_cfg, reals, numerics, labels, dev):
     return rec
 
 
+def fp32_tc_record(cfg, ed_cfg, dev, B=2048, cycles=3):
+    """The fp32 parity mode (1e-5 against the oracle) with its contractions on the CUDA cores (default) and as six bf16
+    tensor-core terms per product (mg_debug_set("fp32_tc", 1): float32 operands split exactly into three bf16 parts, the same
+    tcgen05 kernels as bf16 mode, fp32 TMEM accumulation): eager cycles of 5 critic + 1 generator step at per-GPU batch B,
+    identical parameters and inputs, losses of the first cycle compared."""
+    import ctypes
+    import torch
+    from melogan import _native
+    from melogan.trainer import GanTrainer
+    L = _native.lib()
+    L.mg_debug_set.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    K = int(cfg.get("CRITIC_ITERS", 5))
+    T, F = cfg["MAX_NOTES"], cfg.get("NUMERIC_INPUT_DIM", 6)
+    g = torch.Generator(device=dev).manual_seed(99)
+    reals = torch.rand((K, B, T, 4), generator=g, device=dev) * 2 - 1
+    numerics = torch.randn((K, B, F), generator=g, device=dev)
+    numerics[..., 5] = 0.0
+    labels = (torch.arange(B, device=dev) % 4).to(torch.int64)
+    rec = {"per_gpu_batch": B, "cycles_timed": cycles}
+    import contextlib
+    for name, on in (("cuda_cores", 0), ("tensor_cores_bf16x6", 1)):
+        L.mg_debug_set(b"fp32_tc", on)
+        try:
+            torch.manual_seed(4321)
+            with contextlib.redirect_stdout(sys.stderr):
+                tr = GanTrainer(cfg, ed_cfg, batch=B, precision="fp32", device=dev, seed_offset=0)
+            tr.train_cycle(reals, numerics, labels)              # also the lazily allocated scratch
+            torch.cuda.synchronize(dev)
+            first = [float(x) for x in tr.loss_acc.cpu()]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(cycles):
+                tr.train_cycle(reals, numerics, labels)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / cycles
+            rec[name] = {"ms_per_cycle": ms, "rolls_per_s": K * B / (ms * 1e-3), "first_cycle_loss_sums": first}
+            tr.engine.close()
+        finally:
+            L.mg_debug_set(b"fp32_tc", -1)
+        torch.cuda.empty_cache()
+    a, b = rec["tensor_cores_bf16x6"]["first_cycle_loss_sums"], rec["cuda_cores"]["first_cycle_loss_sums"]
+    rec["max_rel_diff_of_losses"] = max(abs(x - y) / max(abs(y), 1e-3) for x, y in zip(a, b))
+    rec["speedup"] = rec["cuda_cores"]["ms_per_cycle"] / rec["tensor_cores_bf16x6"]["ms_per_cycle"]
+    return rec
+
+
 def stock_torch_yardstick(dev, B, budget_cycles=3):
     """The reference modules run by stock PyTorch eager (cuDNN / cuBLAS) on THIS GPU, same cycle, same batch:
     the "reference's Blackwell kernels" this framework has to beat (SURVEY.md 8d / BASELINE.md 3.4)."""
@@ -639,6 +686,10 @@ def main():
                 extra["stock_torch_eager_same_gpu"] = stock_torch_yardstick(dev, B)
             except Exception as e:
                 extra["stock_torch_eager_same_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"}
+        try:       # last: an opt-in kernel path; nothing after it depends on the device
+            extra["fp32_mode"] = fp32_tc_record(cfg, ed_cfg, dev)
+        except Exception as e:
+            extra["fp32_mode"] = {"error": f"{type(e).__name__}: {e}"}
 
     rolls_per_step = K * B * world
     value = rolls_per_step / (ms_dev / args.steps * 1e-3)

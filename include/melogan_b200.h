@@ -420,7 +420,8 @@ int mg_debug_layer_run(const mg_debug_layer* layer, void* stream);
 /* Kernel-selection overrides of the harness: "force_bn" (64/128), "max_stages", "staging_bufs" (1/2), "no_ws",
  * "dbg" (ablation bits, -1 = off), "reverse" (-1 = alternate), "no_tma_store", "no_tma_mask", "no_reuse", "no_pair"
  * (never the CTA-pair cta_group::2 kernel), "no_rot", "no_fuse" (bits: 1 no pooling, 2 no column sums, 4 no BatchNorm statistics in
- * the epilogues);
+ * the epilogues), "fp32_tc" (1 = float32 contractions of the fp32 parity mode as six bf16 tensor-core terms -- every float32
+ * operand is split exactly into three bf16 parts -- instead of CUDA-core FFMA; 0 = off; -1 = MELOGAN_FP32_TC, default off);
  * "reset" restores the product heuristics.  Returns MG_ERR_INVALID for an unknown key. */
 int mg_debug_set(const char* key, int value);
 /* One line describing the last tensor-core launch of this thread (kernel variant, grid, stages, ...); "" if the

@@ -103,6 +103,7 @@ extern "C" int mg_debug_set(const char* key, int value) {
     if (!strcmp(key, "no_ws")) { t.no_ws = value; return MG_OK; }
     if (!strcmp(key, "no_pair")) { t.no_pair = value; return MG_OK; }
     if (!strcmp(key, "no_rot")) { t.no_rot = value; return MG_OK; }
+    if (!strcmp(key, "fp32_tc")) { t.fp32_tc = value; return MG_OK; }
     if (!strcmp(key, "no_fuse")) { t.no_fuse = value; return MG_OK; }
     if (!strcmp(key, "ring2_stages")) { t.ring2_stages = value; return MG_OK; }
     if (!strcmp(key, "dbg")) { t.dbg = value; return MG_OK; }
@@ -118,13 +119,13 @@ extern "C" const char* mg_debug_last_launch(void) {
     const tc::LaunchInfo& li = tc::last_launch();
     if (li.kind == 0) { g_line[0] = 0; return g_line; }
     if (li.kind == 2)
-        snprintf(g_line, sizeof(g_line), "tc_wgrad rows=%lld N=%d K=%d taps=%d BNK=%d splits=%d flops=%.6e bytes=%.6e", li.rows,
-                 li.N, li.K, li.taps, li.BN, li.splits, li.flops, li.bytes);
+        snprintf(g_line, sizeof(g_line), "tc_wgrad rows=%lld N=%d K=%d taps=%d BNK=%d splits=%d fp32x6=%d flops=%.6e bytes=%.6e", li.rows,
+                 li.N, li.K, li.taps, li.BN, li.splits, li.fp32x6, li.flops, li.bytes);
     else
         snprintf(g_line, sizeof(g_line),
                  "tc_tap rows=%lld N=%d K=%d taps=%d groups=%d halo=%d BN=%d out%d ws=%d stages=%d act=%d mul=%d aux=%d "
-                 "tma_store=%d tma_mask=%d nsb=%d reverse=%d grid=%dx%d tf32=%d pair=%d pool=%d flops=%.6e bytes=%.6e",
+                 "tma_store=%d tma_mask=%d nsb=%d reverse=%d grid=%dx%d tf32=%d pair=%d pool=%d fp32x6=%d flops=%.6e bytes=%.6e",
                  li.rows, li.N, li.K, li.taps, li.groups, li.halo, li.BN, li.out_bytes, li.ws, li.stages, li.act, li.mul, li.aux,
-                 li.tma_store, li.tma_mask, li.nsb, li.reverse, li.ctas_x, li.slabs, li.tf32, li.pair, li.pool, li.flops, li.bytes);
+                 li.tma_store, li.tma_mask, li.nsb, li.reverse, li.ctas_x, li.slabs, li.tf32, li.pair, li.pool, li.fp32x6, li.flops, li.bytes);
     return g_line;
 }

@@ -55,6 +55,9 @@ struct TapGemmArgs {
     // optional fused BatchNorm batch statistics of a float32 output: stats_out[n] += sum Out[., ., n], stats_out[N + n] += sum
     // Out[., ., n]^2 over all rows, by atomicAdd into a zeroed [2][N] buffer; same contract for *stats_done
     float* stats_out; int* stats_done;
+    // set by the fp32-on-tensor-cores path only (gemm_tc.cuh, try_split_tapgemm): K is 6 x the layer's K, A holds the six
+    // bf16 operand parts per row, and the pack kernel writes the matching six parts of every fp32 weight row
+    int w_split;
 };
 
 struct WgradArgs {

@@ -38,7 +38,7 @@ struct CacheEntry {
 std::vector<CacheEntry> g_cache;
 thread_local bool g_cache_on = false;   // set per API call from the context (set_cache_mode)
 bool same_key(const PackArgs& a, const PackArgs& b) {
-    if (a.W != b.W || a.ntaps != b.ntaps || a.N != b.N || a.K != b.K || a.f32 != b.f32 || a.w_nstride != b.w_nstride ||
+    if (a.W != b.W || a.ntaps != b.ntaps || a.N != b.N || a.K != b.K || a.f32 != b.f32 || a.split != b.split || a.w_nstride != b.w_nstride ||
         a.w_kstride != b.w_kstride || a.n_perm_q != b.n_perm_q || a.n_perm_p != b.n_perm_p || a.k_perm_q != b.k_perm_q ||
         a.k_perm_p != b.k_perm_p)
         return false;
@@ -122,6 +122,28 @@ __nv_bfloat16* wgrad_cast_scratch(size_t elems, cudaStream_t st) {
         cap = elems;
     }
     return buf;
+}
+void* split_scratch(int kind, size_t bytes, cudaStream_t st) {
+    static std::vector<void*> kept;
+    static void* buf[3] = {nullptr, nullptr, nullptr};
+    static size_t cap[3] = {0, 0, 0};
+    if (kind < 0 || kind > 2) return nullptr;
+    if (bytes > cap[kind]) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cs != cudaStreamCaptureStatusNone) return nullptr;
+        void* nb = nullptr;
+        if (cudaMalloc(&nb, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (buf[kind]) kept.push_back(buf[kind]);
+        buf[kind] = nb;
+        cap[kind] = bytes;
+    }
+    return buf[kind];
+}
+bool fp32_tc_enabled() {
+    static const bool env_on = getenv("MELOGAN_FP32_TC") != nullptr && getenv("MELOGAN_FP32_TC")[0] == '1';
+    const int t = tuning().fp32_tc;
+    return t >= 0 ? t != 0 : env_on;
 }
 bool pair_enabled() {
     static const bool on = getenv("MELOGAN_DISABLE_PAIR") == nullptr;

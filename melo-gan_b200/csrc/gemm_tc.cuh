@@ -1372,18 +1372,60 @@ struct PackArgs {
     const float* W; int w_toff[kMaxTaps]; int w_nstride, w_kstride, n_perm_q, n_perm_p, k_perm_q, k_perm_p;
     int ntaps, N, K;
     void* out; int f32;          // packed [tap][n][k] as bf16, or as fp32 for the TF32 path
+    int split;                   // fp32 on the tensor cores: K = 6 x the layer's K, segment s of a row holds part kSplitW[s]
 };
+// ---- fp32 contractions on the bf16 tensor cores (MELOGAN_FP32_TC / mg_debug_set("fp32_tc")) ----
+// A float32 x is EXACTLY h + m + l with h = bf16(x), m = bf16(x - h), l = bf16(x - h - m) (8 + 8 + 8 significand bits, each
+// difference is exact in float32).  x * w = hh + hm + mh + hl + lh + mm + O(2^-26 |x w|): six bf16 products, each exact in
+// the fp32 accumulator.  The six terms are laid out along the reduction index -- row k-segments of A: h h m h l m, of W:
+// h m h l h m -- so that the UNCHANGED bf16 tap-GEMM kernels compute the float32 contraction with K' = 6 K; the weight
+// gradient stacks the same parts along the samples instead (its reduction runs over the rows).
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void split3(float x, float (&p)[3]) {
+    p[0] = bf16_round(x);
+    const float r = x - p[0];
+    p[1] = bf16_round(r);
+    p[2] = bf16_round(r - p[1]);
+}
+// Smallest terms first (mm, hl, lh, hm, mh, hh): tcgen05 adds into its fp32 accumulator with truncation, an error of up to one
+// ulp OF THE ACCUMULATOR per instruction -- while only small terms have been added the accumulator, and with it that error, is
+// 2^-8 of its final size.  (With several taps this holds for the first tap only)
+constexpr unsigned kSplitA = 0x010201u;   // part of segment s = (order >> 4 s) & 3:  m h l h m h
+constexpr unsigned kSplitW = 0x001021u;   //                                           m l h m h h
 static __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs P) {
     const long long total = (long long)P.ntaps * P.N * P.K;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int K0 = P.split ? P.K / 6 : P.K;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int k = (int)(i % P.K);
+        const int kk = (int)(i % P.K);
+        const int seg = kk / K0, k = kk - seg * K0;
         const long long tn = i / P.K;
         const int n = (int)(tn % P.N), t = (int)(tn / P.N);
-        const float w = __ldg(P.W + P.w_toff[t] + (long long)perm_index(n, P.n_perm_q, P.n_perm_p) * P.w_nstride +
-                              (long long)perm_index(k, P.k_perm_q, P.k_perm_p) * P.w_kstride);
+        float w = __ldg(P.W + P.w_toff[t] + (long long)perm_index(n, P.n_perm_q, P.n_perm_p) * P.w_nstride +
+                        (long long)perm_index(k, P.k_perm_q, P.k_perm_p) * P.w_kstride);
+        if (P.split) { float p[3]; split3(w, p); w = p[(kSplitW >> (4 * seg)) & 3u]; }
         if (P.f32) static_cast<float*>(P.out)[i] = w;
         else static_cast<__nv_bfloat16*>(P.out)[i] = __float2bfloat16_rn(w);
+    }
+}
+// y[(i / inner) * 6 * inner + s * inner + i % inner] = part order[s] of x[i]   (4 elements per thread; inner % 4 == 0).
+// inner = K: the six k-segments of every activation row (tap-GEMM); inner = n: six stacked copies of the tensor (wgrad).
+template <unsigned ORDER>
+static __global__ void __launch_bounds__(256) split3_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            long long n4, long long inner) {
+    for (long long i4 = (long long)blockIdx.x * 256 + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * 256) {
+        const float4 v = __ldg(x + i4);
+        float p[4][3];
+        split3(v.x, p[0]); split3(v.y, p[1]); split3(v.z, p[2]); split3(v.w, p[3]);
+        const long long i = i4 * 4, outer = i / inner, in = i - outer * inner;
+        __nv_bfloat16* row = y + outer * 6 * inner + in;
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            const int q = (int)((ORDER >> (4 * s)) & 3u);      // a compile-time constant once the loop is unrolled
+            const __nv_bfloat162 a = __floats2bfloat162_rn(p[0][q], p[1][q]), b = __floats2bfloat162_rn(p[2][q], p[3][q]);
+            *reinterpret_cast<uint2*>(row + s * inner) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        }
     }
 }
 
@@ -1427,6 +1469,10 @@ bool mask_tma_enabled();     // MELOGAN_DISABLE_TMA_MASK=1 keeps per-thread mask
 bool tma_store_enabled();    // MELOGAN_DISABLE_TMA_STORE=1 keeps the row-per-thread epilogue stores (A/B profiling)
 // 2-D view (k, rows) of a packed weight [rows][K]
 int make_weight_map(CUtensorMap* map, const void* base, int K, long long rows, int box_rows, int elem_bytes = 2);
+bool fp32_tc_enabled();      // tuning().fp32_tc, else MELOGAN_FP32_TC=1
+// grow-only device scratch of the fp32_tc path (0 = split activations, 1 = packed split weights, 2 = split gradients); like
+// wgrad_cast_scratch it never frees (captured graphs keep the addresses) and refuses to grow inside a stream capture
+void* split_scratch(int kind, size_t bytes, cudaStream_t st);
 bool tf32_enabled();         // set per API call from the context's precision (fp32 parity mode never uses TF32)
 void set_tf32(bool on);
 
@@ -1540,6 +1586,7 @@ struct Tuning {
     int no_pair = 0;         // 1 = never the CTA-pair (cta_group::2) kernel
     int no_rot = 0;          // 1 = every slab walks the row tiles in the same order
     int ring2_stages = 0;    // activation stages a second staging set must leave (0 = 4)
+    int fp32_tc = -1;        // float32 contractions as six bf16 tensor-core terms (-1 = MELOGAN_FP32_TC, default off)
     int no_fuse = 0;         // bits: 1 = no pooling, 2 = no column sums, 4 = no BatchNorm statistics in the epilogues (the callers
                              // then run their own passes)
 };
@@ -1550,6 +1597,7 @@ struct LaunchInfo {
     long long rows = 0;
     int N = 0, K = 0, taps = 0, groups = 0, halo = 0, BN = 0, out_bytes = 0, ws = 0, stages = 0, act = 0, mul = 0, aux = 0;
     int tma_store = 0, tma_mask = 0, nsb = 0, reverse = 0, ctas_x = 0, slabs = 0, tf32 = 0, splits = 0, pair = 0, pool = 0;
+    int fp32x6 = 0;          // the launch was the six-term bf16 form of a float32 contraction
     double flops = 0, bytes = 0;
 };
 LaunchInfo& last_launch();
@@ -1712,11 +1760,59 @@ int run_tc_tap(const CUtensorMap& am, const CUtensorMap& bm, TcTapArgs a, int BN
 // Try to run a tap-GEMM described in SIMT terms on the tensor cores.  Returns 1 if launched, 0 if the shape
 // does not qualify (caller falls back to the CUDA-core kernel), or a negative mg_status on error.
 template <typename TA, typename TO, typename TMSK>
+int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st);
+
+static inline int split_blocks(long long n4) {
+    const long long b = (n4 + 255) / 256, cap = (long long)num_sms() * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// float32 tap-GEMM on the bf16 tensor cores (see split3 above): the activation is re-written once as six bf16 k-segments
+// per row (12 bytes per element of scratch), the weights are packed as the matching six segments, and the bf16 kernels run
+// with K' = 6 K.  Exact to O(2^-24) per product plus the fp32 accumulation order of the tensor core.
+template <typename TO, typename TMSK>
+int try_split_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
+    const long long rows = (long long)P.B * P.Mper;
+    if (P.w_split || rows < 1024 || P.K % 64 || P.N % 64 || P.row_scale || P.ntaps < 1 || P.ntaps > kMaxTaps || !is_pow2(P.Mper) ||
+        (P.Mper > 128 && P.Mper % 128))
+        return 0;
+    if (P.Mper > 1 && P.a_mstride != P.K && P.a_mstride != 2 * P.K) return 0;
+    if (P.a_valid % P.K || P.a_bstride != P.a_valid || ((uintptr_t)P.A) % 16 || ((uintptr_t)P.Out) % 16) return 0;
+    if (P.o_off % 8 || P.o_mstride % 8 || P.o_bstride % 8) return 0;
+    for (int t = 0; t < P.ntaps; ++t)
+        if (P.a_toff[t] % P.K) return 0;
+    const long long nA = (long long)P.B * P.a_bstride;
+    if (nA * 6 >= (1LL << 40) || 6LL * P.a_bstride >= (1LL << 31) || 6LL * P.ntaps * P.N * P.K >= (1LL << 31)) return 0;
+    __nv_bfloat16* a6 = static_cast<__nv_bfloat16*>(split_scratch(0, (size_t)nA * 6 * sizeof(__nv_bfloat16), st));
+    if (!a6) return 0;
+    split3_kernel<kSplitA><<<split_blocks(nA / 4), 256, 0, st>>>(static_cast<const float4*>(P.A), a6, nA / 4, (long long)P.K);
+    MG_LAUNCH_OK();
+    TapGemmArgs Q = P;
+    Q.A = a6; Q.K = 6 * P.K; Q.w_split = 1;
+    Q.a_bstride = 6 * P.a_bstride; Q.a_mstride = 6 * P.a_mstride; Q.a_valid = 6 * P.a_valid;
+    for (int t = 0; t < P.ntaps; ++t) Q.a_toff[t] = 6 * P.a_toff[t];
+    // the fused reductions (pooling, column sums, BatchNorm statistics) are float32 atomics: the parity mode keeps the
+    // callers' deterministic passes (their *_done flags stay 0)
+    Q.pool_out = nullptr; Q.pool_done = nullptr; Q.pool_only = 0; Q.colsum_out = nullptr; Q.colsum_done = nullptr;
+    Q.stats_out = nullptr; Q.stats_done = nullptr;
+    const int rc = try_tc_tapgemm<__nv_bfloat16, TO, TMSK>(Q, st);
+    if (rc == 1) {
+        LaunchInfo& li = last_launch();
+        li.fp32x6 = 1; li.K = P.K;
+        li.flops /= 6.0;                      // the layer's float32 FLOPs, not the bf16 ones issued
+    }
+    return rc;
+}
+
+template <typename TA, typename TO, typename TMSK>
 int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     constexpr bool TF32 = std::is_same<TA, float>::value;
     constexpr int EB = TF32 ? 4 : 2, KT = TF32 ? 32 : 64;          // operand element bytes, elements per 128-byte k-block
     if (!enabled()) return 0;
-    if (TF32 && !(tf32_enabled() && P.Mper == 1 && P.ntaps == 1 && P.B >= 128)) return 0;   // the fp32 Linears of bf16 mode
+    if (TF32 && !(tf32_enabled() && P.Mper == 1 && P.ntaps == 1 && P.B >= 128)) {   // TF32: the fp32 Linears of bf16 mode only
+        if (fp32_tc_enabled() && !tf32_enabled()) return try_split_tapgemm<TO, TMSK>(P, st);
+        return 0;
+    }
     if (P.K % KT || P.N % 64 || P.row_scale || P.ntaps < 1 || P.ntaps > kMaxTaps) return 0;
     if (!is_pow2(P.Mper) || (P.Mper > 128 && P.Mper % 128)) return 0;
     int stride;
@@ -1756,8 +1852,13 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     for (int t = 0; t < P.ntaps; ++t) pk.w_toff[t] = P.w_toff[t];
     pk.W = P.W; pk.w_nstride = P.w_nstride; pk.w_kstride = P.w_kstride; pk.n_perm_q = P.n_perm_q; pk.n_perm_p = P.n_perm_p;
     pk.k_perm_q = P.k_perm_q; pk.k_perm_p = P.k_perm_p; pk.ntaps = P.ntaps; pk.N = P.N; pk.K = P.K; pk.f32 = TF32 ? 1 : 0;
+    pk.split = P.w_split;
     bool packed = false;
     __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(cache_lookup(pk, need * EB, &packed));
+    if (!wp && P.w_split) {                 // six-segment weights do not fit the ring slots a context sized for bf16 weights
+        wp = static_cast<__nv_bfloat16*>(split_scratch(1, need * EB, st));
+        if (!wp) return 0;
+    }
     if (!wp) {
         if (need * EB > sc.slot_elems * 2) return 0;
         wp = sc.slot[sc.next];
@@ -1827,8 +1928,48 @@ static __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* _
 __nv_bfloat16* wgrad_cast_scratch(size_t elems, cudaStream_t st);
 
 template <typename TG, typename TA>
+int try_tc_wgrad(const WgradArgs& P, cudaStream_t st);
+
+// float32 weight gradient on the bf16 tensor cores: the reduction runs over the rows, so the six part pairs are stacked along
+// the samples (G: h h m h l m, A: h m h l h m; six bf16 copies of each tensor in scratch) and tc_wgrad_kernel reduces over
+// 6 x the rows into the same fp32 gradient.
+static thread_local int t_wgrad_wave_mult = 1;   // set around the inner call of try_split_wgrad
+static inline int try_split_wgrad(const WgradArgs& P, cudaStream_t st) {
+    const long long nrows = (long long)P.row_end - P.row_begin;
+    if (P.row_begin != 0 || nrows < 1024 || nrows % P.Mper || P.K % 64 || P.N % 128 || P.g_off || P.ntaps < 1 || P.ntaps > kMaxTaps ||
+        !is_pow2(P.Mper) || (P.Mper > 64 && P.Mper % 64))
+        return 0;
+    if (P.Mper > 1 && (P.g_mstride != P.N || P.g_bstride != (long long)P.Mper * P.N)) return 0;
+    if (P.Mper == 1 && P.g_bstride != P.N) return 0;
+    if (P.Mper > 1 && P.a_mstride != P.K && P.a_mstride != 2 * P.K) return 0;
+    if (P.a_valid % P.K || P.a_bstride != P.a_valid || ((uintptr_t)P.A) % 16 || ((uintptr_t)P.G) % 16) return 0;
+    const long long nb = nrows / P.Mper, nG = nrows * P.N, nA = nb * P.a_bstride;
+    if (6 * nrows >= (1LL << 31)) return 0;
+    __nv_bfloat16* g6 = static_cast<__nv_bfloat16*>(split_scratch(2, (size_t)nG * 6 * sizeof(__nv_bfloat16), st));
+    __nv_bfloat16* a6 = static_cast<__nv_bfloat16*>(split_scratch(0, (size_t)nA * 6 * sizeof(__nv_bfloat16), st));
+    if (!g6 || !a6) return 0;
+    split3_kernel<kSplitA><<<split_blocks(nG / 4), 256, 0, st>>>(static_cast<const float4*>(P.G), g6, nG / 4, nG);
+    MG_LAUNCH_OK();
+    split3_kernel<kSplitW><<<split_blocks(nA / 4), 256, 0, st>>>(static_cast<const float4*>(P.A), a6, nA / 4, nA);
+    MG_LAUNCH_OK();
+    WgradArgs Q = P;
+    Q.G = g6; Q.A = a6; Q.B = (int)(6 * nb); Q.row_end = (int)(6 * nrows);
+    // six times the rows: six times the splits, so that one CTA's TMEM accumulation chain (whose truncation error grows with its
+    // length) is as long as in bf16 mode and mostly covers ONE part pair; the partial sums meet in fp32 atomics
+    t_wgrad_wave_mult = 6;
+    const int rc = try_tc_wgrad<__nv_bfloat16, __nv_bfloat16>(Q, st);
+    t_wgrad_wave_mult = 1;
+    if (rc == 1) {
+        LaunchInfo& li = last_launch();
+        li.fp32x6 = 1; li.rows = nrows; li.flops /= 6.0;
+    }
+    return rc;
+}
+
+template <typename TG, typename TA>
 int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
     if (std::is_same<TG, float>::value && std::is_same<TA, float>::value) {
+        if (enabled() && fp32_tc_enabled() && !tf32_enabled()) return try_split_wgrad(P, st);
         // bf16 mode: the weight gradients of the float32 Linears (critic fc.1, the generator's / encoder's MLPs) ran on the CUDA
         // cores (critic fc.1: 122 us for 3.2 GFLOP).  Their forward and dgrad already read the operands as TF32 (10 mantissa
         // bits); here both operands are rounded to bf16 copies (8 bits, like every conv's weight gradient) and the reduction over
@@ -1888,7 +2029,7 @@ int try_tc_wgrad(const WgradArgs& P, cudaStream_t st) {
     const size_t smem_cta = (BNK == 128 ? sizeof(WgradSmem<128>) : sizeof(WgradSmem<64>)) + 1024;
     const long long cap = (long long)num_sms() * (long long)((227 * 1024) / smem_cta);
     static const int waves = getenv("MELOGAN_WGRAD_WAVES") ? atoi(getenv("MELOGAN_WGRAD_WAVES")) : 1;
-    long long want = cap * (waves > 0 ? waves : 1) / tiles;
+    long long want = cap * (waves > 0 ? waves : 1) * t_wgrad_wave_mult / tiles;
     long long maxs = (nrows + 255) / 256;                    // at least 4 chunks per CTA
     long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
     if (splits > 65535) splits = 65535;

@@ -103,11 +103,30 @@ def cycle_layers(B):
     return S
 
 
+_FULL_FP32 = False      # Layer(spec with full_fp32=True): operands keep all 24 significand bits (the fp32_tc path)
+
+
 def _grid(shape, gen, dev, scale=1.0, bf16=True):
     """Random values that are exactly representable in bf16 (so that bf16 / TF32 operand rounding is the identity)."""
     x = torch.randn(shape, generator=gen, device=dev) * scale
+    if _FULL_FP32:
+        assert not bf16
+        return x
     x = x.to(torch.bfloat16)
     return x if bf16 else x.float()
+
+
+def fp32_layers(B):
+    """The same contractions as cycle_layers(B) in float32 storage with full-precision operands: what the fp32 parity mode
+    launches, for the six-term bf16 tensor-core form (mg_debug_set("fp32_tc", 1), csrc/gemm_tc.cuh try_split_*)."""
+    out = []
+    for s in cycle_layers(B):
+        if s["tf32"] and s["name"] not in ("D.fc.fwd.tf32", "D.fc.dgrad.tf32", "D.fc.wgrad.f32"):
+            continue
+        d = dict(s)
+        d.update(in_bf16=0, out_bf16=0, mask_bf16=0, tf32=0, full_fp32=True, name=s["name"].replace(".tf32", "").replace(".f32", "") + ".fp32")
+        out.append(d)
+    return out
 
 
 class Layer:
@@ -115,6 +134,14 @@ class Layer:
 
     def __init__(self, spec, seed=0, dev="cuda"):
         self.s = s = dict(spec)
+        global _FULL_FP32
+        _FULL_FP32 = bool(s.get("full_fp32"))
+        try:
+            self._build(s, seed, dev)
+        finally:
+            _FULL_FP32 = False
+
+    def _build(self, s, seed, dev):
         g = torch.Generator(device=dev).manual_seed(seed)
         op, R, Cin, Cout = s["op"], s["R"], s["Cin"], s["Cout"]
         Lin = s.get("Lin", 1)
@@ -171,7 +198,7 @@ class Layer:
                 self.aux = torch.empty(oshape, dtype=odt, device=dev)
             if s["mul"] != MUL_NONE:
                 mdt = torch.bfloat16 if s["mask_bf16"] else torch.float32
-                self.mask = _grid(oshape, g, dev, bf16=True).to(mdt)
+                self.mask = _grid(oshape, g, dev, bf16=not _FULL_FP32).to(mdt)
                 if s["inplace_mask"]:          # the adjoint chain overwrites the saved activation it masks with
                     self.out = self.mask.clone().to(odt)
                     self.mask0 = self.mask
