@@ -79,10 +79,21 @@ LaunchInfo& last_launch() { return g_last_launch; }
 
 int ensure_scratch(size_t elems) {
     if (elems <= g_scratch.slot_elems) return MG_OK;
+    // Grow by allocating NEW slots; the old ones stay alive until the process ends: CUDA graphs captured by an earlier, smaller
+    // context (GanTrainer.capture_cycle) have the old slot addresses baked in and keep replaying on them.
+    static std::vector<__nv_bfloat16*> retired;
+    __nv_bfloat16* fresh[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < 4; ++i) {
-        if (g_scratch.slot[i]) MG_CUDA_OK(cudaFree(g_scratch.slot[i]));
-        g_scratch.slot[i] = nullptr;
-        MG_CUDA_OK(cudaMalloc(&g_scratch.slot[i], elems * sizeof(__nv_bfloat16)));
+        if (cudaMalloc(&fresh[i], elems * sizeof(__nv_bfloat16)) != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < i; ++j) cudaFree(fresh[j]);
+            set_error("packed-weight scratch: cudaMalloc of %zu bytes failed", elems * sizeof(__nv_bfloat16));
+            return MG_ERR_CUDA;
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (g_scratch.slot[i]) retired.push_back(g_scratch.slot[i]);
+        g_scratch.slot[i] = fresh[i];
     }
     g_scratch.slot_elems = elems;
     return MG_OK;

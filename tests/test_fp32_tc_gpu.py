@@ -114,7 +114,9 @@ def test_fp32_step_on_tensor_cores_stays_close_to_cuda_core_step(which):
     from gan_testlib import rel_l2
     m0, g0 = _step(160, which, False)
     m1, g1 = _step(160, which, True)
-    errs = {k: rel_l2(g1[k], g0[k]) for k in g0}
+    # (the biases in front of a train-mode BatchNorm have a true gradient of zero: both paths return cancellation noise there)
+    noise = ("decoder.deconv.0.bias", "decoder.deconv.3.bias")
+    errs = {k: rel_l2(g1[k], g0[k]) for k in g0 if k not in noise}
     rec = {"step": which, "B": 160, "losses_cuda_core": m0.tolist(), "losses_tc": m1.tolist(),
            "worst_grad": max(errs, key=errs.get), "worst_grad_rel_l2": max(errs.values()),
            "median_grad_rel_l2": sorted(errs.values())[len(errs) // 2]}
@@ -123,5 +125,5 @@ def test_fp32_step_on_tensor_cores_stays_close_to_cuda_core_step(which):
         with open("gpurun_out/fp32_tc_layers.jsonl", "a") as f:
             f.write(json.dumps(rec) + "\n")
     assert torch.allclose(m1, m0, rtol=2e-5, atol=1e-6), (m1, m0)
-    for k in g0:
+    for k in errs:
         assert_close_l2(g1[k], g0[k], 5e-3, f"{which}: grad {k}")
