@@ -430,6 +430,19 @@ def fp32_tc_record(cfg, ed_cfg, dev, B=2048, cycles=3):
     a, b = rec["tensor_cores_bf16x6"]["first_cycle_loss_sums"], rec["cuda_cores"]["first_cycle_loss_sums"]
     rec["max_rel_diff_of_losses"] = max(abs(x - y) / max(abs(y), 1e-3) for x, y in zip(a, b))
     rec["speedup"] = rec["cuda_cores"]["ms_per_cycle"] / rec["tensor_cores_bf16x6"]["ms_per_cycle"]
+    # whole-cycle float32 FLOP rate against the effective peak of the six-term form: one float32 product costs six bf16 products
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf = float(json.load(f).get("bf16_tflops_sustained", 1400.0))
+    except Exception:
+        peak_tf = 1400.0
+    for k in ("cuda_cores", "tensor_cores_bf16x6"):
+        rec[k]["whole_cycle_fp32_tflops"] = rec[k]["rolls_per_s"] * MFLOP_PER_ROLL * 1e6 / 1e12
+    rec["effective_fp32_peak_tflops"] = peak_tf / 6.0
+    rec["frac_of_effective_peak"] = rec["tensor_cores_bf16x6"]["whole_cycle_fp32_tflops"] / (peak_tf / 6.0)
+    rec["note"] = ("opt-in (MELOGAN_FP32_TC=1): operands split exactly into three bf16 parts, six part products per float32 product on "
+                   "the bf16 tcgen05 kernels; effective peak = measured sustained bf16 peak / 6; the whole-cycle rate includes the "
+                   "operand-split passes, the 4-channel layers, element-wise kernels and Adam (DESIGN.md 5)")
     return rec
 
 
