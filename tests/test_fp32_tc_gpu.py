@@ -8,7 +8,8 @@ split is exact and the dropped part products are O(2^-26); what remains is the t
 into the fp32 TMEM accumulator with truncation, up to one ulp of the accumulator per instruction and always towards zero,
 so the error grows linearly with the number n of instructions issued on a full-size accumulator (measured: ~0.5 ulp each)
 where the CUDA cores' round-to-nearest FFMA chain grows like sqrt(n).  Bar per layer: max(1e-5 of the tensor's scale,
-1.25 n 2^-24) with n = 6 x taps x K / 16; weight gradients 1e-4 (as for bf16 mode).  Then the whole critic and generator
+n 2^-23) with n = 6 x taps x K / 16 (the worst case of that model; measured: at most half of it); weight gradients 1e-4 (as
+for bf16 mode).  Then the whole critic and generator
 steps of the fp32 parity mode with the switch on against the switch off: losses to 2e-5, gradients to 5e-3 -- measured up to
 1.3e-3 on the generator's first layer, where BatchNorm backward's cancellations amplify the per-layer bias; that is why the
 switch is opt-in and the default fp32 parity mode (5e-5 on gradients against the oracle) stays on the CUDA cores."""
@@ -76,7 +77,7 @@ def test_fp32_layer_on_tensor_cores_matches_float64(spec):
                 else:
                     taps = {0: s["ks"], 1: s["ks"], 2: 3}.get(s["op"], 1)       # op 2: up to 3 taps per sub-pixel phase
                     kred = s["Cout"] if s["op"] in (1, 4) else s["Cin"]
-                    tol = max(F32_TOL, 1.25 * (6 * taps * kred / 16) * 2.0 ** -24)
+                    tol = max(F32_TOL, (6 * taps * kred / 16) * 2.0 ** -23)      # one ulp per instruction: the worst case
                 assert err <= tol, f"{s['name']}: rel err {err:.3e} > {tol:.1e} ({info})"
     finally:
         TL.debug_set("reset", 0)
