@@ -289,6 +289,8 @@ struct TcTapArgs {
     const float* bias; const float* col_scale; int act;
     const void* mul_src; int mul_mode; void* aux;
     float alpha; int accumulate;
+    int kb_outer;                       // one-tile kernel: walk k-blocks outermost, taps innermost (fp32_tc: the five small-term
+                                        // segments of ALL taps before the full-size one, see kSplitA)
     int tma_mask;                       // ... and the mask tile (f' of the saved activation) arrives by TMA as well
     int tma_store;                      // weight-stationary kernel: tiles leave through shared memory + TMA bulk stores
     int nsb;                            // ... through a ring of nsb (1 or 2) staging tiles: the bulk store of one tile drains
@@ -815,7 +817,7 @@ __global__ void __launch_bounds__(192) tc_tapgemm_kernel(const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages, it = kb / kStages;
                 mbar_wait(&S.empty[s], (it & 1) ^ 1);
-                const int t = kb / P.kblocks, kc = kb - t * P.kblocks;
+                const int t = P.kb_outer ? kb % P.ntaps : kb / P.kblocks, kc = P.kb_outer ? kb / P.ntaps : kb - t * P.kblocks;
                 mbar_expect_tx(&S.full[s], kStageBytes);
                 tma_load_4d(&a_map, &S.full[s], S.a[s], kc * P.ktile, P.a_p[t], m0 + P.a_dm[t], b0);
                 tma_load_2d(&b_map, &S.full[s], S.b[s], kc * P.ktile, P.b_row[t] + n0);
@@ -1389,7 +1391,8 @@ __device__ __forceinline__ void split3(float x, float (&p)[3]) {
 }
 // Smallest terms first (mm, hl, lh, hm, mh, hh): tcgen05 adds into its fp32 accumulator with truncation, an error of up to one
 // ulp OF THE ACCUMULATOR per instruction -- while only small terms have been added the accumulator, and with it that error, is
-// 2^-8 of its final size.  (With several taps this holds for the first tap only)
+// 2^-8 of its final size.  The one-tile kernel therefore walks the k-blocks outermost (TcTapArgs::kb_outer): the small-term
+// segments of every tap come before the first full-size product; see DESIGN.md 5.
 constexpr unsigned kSplitA = 0x010201u;   // part of segment s = (order >> 4 s) & 3:  m h l h m h
 constexpr unsigned kSplitW = 0x001021u;   //                                           m l h m h h
 static __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs P) {
@@ -1839,6 +1842,7 @@ int try_tc_tapgemm(const TapGemmArgs& P, cudaStream_t st) {
     a.Out = P.Out; a.o_bstride = P.o_bstride; a.o_mstride = P.o_mstride; a.o_off = P.o_off;
     a.bias = P.bias; a.col_scale = P.col_scale; a.act = P.act; a.mul_src = P.mul_src; a.mul_mode = P.mul_mode;
     a.aux = P.aux; a.alpha = P.alpha; a.accumulate = P.accumulate;
+    a.kb_outer = P.w_split;
     a.n_perm_q = P.n_perm_q; a.n_perm_p = P.n_perm_p;
     a.pool_out = P.pool_out; a.pool_scale = P.pool_scale; a.pool_done = P.pool_done; a.skip_out = 0;
     a.colsum_out = P.colsum_out; a.colsum_tiles = (int)(P.colsum_rows / 128); a.colsum_done = P.colsum_done;

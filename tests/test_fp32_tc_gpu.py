@@ -5,14 +5,15 @@ tcgen05 kernels bf16 mode uses).  Opt-in: mg_debug_set("fp32_tc", 1) or MELOGAN_
 Every layer of the training cycle in float32 storage with FULL-precision random operands against the float64 contraction,
 the CUDA-core result of the same launch measured beside it (both land in gpurun_out/fp32_tc_layers.jsonl).  The operand
 split is exact and the dropped part products are O(2^-26); what remains is the tensor core's own accumulation: tcgen05 adds
-into the fp32 TMEM accumulator with truncation, up to one ulp of the accumulator per instruction and always towards zero,
-so the error grows linearly with the number n of instructions issued on a full-size accumulator (measured: ~0.5 ulp each)
-where the CUDA cores' round-to-nearest FFMA chain grows like sqrt(n).  Bar per layer: max(1e-5 of the tensor's scale,
-n 2^-23) with n = 6 x taps x K / 16 (the worst case of that model; measured: at most half of it); weight gradients 1e-4 (as
-for bf16 mode).  Then the whole critic and generator
-steps of the fp32 parity mode with the switch on against the switch off: losses to 2e-5, gradients to 5e-3 -- measured up to
-1.3e-3 on the generator's first layer, where BatchNorm backward's cancellations amplify the per-layer bias; that is why the
-switch is opt-in and the default fp32 parity mode (5e-5 on gradients against the oracle) stays on the CUDA cores."""
+into the fp32 TMEM accumulator with truncation, up to one ulp OF THE ACCUMULATOR per instruction and always towards zero
+(measured ~0.5 ulp each), where the CUDA cores' FFMA chain rounds to nearest.  The kernels therefore issue the five small-
+term segments of all taps first, while the accumulator is 2^-8 of its final size, and the full-size hh segment last; the
+error is then that of the hh chain alone (taps x K / 16 instructions).  Bar per layer: max(1e-5 of the tensor's scale,
+n 2^-23) with n = 6 x taps x K / 16 (the worst case had ALL six segments run on a full-size accumulator; measured:
+3e-7..2.7e-6, at or below the CUDA-core kernels, 1.9e-5 for the K = 16384 reduction of pre.2's dgrad); weight gradients
+1e-4 (as for bf16 mode; measured <= 9e-6).  Then the whole critic and generator steps of the fp32 parity mode with the
+switch on against the switch off: losses to 2e-5, gradients to 5e-3 (measured: critic step 4.5e-5 worst, generator step
+5e-4 on its first layer, where BatchNorm backward's cancellations amplify the residual bias of the hh chains)."""
 import json
 import os
 
