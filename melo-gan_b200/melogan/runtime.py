@@ -27,6 +27,18 @@ def set_precision(p):
     PRECISION = p
 
 
+def set_fp32_tensor_cores(on):
+    """fp32 mode's contractions as six bf16 tensor-core terms per float32 product (operands split exactly into three bf16
+    parts) instead of CUDA-core FFMA.  True / False, or None to follow MELOGAN_FP32_TC (default: off).
+    Process-wide, like the kernel-selection switches of mg_debug_set."""
+    import ctypes
+    from . import _native
+    lib = _native.lib()
+    lib.mg_debug_set.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.mg_debug_set.restype = ctypes.c_int
+    _native.check(lib.mg_debug_set(b"fp32_tc", -1 if on is None else (1 if on else 0)))
+
+
 def engine_for(device, batch, **shape):
     if torch.device(device).type != "cuda":
         raise RuntimeError("melogan_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback. "

@@ -46,3 +46,16 @@ def test_scale_mask_matches_reference_tables():
                 want |= 1 << ((i + root) % 12)
             assert scale_mask(name, root) == want
     assert scale_mask("no_such_scale", 3) == 0xFFF
+
+
+def test_kernel_selection_switches_are_host_state():
+    """mg_debug_set only records a choice (no device needed): known keys succeed, unknown keys fail loudly; the fp32-on-
+    tensor-cores switch is reachable from the Python runtime."""
+    from melogan import runtime
+    L = _native.lib()
+    L.mg_debug_set.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.mg_debug_set.restype = ctypes.c_int
+    for on in (True, False, None):
+        runtime.set_fp32_tensor_cores(on)
+    assert L.mg_debug_set(b"no_such_switch", 1) == _native.MG_ERR_INVALID and b"unknown key" in L.mg_last_error()
+    assert L.mg_debug_set(b"reset", 0) == 0
