@@ -1937,7 +1937,8 @@ int try_tc_wgrad(const WgradArgs& P, cudaStream_t st);
 // float32 weight gradient on the bf16 tensor cores: the reduction runs over the rows, so the six part pairs are stacked along
 // the samples (G: h h m h l m, A: h m h l h m; six bf16 copies of each tensor in scratch) and tc_wgrad_kernel reduces over
 // 6 x the rows into the same fp32 gradient.
-static thread_local int t_wgrad_wave_mult = 1;   // set around the inner call of try_split_wgrad
+inline thread_local int t_wgrad_wave_mult = 1;   // set around the inner call of try_split_wgrad (ONE variable for all
+                                                 // translation units: the templates that read it are merged by the linker)
 static inline int try_split_wgrad(const WgradArgs& P, cudaStream_t st) {
     const long long nrows = (long long)P.row_end - P.row_begin;
     if (P.row_begin != 0 || nrows < 1024 || nrows % P.Mper || P.K % 64 || P.N % 128 || P.g_off || P.ntaps < 1 || P.ntaps > kMaxTaps ||
